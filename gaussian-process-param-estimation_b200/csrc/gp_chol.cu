@@ -1,0 +1,357 @@
+// Blocked FP64 Cholesky, triangular solves, inverse and log-determinant on the padded matrix K + eta*I.
+// Replaces what the reference obtains from scipy.linalg.solve(assume_a='pos') (LAPACK dposv, one fresh O(n^3)
+// factorisation per call: gaussian_proc/_mixed_correlation/mixed_correlation.py:280-299, _linear_solver.py:71)
+// and from imate's 'cholesky' logdet / traceinv (mixed_correlation.py:183-191,250-261).
+//
+// potrf : right-looking, two-level blocking (outer panel 512, inner 128). The 128x128 diagonal block is factored
+//         AND inverted by one CTA in shared memory; the panel solve is a GEMM with that inverse and all trailing
+//         updates are DMMA GEMMs (gp_gemm.cu), lower tiles only.
+// potrs : block forward/back substitution that reuses the inverted diagonal blocks.
+// potri : W = inv(L) by recursive halving (two triangular GEMMs per level), then inv(A) = W^T W (one TN GEMM).
+#include "../../include/gpgp.h"
+#include "gp_common.cuh"
+#include "gp_internal.h"
+
+namespace gp {
+
+constexpr int DB = 128;         // diagonal block
+constexpr int DPITCH = DB + 1;  // shared pitch (odd -> conflict-free column walks)
+constexpr int DIAG_THREADS = 512;
+constexpr int OUTER_NB = 512;
+
+// Factor the 128x128 diagonal block at `Ajj` (lower, in place) and write inv(L_jj) (lower, zero above) to `Linv`.
+// Shared array S[128][129]: lower triangle holds A/L, W[i][c] (c <= i) lives at S[c][i+1] (strict upper).
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0, int nvalid) {
+    extern __shared__ double S[];
+    __shared__ int bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = DIAG_THREADS / 32;
+    if (tid == 0) bad = 0;
+    for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
+        int i = idx >> 7, k = idx & 127;
+        if (k <= i) S[i * DPITCH + k] = Ajj[(int64_t)i * lda + k];
+        else S[i * DPITCH + k + 0] = 0.0;  // W region (shifted by one column below) starts at zero
+    }
+    if (tid < DB) S[tid * DPITCH + DB] = 0.0;
+    __syncthreads();
+
+    for (int j = 0; j < DB; ++j) {
+        double ajj = S[j * DPITCH + j];
+        if (!(ajj > 0.0)) {  // also catches NaN
+            if (tid == 0 && !bad) { bad = 1; if (j0 + j < nvalid) atomicCAS(info, 0, j0 + j + 1); }
+        }
+        double d = sqrt(ajj), inv = 1.0 / d;
+        __syncthreads();  // everyone has read the pivot
+        // phase A: scale column j of L (rows > j), row j of W (cols < j); set L_jj, W_jj
+        for (int i = j + 1 + tid; i < DB; i += DIAG_THREADS) S[i * DPITCH + j] *= inv;
+        for (int c = tid; c < j; c += DIAG_THREADS) S[c * DPITCH + j + 1] *= inv;
+        if (tid == 0) { S[j * DPITCH + j] = d; S[j * DPITCH + j + 1] = inv; }
+        __syncthreads();
+        // phase B: rank-1 updates of the trailing A (cols j+1..i) and of W rows i > j (cols 0..j)
+        for (int i = j + 1 + warp; i < DB; i += NW) {
+            double lij = S[i * DPITCH + j];
+            for (int k = j + 1 + lane; k <= i; k += 32) S[i * DPITCH + k] -= lij * S[k * DPITCH + j];
+            for (int c = lane; c <= j; c += 32) S[c * DPITCH + i + 1] -= lij * S[c * DPITCH + j + 1];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
+        int i = idx >> 7, k = idx & 127;
+        if (k <= i) {
+            Ajj[(int64_t)i * lda + k] = S[i * DPITCH + k];
+            Linv[i * DB + k] = S[k * DPITCH + i + 1];
+        } else {
+            Linv[i * DB + k] = 0.0;
+        }
+    }
+}
+
+__global__ void logdet_kernel(const double* L, int n, int64_t ld, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(L[(int64_t)i * ld + i]);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *out = 2.0 * s;
+}
+
+__global__ void shift_copy_kernel(const double* __restrict__ K, int n, int npad, double eta, double* __restrict__ A) {
+    // lower tiles only (the factorisation never references the strict upper triangle)
+    int tm = blockIdx.y, tn = blockIdx.x;
+    if (tn > tm) return;
+    int r0 = tm * 128, c0 = tn * 128;
+    for (int idx = threadIdx.x; idx < 128 * 64; idx += blockDim.x) {
+        int r = idx >> 6, c2 = (idx & 63) * 2;
+        int64_t o = (int64_t)(r0 + r) * npad + c0 + c2;
+        double2 v = *reinterpret_cast<const double2*>(K + o);
+        int gi = r0 + r, gj = c0 + c2;
+        if (gi < n) {
+            if (gi == gj) v.x += eta;
+            if (gi == gj + 1) v.y += eta;
+        }
+        *reinterpret_cast<double2*>(A + o) = v;
+    }
+}
+
+// ---- substitution kernels -------------------------------------------------------------------------------
+
+constexpr int MAX_RHS = 16;
+
+// y = op(Linv_j) * b_j for one 128-row block (in place in B). TRANS: use Linv^T.
+// Linv is row-major [i][k]: the plain product walks rows with a warp (coalesced), the transposed one assigns a
+// thread per output row so that consecutive threads read consecutive columns.
+template <bool TRANS>
+__global__ void __launch_bounds__(256)
+diag_apply_kernel(const double* __restrict__ Linv, double* Bj, int nrhs, int64_t ldb) {
+    __shared__ double bs[DB * MAX_RHS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < DB * nrhs; idx += 256) bs[idx] = Bj[(int64_t)(idx / nrhs) * ldb + idx % nrhs];
+    __syncthreads();
+    if (!TRANS) {
+        for (int i = warp; i < DB; i += 8) {
+            double l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { int k = lane + 32 * q; l[q] = (k <= i) ? Linv[i * DB + k] : 0.0; }
+            for (int c = 0; c < nrhs; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s += l[q] * bs[(lane + 32 * q) * nrhs + c];
+                s = warp_sum(s);
+                if (lane == 0) Bj[(int64_t)i * ldb + c] = s;
+            }
+        }
+    } else {
+        // two threads per output row split the k range
+        int i = tid & 127, half = tid >> 7;
+        __shared__ double part[DB * MAX_RHS];
+        int kb = half ? (i + DB) / 2 + 1 : i, ke = half ? DB : (i + DB) / 2 + 1;
+        for (int c = 0; c < nrhs; ++c) {
+            double s = 0.0;
+            for (int k = kb; k < ke; ++k) s += Linv[k * DB + i] * bs[k * nrhs + c];
+            if (half) part[i * nrhs + c] = s;
+            __syncthreads();
+            if (!half) Bj[(int64_t)i * ldb + c] = s + part[i * nrhs + c];
+            __syncthreads();
+        }
+    }
+}
+
+// forward: B[r] -= L[r, j:j+128] * Y_j   for rows r in [row0, npad); one warp per row, 8 rows per CTA
+template <int NR>
+__global__ void __launch_bounds__(256)
+fwd_update_kernel(const double* __restrict__ L, int64_t ldl, int row0, int j0, const double* Yj, double* B, int64_t ldb,
+                  int nrows, int nrhs) {
+    __shared__ double ys[DB * NR];
+    for (int idx = threadIdx.x; idx < DB * NR; idx += 256) {
+        int k = idx / NR, c = idx - k * NR;
+        ys[idx] = (c < nrhs) ? Yj[(int64_t)k * ldb + c] : 0.0;
+    }
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = blockIdx.x * 8 + warp; r < nrows; r += gridDim.x * 8) {
+        const double* lrow = L + (int64_t)(row0 + r) * ldl + j0;
+        double acc[NR];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int k = lane + 32 * q;
+            double l = lrow[k];
+#pragma unroll
+            for (int c = 0; c < NR; ++c) acc[c] += l * ys[k * NR + c];
+        }
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[c] = warp_sum(acc[c]);
+        if (lane == 0) {
+            double* b = B + (int64_t)(row0 + r) * ldb;
+            for (int c = 0; c < nrhs; ++c) b[c] -= acc[c];
+        }
+    }
+}
+
+// backward: Y[c] -= sum_r L[j0 + r][c] * Z_j[r]   for c in [0, j0); thread per column c
+template <int NR>
+__global__ void __launch_bounds__(256)
+bwd_update_kernel(const double* __restrict__ L, int64_t ldl, int j0, const double* Zj, double* Y, int64_t ldb, int nrhs) {
+    __shared__ double zs[DB * NR];
+    for (int idx = threadIdx.x; idx < DB * NR; idx += 256) {
+        int k = idx / NR, c = idx - k * NR;
+        zs[idx] = (c < nrhs) ? Zj[(int64_t)k * ldb + c] : 0.0;
+    }
+    __syncthreads();
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= j0) return;
+    double acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+    const double* lp = L + (int64_t)j0 * ldl + c;
+#pragma unroll 4
+    for (int r = 0; r < DB; ++r) {
+        double l = lp[(int64_t)r * ldl];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[q] += l * zs[r * NR + q];
+    }
+    double* y = Y + (int64_t)c * ldb;
+    for (int q = 0; q < nrhs; ++q) y[q] -= acc[q];
+}
+
+__global__ void place_diag_inverse_kernel(const double* __restrict__ Linv, double* W, int64_t ldw) {
+    int b = blockIdx.x;
+    const double* src = Linv + (int64_t)b * DB * DB;
+    double* dst = W + (int64_t)b * DB * ldw + b * DB;
+    for (int idx = threadIdx.x; idx < DB * DB; idx += blockDim.x) dst[(int64_t)(idx >> 7) * ldw + (idx & 127)] = src[idx];
+}
+
+// recursive inverse of the lower-triangular L over block range [lo, hi) (units of 128); T = scratch
+static int trtri_rec(const double* L, double* W, int64_t ld, int lo, int hi, double* T, cudaStream_t s) {
+    if (hi - lo <= 1) return 0;
+    int mid = lo + (hi - lo) / 2;  // first half has floor((hi-lo)/2) blocks
+    int rc = trtri_rec(L, W, ld, lo, mid, T, s);
+    if (rc) return rc;
+    rc = trtri_rec(L, W, ld, mid, hi, T, s);
+    if (rc) return rc;
+    int M = (hi - mid) * DB, N = (mid - lo) * DB;
+    // T (M x N) = L21 * W11      (W11 lower: k >= n0)
+    rc = launch_dgemm(0, 1, T, N, L + (int64_t)mid * DB * ld + (int64_t)lo * DB, ld,
+                      W + (int64_t)lo * DB * ld + (int64_t)lo * DB, ld, M, N, N, 1.0, 0.0, KR_B_LOWER, TM_ALL, s);
+    if (rc) return rc;
+    // W21 = -W22 * T             (W22 lower: k < m0 + 128)
+    rc = launch_dgemm(0, 1, W + (int64_t)mid * DB * ld + (int64_t)lo * DB, ld,
+                      W + (int64_t)mid * DB * ld + (int64_t)mid * DB, ld, T, N, M, N, M, -1.0, 0.0, KR_A_LOWER, TM_ALL, s);
+    return rc;
+}
+
+template <int NR>
+static void launch_fwd(const double* L, int64_t npad, int row0, int j0, const double* Yj, double* B, int64_t ldb, int nrows,
+                       int nrhs, cudaStream_t s) {
+    int grid = (nrows + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    fwd_update_kernel<NR><<<grid, 256, 0, s>>>(L, npad, row0, j0, Yj, B, ldb, nrows, nrhs);
+}
+template <int NR>
+static void launch_bwd(const double* L, int64_t npad, int j0, const double* Zj, double* Y, int64_t ldb, int nrhs, cudaStream_t s) {
+    bwd_update_kernel<NR><<<(j0 + 255) / 256, 256, 0, s>>>(L, npad, j0, Zj, Y, ldb, nrhs);
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" {
+
+int gp_shift_copy(const double* K, int64_t n, int64_t npad, double eta, double* A, void* stream) {
+    if (!K || !A || n <= 0 || npad != gp_padded_size(n)) return -1;
+    dim3 grid((unsigned)(npad / 128), (unsigned)(npad / 128));
+    shift_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(K, (int)n, (int)npad, eta, A);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t gp_potrf_workspace_bytes(int64_t npad) { return (npad / DB) * (int64_t)DB * DB * sizeof(double); }
+
+int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, void* stream) {
+    if (!A || !info_dev || !ws || npad <= 0 || (npad % DB) || npad > INT32_MAX || n > npad) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* linv = (double*)ws;
+    static bool configured = false;
+    const int diag_smem = DB * DPITCH * sizeof(double);
+    if (!configured) {
+        GP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+        configured = true;
+    }
+    GP_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+    const int N = (int)npad;
+    for (int J = 0; J < N; J += OUTER_NB) {
+        int Jend = (J + OUTER_NB < N) ? J + OUTER_NB : N;
+        for (int j = J; j < Jend; j += DB) {
+            double* Ajj = A + (int64_t)j * npad + j;
+            double* Lj = linv + (int64_t)(j / DB) * DB * DB;
+            chol_diag_block_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(Ajj, npad, Lj, info_dev, j, (int)n);
+            GP_LAUNCH_CHECK();
+            int below = N - (j + DB);
+            if (below <= 0) continue;
+            double* A21 = A + (int64_t)(j + DB) * npad + j;
+            // panel solve L21 = A21 * inv(L_jj)^T  (in place: each CTA reads exactly the tile it overwrites)
+            int rc = launch_dgemm(0, 0, A21, npad, A21, npad, Lj, DB, below, DB, DB, 1.0, 0.0, KR_FULL, TM_ALL, s);
+            if (rc) return rc;
+            int ncols = Jend - (j + DB);
+            if (ncols > 0) {
+                rc = launch_dgemm(0, 0, A + (int64_t)(j + DB) * npad + (j + DB), npad, A21, npad, A21, npad, below, ncols,
+                                  DB, -1.0, 1.0, KR_FULL, TM_LOWER, s);
+                if (rc) return rc;
+            }
+        }
+        int rows = N - Jend;
+        if (rows > 0) {
+            const double* P = A + (int64_t)Jend * npad + J;
+            int rc = launch_dgemm(0, 0, A + (int64_t)Jend * npad + Jend, npad, P, npad, P, npad, rows, rows, Jend - J, -1.0,
+                                  1.0, KR_FULL, TM_LOWER, s);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int gp_logdet_from_chol(const double* L, int64_t n, int64_t npad, double* out_dev, void* stream) {
+    if (!L || !out_dev || n <= 0 || n > npad) return -1;
+    logdet_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(L, (int)n, npad, out_dev);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+int gp_potrs_f64(const double* L, int64_t npad, const void* potrf_ws, double* B, int64_t nrhs, int64_t ldb, void* stream) {
+    if (!L || !potrf_ws || !B || nrhs <= 0 || nrhs > MAX_RHS || ldb < nrhs || (npad % DB)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const double* linv = (const double*)potrf_ws;
+    const int N = (int)npad, nb = N / DB, nr = (int)nrhs;
+    for (int b = 0; b < nb; ++b) {
+        int j = b * DB;
+        double* Bj = B + (int64_t)j * ldb;
+        diag_apply_kernel<false><<<1, 256, 0, s>>>(linv + (int64_t)b * DB * DB, Bj, nr, ldb);
+        int below = N - (j + DB);
+        if (below > 0) {
+            if (nr <= 8) launch_fwd<8>(L, npad, j + DB, j, Bj, B, ldb, below, nr, s);
+            else launch_fwd<16>(L, npad, j + DB, j, Bj, B, ldb, below, nr, s);
+        }
+    }
+    for (int b = nb - 1; b >= 0; --b) {
+        int j = b * DB;
+        double* Bj = B + (int64_t)j * ldb;
+        diag_apply_kernel<true><<<1, 256, 0, s>>>(linv + (int64_t)b * DB * DB, Bj, nr, ldb);
+        if (j > 0) {
+            if (nr <= 8) launch_bwd<8>(L, npad, j, Bj, B, ldb, nr, s);
+            else launch_bwd<16>(L, npad, j, Bj, B, ldb, nr, s);
+        }
+    }
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t gp_potri_workspace_bytes(int64_t npad) {
+    int64_t nb = npad / DB, h1 = nb / 2, h2 = nb - h1;
+    return h1 * h2 * (int64_t)DB * DB * sizeof(double) + 256;
+}
+
+int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws, void* ws, void* stream) {
+    if (!L || !W || !potrf_ws || !ws || (npad % DB)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    int nb = (int)(npad / DB);
+    place_diag_inverse_kernel<<<nb, 256, 0, s>>>((const double*)potrf_ws, W, npad);
+    GP_LAUNCH_CHECK();
+    return trtri_rec(L, W, npad, 0, nb, (double*)ws, s);
+}
+
+int gp_lauum_f64(const double* W, double* Ainv, int64_t npad, void* stream) {
+    if (!W || !Ainv || (npad % DB)) return -1;
+    // Ainv_lower[i][j] = sum_{k >= i} W[k][i] W[k][j]
+    return launch_dgemm(1, 1, Ainv, npad, W, npad, W, npad, (int)npad, (int)npad, (int)npad, 1.0, 0.0, KR_TN_LOWER, TM_LOWER,
+                        (cudaStream_t)stream);
+}
+
+int gp_potri_f64(double* A, double* W, int64_t npad, const void* potrf_ws, void* ws, void* stream) {
+    int rc = gp_trtri_f64(A, W, npad, potrf_ws, ws, stream);
+    if (rc) return rc;
+    return gp_lauum_f64(W, A, npad, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// Dense Matern correlation generator (and optional dK/drho) -- replaces
+// gaussian_proc/generate_correlation/_generate_dense_correlation.pyx:23-91 (OpenMP row loop over i, j >= i with
+// mirror store) by 128x128 output tiles: the two point tiles are staged in shared memory, lower tiles are
+// evaluated once and stored twice (direct rows as 32-byte per-thread segments, the mirror through a padded
+// shared-memory transpose so both stores are fully coalesced). HBM-write bound: 8 n^2 bytes (16 n^2 with dK).
+#include "../../include/gpgp.h"
+#include "gp_common.cuh"
+#include "gp_matern.cuh"
+
+namespace gp {
+
+constexpr int MT = 128;          // tile edge
+constexpr int MAXD = 8;          // max spatial dimension staged in shared memory
+constexpr int CH = 32;           // rows per transpose chunk
+constexpr int PITCH = MT + 1;    // padded pitch of the transpose buffer (doubles)
+
+template <int MODE, bool WITH_DK>
+__global__ void __launch_bounds__(256)
+matern_dense_kernel(const double* __restrict__ pts, int n, int d, int npad, double* __restrict__ K,
+                    double* __restrict__ dK, MaternParams mp) {
+    extern __shared__ double dyn_smem[];
+    double (*pr)[MT] = reinterpret_cast<double (*)[MT]>(dyn_smem);           // row points, coordinate-major [d][MT]
+    double (*pc)[MT] = reinterpret_cast<double (*)[MT]>(dyn_smem + d * MT);  // column points [d][MT]
+    double* tbuf = dyn_smem + 2 * d * MT;                                     // [(1|2)][CH][PITCH]
+    __shared__ double isc[MAXD];
+
+    // lower-triangular tile enumeration
+    int b = blockIdx.x;
+    int tm = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= b) ++tm;
+    while (tm * (tm + 1) / 2 > b) --tm;
+    int tn = b - tm * (tm + 1) / 2;
+    const int m0 = tm * MT, n0 = tn * MT;
+    const int tid = threadIdx.x;
+
+    if (tid < d) isc[tid] = mp.inv_scale[tid];
+    for (int idx = tid; idx < MT * d; idx += 256) {
+        int r = idx / d, k = idx - r * d;
+        int gr = m0 + r, gc = n0 + r;
+        pr[k][r] = (gr < n) ? pts[(int64_t)gr * d + k] : 0.0;
+        pc[k][r] = (gc < n) ? pts[(int64_t)gc * d + k] : 0.0;
+    }
+    __syncthreads();
+
+    const int tx = tid & 31, ty = tid >> 5;  // tx: 4 consecutive columns; ty: rows ty + 8*rr
+    double cx[MAXD][4];
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k)
+        if (k < d)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cx[k][e] = pc[k][tx * 4 + e];
+
+    for (int chunk = 0; chunk < MT / CH; ++chunk) {
+        double v[4][4], dv[4][4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            int r = chunk * CH + ty + 8 * rr;
+            int gi = m0 + r;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int gj = n0 + tx * 4 + e;
+                double val, dval = 0.0;
+                if (gi >= n || gj >= n) {
+                    val = (gi == gj) ? 1.0 : 0.0;
+                } else if (gi == gj) {
+                    val = 1.0;
+                } else {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < MAXD; ++k)
+                        if (k < d) {
+                            double t = (pr[k][r] - cx[k][e]) * isc[k];
+                            s += t * t;
+                        }
+                    double x = sqrt(s);
+                    if (WITH_DK) matern_value_drho<MODE>(x, mp, &val, &dval);
+                    else val = matern_value<MODE>(x, mp);
+                }
+                v[rr][e] = val;
+                dv[rr][e] = dval;
+            }
+            // direct store: 4 doubles = 32 bytes per thread, a warp covers one full 1 KB tile row
+            double* dst = K + (int64_t)gi * npad + n0 + tx * 4;
+            reinterpret_cast<double2*>(dst)[0] = make_double2(v[rr][0], v[rr][1]);
+            reinterpret_cast<double2*>(dst)[1] = make_double2(v[rr][2], v[rr][3]);
+            if (WITH_DK) {
+                double* dd = dK + (int64_t)gi * npad + n0 + tx * 4;
+                reinterpret_cast<double2*>(dd)[0] = make_double2(dv[rr][0], dv[rr][1]);
+                reinterpret_cast<double2*>(dd)[1] = make_double2(dv[rr][2], dv[rr][3]);
+            }
+        }
+        if (tm != tn) {
+            // mirror store through shared memory: tbuf[r_local][c]
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                int rl = ty + 8 * rr;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tbuf[rl * PITCH + tx * 4 + e] = v[rr][e];
+                    if (WITH_DK) tbuf[CH * PITCH + rl * PITCH + tx * 4 + e] = dv[rr][e];
+                }
+            }
+            __syncthreads();
+            // lane -> local row (32 consecutive doubles = 256 B of the mirrored row), warp -> column
+            for (int c = ty; c < MT; c += 8) {
+                int64_t o = (int64_t)(n0 + c) * npad + m0 + chunk * CH + tx;
+                K[o] = tbuf[tx * PITCH + c];
+                if (WITH_DK) dK[o] = tbuf[CH * PITCH + tx * PITCH + c];
+            }
+        }
+    }
+}
+
+template <int MODE>
+static int launch_mode(const double* pts, int n, int d, int npad, double* K, double* dK, const MaternParams& mp,
+                       cudaStream_t s) {
+    int T = npad / MT;
+    int tiles = T * (T + 1) / 2;
+    size_t smem = sizeof(double) * (2 * d * MT + (dK ? 2 : 1) * CH * PITCH);
+    if (dK) {
+        GP_CUDA_CHECK(cudaFuncSetAttribute(matern_dense_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        matern_dense_kernel<MODE, true><<<tiles, 256, smem, s>>>(pts, n, d, npad, K, dK, mp);
+    } else {
+        GP_CUDA_CHECK(cudaFuncSetAttribute(matern_dense_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        matern_dense_kernel<MODE, false><<<tiles, 256, smem, s>>>(pts, n, d, npad, K, nullptr, mp);
+    }
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace gp
+
+extern "C" int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* scale_host, double nu,
+                               double* K, int64_t ldk, double* dK, void* stream) {
+    using namespace gp;
+    if (n <= 0 || d <= 0 || d > MAXD || !points || !K || !scale_host) return -1;
+    int64_t npad = gp_padded_size(n);
+    if (ldk != npad || npad > INT32_MAX) return -2;
+    cudaStream_t s = (cudaStream_t)stream;
+    MaternParams mp;
+    for (int k = 0; k < d; ++k) {
+        if (!(scale_host[k] > 0.0)) return -3;
+        if (dK && scale_host[k] != scale_host[0]) return -4;  // d/drho is defined for an isotropic scale only
+        mp.inv_scale[k] = 1.0 / scale_host[k];
+    }
+    mp.nu = nu;
+    mp.coef = 0.0;
+    mp.sq2nu = 0.0;
+    mp.inv_rho = 1.0 / scale_host[0];
+    int mode = matern_mode_of(nu);
+    if (mode == MAT_GENERAL) {
+        if (!(nu > 0.0)) return -5;
+        mp.coef = pow(2.0, 1.0 - nu) / tgamma(nu);
+        mp.sq2nu = sqrt(2.0 * nu);
+    }
+    switch (mode) {
+        case MAT_05: return launch_mode<MAT_05>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+        case MAT_15: return launch_mode<MAT_15>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+        case MAT_25: return launch_mode<MAT_25>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+        case MAT_GAUSS: return launch_mode<MAT_GAUSS>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+        default: return launch_mode<MAT_GENERAL>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+    }
+}

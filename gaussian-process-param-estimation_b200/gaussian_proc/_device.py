@@ -1,0 +1,114 @@
+"""
+ctypes binding of ``libgpgp.so`` (the C ABI declared in ``include/gpgp.h``) and the small amount of device-buffer
+plumbing shared by the package. PyTorch is used only to own device memory and streams.
+
+There is deliberately NO CPU fallback: importing the library or calling any compute entry point without the
+CUDA extension / a CUDA device raises.
+"""
+
+import ctypes
+import os
+
+import numpy
+
+__all__ = ['lib', 'check', 'GpgpError', 'padded_size', 'stream_ptr', 'torch', 'require_cuda']
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libgpgp.so')
+
+
+class GpgpError(RuntimeError):
+    """Raised when a libgpgp entry point reports a bad argument or a CUDA error (negative status)."""
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            'libgpgp.so not found at %s. Build it with `python __graft_entry__.py build` (nvcc, sm_100a). '
+            'This package has no CPU fallback.' % _LIB_PATH)
+    return ctypes.CDLL(_LIB_PATH)
+
+
+lib = _load()
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_f64 = ctypes.c_double
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); must list every symbol of include/gpgp.h (tests/test_abi.py checks that)
+SIGNATURES = {
+    'gp_abi_version': (_int, []),
+    'gp_padded_size': (_i64, [_i64]),
+    'gp_matern_dense': (_int, [_vp, _i64, _i64, _vp, _f64, _vp, _i64, _vp, _vp]),
+    'gp_dgemm_f64': (_int, [_int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _int, _int,
+                            _vp]),
+    'gp_shift_copy': (_int, [_vp, _i64, _i64, _f64, _vp, _vp]),
+    'gp_potrf_workspace_bytes': (_i64, [_i64]),
+    'gp_potrf_f64': (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    'gp_logdet_from_chol': (_int, [_vp, _i64, _i64, _vp, _vp]),
+    'gp_potrs_f64': (_int, [_vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    'gp_potri_workspace_bytes': (_i64, [_i64]),
+    'gp_potri_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    'gp_trtri_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    'gp_lauum_f64': (_int, [_vp, _vp, _i64, _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status, what):
+    """Map a negative libgpgp status to an exception; non-negative values (LAPACK-style info) are returned."""
+    if status < 0:
+        if status <= -1000:
+            raise GpgpError('%s: CUDA error %d' % (what, -status - 1000))
+        raise GpgpError('%s: invalid argument (status %d)' % (what, status))
+    return status
+
+
+def padded_size(n):
+    return int(lib.gp_padded_size(int(n)))
+
+
+_torch = None
+
+
+def _get_torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+class _TorchProxy(object):
+    def __getattr__(self, name):
+        return getattr(_get_torch(), name)
+
+
+torch = _TorchProxy()
+
+
+def require_cuda():
+    t = _get_torch()
+    if not t.cuda.is_available():
+        raise GpgpError('gaussian_proc (B200 build) needs a CUDA device; there is no CPU fallback.')
+    return t
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream as an integer (0 = legacy default stream)."""
+    t = _get_torch()
+    return ctypes.c_void_p(t.cuda.current_stream().cuda_stream)
+
+
+def host_f64(a):
+    """C-contiguous float64 view/copy of a host array."""
+    return numpy.ascontiguousarray(a, dtype=numpy.float64)
+
+
+def host_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)

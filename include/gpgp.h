@@ -1,0 +1,90 @@
+/*
+ * gpgp.h -- C ABI of libgpgp.so: the B200 (sm_100a) implementation of the Gaussian-process log-likelihood hot
+ * path of ameli/gaussian-process-param-estimation (reference package `gaussian_proc`).
+ *
+ * The reference has no C ABI of its own: its only native surface are the Cython `cdef`
+ * functions of gaussian_proc/generate_correlation/_kernels.pxd:5-13 and the six duck-typed MixedCorrelation
+ * methods. Every entry point below therefore cites the reference function whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - all matrix / vector pointers are DEVICE pointers owned by the caller (e.g. torch CUDA tensors) unless the
+ *    parameter name ends in `_host`; sizes are int64_t; matrices are row-major; `stream` is a cudaStream_t
+ *    passed as void* (NULL = legacy default stream).
+ *  - dense square matrices live in a PADDED buffer: npad = gp_padded_size(n) (next multiple of 128), leading
+ *    dimension npad, with the padding block equal to the identity (zero off-diagonal). Cholesky, inverse and
+ *    log-determinant of the padded matrix restrict exactly to those of the n x n matrix.
+ *  - return value: 0 ok; > 0 LAPACK-style info (1-based index of the first non-positive pivot, or the Lanczos /
+ *    CG breakdown step); < 0 bad argument (-1..-99) or CUDA error (-1000 - cudaError).
+ *  - nothing here allocates persistent device memory; the caller passes workspaces sized by the matching
+ *    *_workspace_bytes query. Calls are stream-ordered and re-entrant per (device, stream).
+ */
+#ifndef GPGP_H
+#define GPGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* library / build identification: returns 100 (the sm_100a build) */
+int gp_abi_version(void);
+/* npad for a matrix of size n */
+int64_t gp_padded_size(int64_t n);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Correlation generation  (reference: generate_correlation/_kernels.pyx:17-136,
+ *                          _generate_dense_correlation.pyx:23-162, _generate_sparse_correlation.pyx:35-594)
+ * nu selects the Matern branch exactly as _kernels.pyx:73-93: 0.5, 1.5, 2.5 closed forms, nu >= 100 Gaussian;
+ * other nu (Bessel K_nu branch, _kernels.pyx:83-88) is evaluated with a device K_nu (Temme series / Steed CF2).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* K[i][j] = matern(||(p_i - p_j) / scale||, nu) into a padded buffer (ldk = npad; padding = identity).
+ * dK (optional, may be NULL) receives dK/d(rho) for an isotropic scale rho = scale_host[0] (all entries of
+ * scale_host must then be equal); its padding is zero. points: (n, d) row-major. */
+int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* scale_host, double nu,
+                    double* K, int64_t ldk, double* dK, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense FP64 linear algebra on K + eta*I  (reference: _mixed_correlation/mixed_correlation.py:155-335 and
+ * _linear_solver.py:71 scipy.linalg.solve(assume_a='pos'), i.e. LAPACK dposv; imate 'cholesky' logdet/traceinv)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* General DMMA GEMM used by everything below; exported for tests and the roofline microbenchmark.
+ * C[MxN] = beta*C + alpha*op(A)*op(B); at/bt: 0 -> operand stored [mn][k], 1 -> stored [k][mn].
+ * krange / tmask: see gp_internal.h (0 / 0 = plain GEMM). M,N multiples of 128, K multiple of 16. */
+int gp_dgemm_f64(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                 int64_t ldb, int64_t M, int64_t N, int64_t K, double alpha, double beta, int krange, int tmask,
+                 void* stream);
+
+/* A (npad x npad, lower triangle referenced) := K + eta*I on the first n diagonal entries (padding diagonal
+ * stays exactly 1); replaces `Kn = K + eta*I` of mixed_correlation.py:184,251,296. */
+int gp_shift_copy(const double* K, int64_t n, int64_t npad, double eta, double* A, void* stream);
+
+/* bytes of workspace for gp_potrf_f64 (holds the inverted 128x128 diagonal blocks of L) */
+int64_t gp_potrf_workspace_bytes(int64_t npad);
+/* In-place lower Cholesky A = L L^T (right-looking, blocked; trailing update on the FP64 tensor pipe).
+ * info_dev: device int, 0 or 1-based index of the first non-positive pivot. ws keeps inv(L_jj) blocks that
+ * gp_potrs_f64 / gp_trtri_f64 reuse. */
+int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, void* stream);
+
+/* logdet(A) = 2 * sum_i log L_ii over the first n rows; out_dev: device double */
+int gp_logdet_from_chol(const double* L, int64_t n, int64_t npad, double* out_dev, void* stream);
+
+/* Solve (L L^T) X = B in place. B is (npad x nrhs) row-major with ldb >= nrhs, rows >= n zero. nrhs <= 16. */
+int gp_potrs_f64(const double* L, int64_t npad, const void* potrf_ws, double* B, int64_t nrhs, int64_t ldb,
+                 void* stream);
+
+/* workspace for gp_potri_f64 */
+int64_t gp_potri_workspace_bytes(int64_t npad);
+/* W := inv(L) (lower, npad x npad, separate buffer) and Ainv_lower := W^T W written over the lower triangle of
+ * `A` (which held L). */
+int gp_potri_f64(double* A, double* W, int64_t npad, const void* potrf_ws, void* ws, void* stream);
+/* the two halves of gp_potri_f64: W := inv(L) (recursive triangular products); Ainv_lower := W^T W */
+int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws, void* ws, void* stream);
+int gp_lauum_f64(const double* W, double* Ainv, int64_t npad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPGP_H */
