@@ -1,0 +1,224 @@
+"""
+Device-resident dense correlation matrix and the FP64 factorisation engine built on libgpgp.
+
+``DeviceCorrelation`` is what ``generate_correlation(..., device=True)`` returns and what ``MixedCorrelation`` keeps
+internally: the padded (npad x npad, identity padding) matrix in HBM plus, when known, the generator parameters
+(points, correlation_scale, nu) that let the d/d(correlation_scale) reductions re-evaluate dK on the fly.
+
+``DenseEngine`` owns the scratch buffers for one matrix size and exposes the stream-ordered building blocks
+(factor, logdet, solve, inverse traces, fused evaluation). One factorisation is cached per eta.
+"""
+
+import ctypes
+
+import numpy
+
+from . import _device as dev
+from ._device import lib, check
+
+__all__ = ['DeviceCorrelation', 'DenseEngine', 'FLAG_TRACEINV', 'FLAG_INVERSE', 'FLAG_DRHO']
+
+FLAG_TRACEINV = 1
+FLAG_INVERSE = 2
+FLAG_DRHO = 4
+MAX_RHS = 16
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class DeviceCorrelation(object):
+    """Padded dense correlation matrix in device memory (float64, row-major, leading dimension npad)."""
+
+    def __init__(self, n, data, points=None, correlation_scale=None, nu=None):
+        self.n = int(n)
+        self.npad = dev.padded_size(n)
+        self.data = data              # torch.float64 CUDA tensor (npad, npad)
+        self.points = points          # torch.float64 CUDA tensor (n, d) or None
+        self.correlation_scale = None if correlation_scale is None else dev.host_f64(correlation_scale)
+        self.nu = nu
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    @classmethod
+    def from_numpy(cls, K):
+        torch = dev.require_cuda()
+        K = numpy.asarray(K, dtype=numpy.float64)
+        if K.ndim != 2 or K.shape[0] != K.shape[1]:
+            raise ValueError('K should be a square matrix.')
+        n = K.shape[0]
+        npad = dev.padded_size(n)
+        data = torch.zeros((npad, npad), dtype=torch.float64, device='cuda')
+        data[:n, :n].copy_(torch.from_numpy(numpy.ascontiguousarray(K)))
+        if npad > n:
+            idx = torch.arange(n, npad, device='cuda')
+            data[idx, idx] = 1.0
+        return cls(n, data)
+
+    def to_numpy(self):
+        return self.data[:self.n, :self.n].cpu().numpy()
+
+    def has_kernel(self):
+        return self.points is not None and self.correlation_scale is not None and self.nu is not None
+
+    def isotropic(self):
+        s = self.correlation_scale
+        return s is not None and bool(numpy.all(s == s[0]))
+
+
+class DenseEngine(object):
+    """Scratch buffers + cached Cholesky state for one DeviceCorrelation."""
+
+    def __init__(self, K):
+        torch = dev.require_cuda()
+        self.K = K
+        self.n, self.npad = K.n, K.npad
+        npad = self.npad
+        f64 = torch.float64
+        self.A = torch.empty((npad, npad), dtype=f64, device='cuda')       # K + eta I -> L (-> inverse in fused mode)
+        self.W = None                                                       # inv(L), allocated on first use
+        self.Ainv = None                                                    # explicit inverse (generic path only)
+        self.potrf_ws = torch.empty(lib.gp_potrf_workspace_bytes(npad) // 8, dtype=f64, device='cuda')
+        self.ws = torch.empty(lib.gp_loglik_workspace_bytes(npad) // 8 + 8, dtype=f64, device='cuda')
+        self.info = torch.zeros(1, dtype=torch.int32, device='cuda')
+        self.scalar = torch.zeros(8, dtype=f64, device='cuda')
+        self._eta = None        # eta whose factor L currently sits in A
+        self._have_W = False
+        self._have_Ainv = False
+        self.launch_count = 0
+
+    # ---- helpers -------------------------------------------------------------------------------------------
+    def _need_W(self):
+        if self.W is None:
+            self.W = dev.torch.zeros((self.npad, self.npad), dtype=dev.torch.float64, device='cuda')
+        return self.W
+
+    def invalidate(self):
+        self._eta = None
+        self._have_W = False
+        self._have_Ainv = False
+
+    def pad_rhs(self, Y):
+        """host (n,) or (n, k) array -> device (npad, k) zero-padded; returns (tensor, was_vector)."""
+        torch = dev.torch
+        Y = numpy.asarray(Y, dtype=numpy.float64)
+        vec = (Y.ndim == 1)
+        Y2 = Y.reshape(self.n, -1)
+        B = torch.zeros((self.npad, Y2.shape[1]), dtype=torch.float64, device='cuda')
+        B[:self.n].copy_(torch.from_numpy(numpy.ascontiguousarray(Y2)))
+        return B, vec
+
+    # ---- building blocks --------------------------------------------------------------------------------------
+    def factor(self, eta):
+        """Cholesky of K + eta I (cached per eta). Raises numpy.linalg.LinAlgError when not positive definite,
+        as scipy.linalg.solve(assume_a='pos') does in the reference (_linear_solver.py:71)."""
+        eta = float(eta)
+        if self._eta is not None and self._eta == eta:
+            return
+        s = dev.stream_ptr()
+        self.invalidate()
+        check(lib.gp_shift_copy(_p(self.K.data), self.n, self.npad, eta, _p(self.A), s), 'gp_shift_copy')
+        check(lib.gp_potrf_f64(_p(self.A), self.n, self.npad, _p(self.info), _p(self.potrf_ws), s), 'gp_potrf_f64')
+        info = int(self.info.item())
+        if info != 0:
+            raise numpy.linalg.LinAlgError(
+                '%d-th leading minor of K + eta*I (eta=%g) is not positive definite.' % (info, eta))
+        self._eta = eta
+
+    def logdet(self, eta):
+        self.factor(eta)
+        check(lib.gp_logdet_from_chol(_p(self.A), self.n, self.npad, _p(self.scalar), dev.stream_ptr()),
+              'gp_logdet_from_chol')
+        return float(self.scalar[0].item())
+
+    def solve(self, eta, Y):
+        self.factor(eta)
+        Y = numpy.asarray(Y, dtype=numpy.float64)
+        vec = (Y.ndim == 1)
+        Y2 = Y.reshape(self.n, -1)
+        out = numpy.empty_like(Y2)
+        for c0 in range(0, Y2.shape[1], MAX_RHS):
+            blk = Y2[:, c0:c0 + MAX_RHS]
+            B, _ = self.pad_rhs(blk)
+            k = B.shape[1]
+            check(lib.gp_potrs_f64(_p(self.A), self.npad, _p(self.potrf_ws), _p(B), k, k, dev.stream_ptr()),
+                  'gp_potrs_f64')
+            out[:, c0:c0 + k] = B[:self.n].cpu().numpy()
+        return out[:, 0] if vec else out
+
+    def _trtri(self, eta):
+        self.factor(eta)
+        if not self._have_W:
+            W = self._need_W()
+            check(lib.gp_trtri_f64(_p(self.A), _p(W), self.npad, _p(self.potrf_ws), _p(self.ws), dev.stream_ptr()),
+                  'gp_trtri_f64')
+            self._have_W = True
+
+    def traceinv(self, eta, exponent=1):
+        """tr (K + eta I)^-p for p in {1, 2} from the Cholesky factor (imate 'cholesky' method restated:
+        tr Kn^-1 = ||inv(L)||_F^2, tr Kn^-2 = ||Kn^-1||_F^2)."""
+        torch = dev.torch
+        self._trtri(eta)
+        s = dev.stream_ptr()
+        if exponent == 1:
+            check(lib.gp_inverse_traces(_p(self.W), self.n, self.npad, 0, _p(self.scalar), _p(self.ws), s),
+                  'gp_inverse_traces')
+            return float(self.scalar[1].item())
+        if exponent == 2:
+            if not self._have_Ainv:
+                if self.Ainv is None:
+                    self.Ainv = torch.empty((self.npad, self.npad), dtype=torch.float64, device='cuda')
+                check(lib.gp_lauum_f64(_p(self.W), _p(self.Ainv), self.npad, s), 'gp_lauum_f64')
+                self._have_Ainv = True
+            check(lib.gp_inverse_traces(_p(self.Ainv), self.n, self.npad, 1, _p(self.scalar), _p(self.ws), s),
+                  'gp_inverse_traces')
+            return float(self.scalar[2].item())
+        raise ValueError('traceinv on the dense Cholesky engine supports exponent 1 and 2.')
+
+    def trace_K(self):
+        """(tr K, tr K^2 = ||K||_F^2) of the unshifted matrix."""
+        check(lib.gp_inverse_traces(_p(self.K.data), self.n, self.npad, 1, _p(self.scalar), _p(self.ws),
+                                    dev.stream_ptr()), 'gp_inverse_traces')
+        v = self.scalar.cpu().numpy()
+        return float(v[1]), float(v[2])
+
+    def matmul(self, X):
+        """K @ X for host X (n,) or (n, k) -- the reference's K_mixed.dot(0, x) (mixed_correlation.py:305-335)."""
+        torch = dev.torch
+        X = numpy.asarray(X, dtype=numpy.float64)
+        vec = (X.ndim == 1)
+        B, _ = self.pad_rhs(X)
+        k = B.shape[1]
+        out = torch.empty((self.npad, k), dtype=torch.float64, device='cuda')
+        check(lib.gp_symm_skinny(_p(self.K.data), self.n, self.npad, _p(B), k, _p(out), dev.stream_ptr()),
+              'gp_symm_skinny')
+        res = out[:self.n].cpu().numpy()
+        return res[:, 0] if vec else res
+
+    # ---- fused evaluation -----------------------------------------------------------------------------------
+    def fused(self, eta, R_dev, p, flags):
+        """One gp_loglik_dense call. R_dev: device (npad, p) = [X z] zero-padded. Returns host array out[]."""
+        torch = dev.torch
+        K = self.K
+        out = torch.empty(int(lib.gp_loglik_out_len(p)), dtype=torch.float64, device='cuda')
+        W = self._need_W() if (flags & 3) else None
+        pts = scale = None
+        d, nu = 0, 0.0
+        if flags & FLAG_DRHO:
+            if not K.has_kernel():
+                raise ValueError('d/d(correlation_scale) needs a correlation generated by generate_correlation('
+                                 '..., device=True) or MixedCorrelation.set_kernel(points, correlation_scale, nu).')
+            if not K.isotropic():
+                raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
+            pts, scale, d, nu = K.points, K.correlation_scale, K.points.shape[1], float(K.nu)
+        self.invalidate()  # A / W are overwritten
+        rc = lib.gp_loglik_dense(_p(K.data), self.n, self.npad, _p(R_dev), p, float(eta), int(flags),
+                                 _p(pts) if pts is not None else None, d,
+                                 dev.host_ptr(scale) if scale is not None else None, nu,
+                                 _p(self.A), _p(W) if W is not None else None, _p(self.potrf_ws), _p(self.ws), _p(out),
+                                 dev.stream_ptr())
+        check(rc, 'gp_loglik_dense')
+        return out

@@ -1,0 +1,77 @@
+"""
+Host-side (m+1)x(m+1) algebra on top of the fused device evaluator (csrc/gp_loglik.cu, `gp_loglik_dense`).
+
+With R = [X z], S = Kn^-1 R and the device outputs G = R^T S, H = S^T S, Q = S^T dK S the quantities of the reference
+formulas follow without touching n-sized data again (M = Kn^-1 - Kn^-1 X (X^T Kn^-1 X)^-1 X^T Kn^-1, c = [-beta; 1]):
+    B = G[:m,:m]            beta = B^-1 G[:m,m]          z^T M z   = G[m,m] - G[:m,m].beta
+    z^T M^2 z = c^T H c     z^T M K M z = c^T (G - eta H) c          z^T M dK M z = c^T Q c
+    tr M = tr Kn^-1 - tr(B^-1 H[:m,:m])                  tr(M dK) = tr(Kn^-1 dK) - tr(B^-1 Q[:m,:m])
+(reference: _direct_likelihood.py:113-150, _profile_likelihood.py:104-130.)
+"""
+
+import numpy
+
+from .. import _device as dev
+from .._dense import FLAG_TRACEINV, FLAG_INVERSE, FLAG_DRHO
+
+__all__ = ['FusedQuantities', 'evaluate']
+
+
+class FusedQuantities(object):
+    """Unpacked result of one fused evaluation at a given eta (all host floats / small arrays)."""
+
+    def __init__(self, out, n, m, eta, flags):
+        p = m + 1
+        self.n, self.m, self.eta, self.flags = n, m, eta, flags
+        self.logdet_Kn = float(out[0])
+        self.trace_Kninv = float(out[1])
+        self.trace_Kninv2 = float(out[2])
+        self.trace_Kninv_dK = float(out[3])
+        self.info = int(out[4])
+        G = out[8:8 + p * p].reshape(p, p)
+        H = out[8 + p * p:8 + 2 * p * p].reshape(p, p)
+        Q = out[8 + 2 * p * p:8 + 3 * p * p].reshape(p, p)
+        self.G, self.H, self.Q = G, H, Q
+        self.B = G[:m, :m]
+        self.Binv = numpy.linalg.inv(self.B)
+        self.beta = self.Binv @ G[:m, m]
+        self.c = numpy.append(-self.beta, 1.0)
+        self.zMz = float(G[m, m] - G[:m, m] @ self.beta)
+        self.zM2z = float(self.c @ H @ self.c)
+        self.zMKMz = float(self.c @ (G - eta * H) @ self.c)
+        self.zMdKMz = float(self.c @ Q @ self.c)
+        self.trace_M = self.trace_Kninv - float(numpy.trace(self.Binv @ H[:m, :m]))
+        self.trace_MdK = self.trace_Kninv_dK - float(numpy.trace(self.Binv @ Q[:m, :m]))
+
+
+def _rhs_device(K_mixed, X, z):
+    """[X z] zero-padded on the device, cached on the operator while X and z are the same objects."""
+    key = (id(X), id(z))
+    cache = getattr(K_mixed, '_rhs_cache', None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    R = numpy.c_[numpy.asarray(X, dtype=float), numpy.asarray(z, dtype=float)]
+    Rd, _ = K_mixed.engine.pad_rhs(R)
+    K_mixed._rhs_cache = (key, Rd, X, z)  # keep X, z alive so the ids stay unique
+    return Rd
+
+
+def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
+    """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite."""
+    if K_mixed.sparse:
+        raise TypeError('the fused dense evaluator needs a dense MixedCorrelation')
+    n, m = X.shape
+    flags = 0
+    if traceinv:
+        flags |= FLAG_TRACEINV
+    if inverse or drho:
+        flags |= FLAG_INVERSE
+    if drho:
+        flags |= FLAG_DRHO
+    Rd = _rhs_device(K_mixed, X, z)
+    out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags).cpu().numpy()
+    q = FusedQuantities(out, n, m, float(eta), flags)
+    if q.info != 0:
+        raise numpy.linalg.LinAlgError(
+            '%d-th leading minor of K + eta*I (eta=%g) is not positive definite.' % (q.info, eta))
+    return q

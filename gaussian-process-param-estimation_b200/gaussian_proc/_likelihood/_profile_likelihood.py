@@ -1,0 +1,139 @@
+"""
+ProfileLikelihood -- log-likelihood in (sigma, eta), its eta-derivative profiled over sigma, and the root-finding
+driver; same signatures and returned numbers as gaussian_proc/_likelihood/_profile_likelihood.py (:38-85
+log_likelihood, :91-132 log_likelihood_der1_eta, :138-192 der2_eta, :198-238 Nelder-Mead maximisation, :244-415
+find_log_likelihood_der1_zeros). Bounds / asymptotes / plots (:456-732) are paper figures and out of scope.
+"""
+
+from functools import partial
+
+import numpy
+from scipy.optimize import minimize
+
+from . import _fused
+from ._root_finding import find_interval_with_sign_change, chandrupatla_method
+
+__all__ = ['ProfileLikelihood']
+
+
+class ProfileLikelihood(object):
+
+    # ---- log likelihood (:38-85); no 2 pi constant ------------------------------------------------
+    @staticmethod
+    def log_likelihood(z, X, K_mixed, sign_switch, hyperparam):
+        sigma, eta = hyperparam[0], hyperparam[1]
+        n, m = X.shape
+        q = _fused.evaluate(z, X, K_mixed, eta)
+        lp = -0.5 * (n - m) * numpy.log(sigma ** 2) - 0.5 * q.logdet_Kn - 0.5 * numpy.log(numpy.linalg.det(q.B)) \
+            - (0.5 / (sigma ** 2)) * q.zMz
+        return -lp if sign_switch else lp
+
+    # ---- d l/d eta at sigma^2_hat(eta) (:91-132); argument is log10(eta) ---------------------------
+    @staticmethod
+    def log_likelihood_der1_eta(z, X, K_mixed, log_eta):
+        eta = 0.0 if numpy.isneginf(log_eta) else 10.0 ** log_eta
+        n, m = X.shape
+        q = _fused.evaluate(z, X, K_mixed, eta, traceinv=True)
+        sigma02 = q.zMz / (n - m)
+        return -0.5 * (q.trace_M - q.zM2z / sigma02)
+
+    # ---- extension: profiled d l/d rho ----------------------------------------------------------
+    @staticmethod
+    def log_likelihood_der1_rho(z, X, K_mixed, eta):
+        """d l^/d rho = -1/2 tr(M dK) + z^T M dK M z / (2 sigma^2_hat(eta)), isotropic correlation_scale."""
+        return ProfileLikelihood.log_likelihood_and_gradient(z, X, K_mixed, eta)[2]
+
+    @staticmethod
+    def log_likelihood_and_gradient(z, X, K_mixed, eta, with_rho=True):
+        """(l^(sigma_hat, eta), d l^/d eta, d l^/d rho) from ONE factorisation -- the unit bench.py counts as a
+        'loglik+grad evaluation'."""
+        n, m = X.shape
+        q = _fused.evaluate(z, X, K_mixed, eta, traceinv=True, drho=with_rho)
+        sigma2 = q.zMz / (n - m)
+        lp = -0.5 * (n - m) * numpy.log(sigma2) - 0.5 * q.logdet_Kn - 0.5 * numpy.log(numpy.linalg.det(q.B)) \
+            - 0.5 * (n - m)
+        deta = -0.5 * (q.trace_M - q.zM2z / sigma2)
+        drho = (-0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sigma2) if with_rho else None
+        return lp, deta, drho
+
+    # ---- second derivative, valid at the stationary point only (:138-192) --------------------------
+    @staticmethod
+    def log_likelihood_der2_eta(z, X, K_mixed, eta):
+        Y = K_mixed.solve(eta, X)
+        V = K_mixed.solve(eta, Y)
+        w = K_mixed.solve(eta, z)
+        n, m = X.shape
+        Binv = numpy.linalg.inv(numpy.matmul(X.T, Y))
+        Mz = w - numpy.matmul(Y, numpy.matmul(Binv, numpy.matmul(Y.T, z)))
+        A = numpy.matmul(Binv, numpy.matmul(Y.T, Y))
+        trace_M = K_mixed.traceinv(eta) - numpy.trace(A)
+        trace_C = numpy.trace(numpy.matmul(Binv, numpy.matmul(Y.T, V)))
+        trace_M2 = K_mixed.traceinv(eta, exponent=2) - 2.0 * trace_C + numpy.trace(numpy.matmul(A, A))
+        v = K_mixed.solve(eta, Mz)
+        MMz = v - numpy.matmul(Y, numpy.matmul(Binv, numpy.matmul(Y.T, Mz)))
+        zMz = numpy.dot(z, Mz)
+        zM3z = numpy.dot(Mz, MMz)
+        sigma02 = zMz / (n - m)
+        return (0.5 / sigma02) * ((trace_M2 / (n - m) + (trace_M / (n - m)) ** 2) * zMz - 2.0 * zM3z)
+
+    # ---- Nelder-Mead over (sigma, eta) (:198-238) --------------------------------------------------------------
+    @staticmethod
+    def maximize_log_likelihood_with_sigma_eta(z, X, K_mixed, tol=1e-6, hyperparam_guess=[0.1, 0.1],
+                                               method='Nelder-Mead'):
+        print('Maximize log likelihood with sigma eta ...')
+        fun = partial(ProfileLikelihood.log_likelihood, z, X, K_mixed, True)
+        res = minimize(fun, hyperparam_guess, method='Nelder-Mead', tol=tol)
+        print('Iter: %d, Eval: %d, success: %s' % (res.nit, res.nfev, res.success))
+        sigma, eta = res.x[0], res.x[1]
+        return {'sigma': sigma, 'sigma0': numpy.sqrt(eta) * sigma, 'eta': eta, 'max_lp': -res.fun}
+
+    # ---- root of d l/d eta (:244-415) ----------------------------------------------------------------------------
+    @staticmethod
+    def find_log_likelihood_der1_zeros(z, X, K_mixed, interval_eta, tol=1e-6, max_iterations=100,
+                                       num_bracket_trials=3):
+
+        def find_optimal_sigma(eta):
+            n, m = X.shape
+            q = _fused.evaluate(z, X, K_mixed, eta)
+            return numpy.sqrt(q.zMz / (n - m))
+
+        def find_optimal_sigma0():
+            n, m = X.shape
+            Binv = numpy.linalg.inv(numpy.matmul(X.T, X))
+            v = numpy.matmul(X, numpy.matmul(Binv, numpy.matmul(X.T, z)))
+            return numpy.sqrt(numpy.dot(z, z - v) / (n - m))
+
+        print('Find root of log likelihood derivative ...')
+        f = partial(ProfileLikelihood.log_likelihood_der1_eta, z, X, K_mixed)
+        bracket = [numpy.log10(interval_eta[0]), numpy.log10(interval_eta[1])]
+        bracket_found, bracket, bracket_values = find_interval_with_sign_change(f, bracket, num_bracket_trials, args=(), )
+
+        if bracket_found:
+            res = chandrupatla_method(f, bracket, bracket_values, verbose=False, eps_m=tol, eps_a=tol,
+                                      maxiter=max_iterations)
+            print('Iter: %d' % (res['iterations']))
+            eta = 10 ** res['root']
+            sigma = find_optimal_sigma(eta)
+            sigma0 = numpy.sqrt(eta) * sigma
+            success = True
+        else:
+            # no sign change: decide between eta -> 0 and eta -> inf from the curvature at eta = 0 (:352-405)
+            dlp_left, dlp_right = bracket_values[0], bracket_values[1]
+            d2lp_zero = ProfileLikelihood.log_likelihood_der2_eta(z, X, K_mixed, 0.0)
+            print('dL/deta   at eta = %0.2e:\t %0.2f' % (bracket[0], dlp_left))
+            print('dL/deta   at eta = %0.2e:\t %0.16f' % (bracket[1], dlp_right))
+            print('d2L/deta2 at eta = 0.0:\t %0.2f' % d2lp_zero)
+            if (dlp_left > 0) and (dlp_right > 0):
+                eta = 0.0 if d2lp_zero > 0 else numpy.inf
+            elif (dlp_left < 0) and (dlp_right < 0):
+                eta = 0.0 if d2lp_zero < 0 else numpy.inf
+            else:
+                raise ValueError('eta must be zero or inf at this point.')
+            if eta == 0:
+                sigma0 = 0
+                sigma = find_optimal_sigma(eta)
+            else:
+                sigma = 0
+                sigma0 = find_optimal_sigma0()
+            success = True
+        return {'sigma': sigma, 'sigma0': sigma0, 'eta': eta, 'success': success}

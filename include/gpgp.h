@@ -84,6 +84,42 @@ int gp_potri_f64(double* A, double* W, int64_t npad, const void* potrf_ws, void*
 int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws, void* ws, void* stream);
 int gp_lauum_f64(const double* W, double* Ainv, int64_t npad, void* stream);
 
+/* Traces of the inverse from the triangular / symmetric inverse (imate 'cholesky' traceinv restated,
+ * mixed_correlation.py:183-191). kind 0: M = inv(L) -> out[1] = ||M||_F^2 = tr Kn^-1.
+ * kind 1: M = Kn^-1 (lower triangle stored) -> out[1] = tr Kn^-1, out[2] = ||Kn^-1||_F^2 = tr Kn^-2.
+ * out_dev: device, >= 5 doubles (same layout as gp_loglik_dense's out[0..4]). */
+int64_t gp_traces_workspace_bytes(int64_t npad);
+int gp_inverse_traces(const double* M, int64_t n, int64_t npad, int kind, double* out_dev, void* ws, void* stream);
+
+/* Y (npad x p) = K * X for a skinny X (npad x p, p <= 16, rows >= n ignored): K_mixed.dot(0, x) of
+ * mixed_correlation.py:305-335 (the eta*x term is added by the caller). */
+int gp_symm_skinny(const double* K, int64_t n, int64_t npad, const double* X, int64_t p, double* Y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused log-likelihood (+ gradient ingredients) evaluation at one (rho, eta)
+ * (reference: _likelihood/_direct_likelihood.py:31-157 log_likelihood + log_likelihood_jacobian,
+ *  _likelihood/_profile_likelihood.py:38-132 log_likelihood + log_likelihood_der1_eta; the d/drho terms are the
+ *  extension named in BASELINE.json's north_star).
+ *
+ * Inputs : K (padded, read-only), R = [X z] (npad x p row-major, rows >= n zero, p = m + 1 <= 16), eta.
+ * Work   : A, W (npad x npad scratch each; W may be NULL when flags & 3 == 0), potrf_ws, ws.
+ * flags  : bit0 (1) tr Kn^-1 via ||inv(L)||_F^2       (enough for d/d eta)
+ *          bit1 (2) full inverse: tr Kn^-1, tr Kn^-2  (needed for d/d rho and the Hessian traces)
+ *          bit2 (4) d/d rho reductions, needs bit1 and points/d/scale_host/nu (dK/drho is re-evaluated on the fly)
+ * Output : out (DEVICE, gp_loglik_out_len(p) doubles):
+ *          out[0] logdet(K + eta I)   out[1] tr Kn^-1   out[2] tr Kn^-2   out[3] tr(Kn^-1 dK/drho)
+ *          out[4] potrf info (0 = ok) out[5..7] reserved
+ *          out[8 ..]            G = R^T Kn^-1 R        (p x p)
+ *          out[8 + p^2 ..]      H = R^T Kn^-2 R        (p x p)
+ *          out[8 + 2 p^2 ..]    Q = (Kn^-1 R)^T dK/drho (Kn^-1 R)   (p x p; zero unless bit2)
+ * The remaining (m+1)x(m+1) algebra is host-side (gaussian_proc/_likelihood/_fused.py).
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t gp_loglik_workspace_bytes(int64_t npad);
+int64_t gp_loglik_out_len(int64_t p);
+int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, int64_t p, double eta, int flags,
+                    const double* points, int64_t d, const double* scale_host, double nu, double* A, double* W,
+                    void* potrf_ws, void* ws, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,259 @@
+"""GPU parity tests (dense path): CUDA product through the C ABI / Python mirror vs the CPU oracle and the committed
+golden fixtures. Tolerances: generator <= 4 ulp-level absolute (values in [0,1]); log-likelihood, derivatives,
+logdet, traces, solves: 1e-9 relative (BASELINE.json north_star), written next to each assert."""
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def rel(a, b):
+    a, b = numpy.asarray(a, dtype=float), numpy.asarray(b, dtype=float)
+    return float(numpy.max(numpy.abs(a - b)) / max(numpy.max(numpy.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope='module')
+def gp():
+    import gaussian_proc
+    return gaussian_proc
+
+
+@pytest.fixture(scope='module')
+def problem():
+    from oracle import data_utilities as du
+    numpy.random.seed(0)
+    pts = numpy.random.rand(300, 2)
+    return pts, du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2)
+
+
+# ---------------------------------------------------------------------------------------------- generator
+@pytest.mark.parametrize('nu', [0.5, 1.5, 2.5, 200.0, 3.3, 0.8])
+def test_dense_generator_matches_reference_golden(gp, golden_generate, nu):
+    pts = golden_generate['points2d']
+    K = gp.generate_correlation(pts, numpy.array([0.1, 0.17]), nu)
+    Kref = golden_generate['dense_nu%g' % nu]
+    assert K.shape == Kref.shape and K.dtype == numpy.float64 and K.flags['C_CONTIGUOUS']
+    tol = 4e-16 if nu in (0.5, 1.5, 2.5, 200.0) else 2e-13   # closed forms: ~ulp; Bessel branch: device K_nu
+    assert numpy.max(numpy.abs(K - Kref)) <= tol
+    assert (K == K.T).all()                      # exact symmetry (reference mirrors one evaluation, Q13)
+    assert (numpy.diag(K) == 1.0).all()          # x == 0 -> exactly 1 (_kernels.pyx:73-74)
+
+
+def test_dense_generator_3d_and_scalar_scale(gp, golden_generate):
+    K = gp.generate_correlation(golden_generate['points3d'], numpy.array([0.2, 0.3, 0.25]), 1.5)
+    assert numpy.max(numpy.abs(K - golden_generate['dense3d_nu1.5'])) <= 4e-16
+    from oracle import matern
+    pts = golden_generate['points2d']
+    K1 = gp.generate_correlation(pts, 0.1, 2.5)        # scalar -> repeated (generate_correlation.py:191-196)
+    assert numpy.max(numpy.abs(K1 - matern.generate_dense_correlation(pts, 0.1, 2.5))) <= 4e-16
+
+
+def test_dense_generator_edge_sizes(gp):
+    from oracle import matern
+    for n in (1, 2, 127, 128, 129, 257):
+        numpy.random.seed(n)
+        pts = numpy.random.rand(n, 2)
+        K = gp.generate_correlation(pts, 0.2, 1.5)
+        assert K.shape == (n, n)
+        assert numpy.max(numpy.abs(K - matern.generate_dense_correlation(pts, 0.2, 1.5))) <= 4e-16
+    # duplicate points: distance exactly zero off the diagonal -> exactly 1
+    pts = numpy.array([[0.1, 0.2], [0.1, 0.2], [0.5, 0.5]])
+    K = gp.generate_correlation(pts, 0.2, 2.5)
+    assert K[0, 1] == 1.0 and K[1, 0] == 1.0
+
+
+def test_generator_dK_matches_oracle(gp, problem):
+    from gaussian_proc.generate_correlation.generate_correlation import generate_dense_correlation
+    from oracle import matern
+    pts = problem[0]
+    for nu in (0.5, 1.5, 2.5, 200.0, 3.3):
+        Kd, dK = generate_dense_correlation(pts, numpy.array([0.1, 0.1]), nu, with_derivative=True)
+        n = pts.shape[0]
+        ref = matern.matern_derivative_rho(pts, 0.1, nu)
+        assert rel(dK[:n, :n].cpu().numpy(), ref) <= 1e-11, nu
+
+
+# ------------------------------------------------------------------------------- mixed correlation operator
+@pytest.mark.parametrize('case', [0, 1, 2, 3, 4])
+def test_mixed_correlation_against_reference_vectors(gp, golden_likelihood, case):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    g = golden_likelihood
+    nu, rho = g['cases'][case]
+    pts, z, X = g['points'], g['z'], g['X']
+    K = gp.generate_correlation(pts, rho, nu, device=True)
+    Km = MixedCorrelation(K, imate_method='cholesky')
+    assert Km.get_matrix_size() == pts.shape[0]
+    for method in ('eigenvalue', 'cholesky'):          # the reference's two deterministic methods agree
+        tag = 'c%d_%s_' % (case, method)
+        for i, t in enumerate(g['log_etas']):
+            eta = 10.0 ** t
+            if case == 4 and t < 0:
+                continue                                # Gaussian kernel, tiny eta: kappa ~ 1e12, outside the 1e-9 regime
+            assert abs(Km.logdet(eta) - g[tag + 'logdet'][i]) <= RTOL * abs(g[tag + 'logdet'][i]) + 1e-9
+            assert rel(Km.traceinv(eta), g[tag + 'traceinv'][i]) <= (1e-8 if t < 0 else RTOL)
+            assert rel(Km.traceinv(eta, exponent=2), g[tag + 'traceinv2'][i]) <= (1e-7 if t < 0 else RTOL)
+    if case != 4:
+        sol = Km.solve(0.1, numpy.c_[X, z])
+        assert rel(sol, g['c%d_solve_eta0.1' % case]) <= RTOL
+        assert rel(Km.solve(0.1, z), g['c%d_solve_eta0.1' % case][:, -1]) <= RTOL
+    # dot / trace against the oracle
+    from oracle import matern
+    Kh = matern.generate_dense_correlation(pts, rho, nu)
+    assert rel(Km.dot(0, z), Kh @ z) <= 1e-12
+    assert rel(Km.dot(0.3, X), Kh @ X + 0.3 * X) <= 1e-12
+    assert rel(Km.trace(0.5), numpy.trace(Kh) + 0.5 * Kh.shape[0]) <= 1e-13
+    assert rel(Km.trace(0.5, exponent=2), numpy.sum((Kh + 0.5 * numpy.eye(Kh.shape[0])) ** 2)) <= 1e-12
+
+
+def test_not_positive_definite_raises(gp):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    A = numpy.eye(200)
+    A[5, 5] = -1.0
+    Km = MixedCorrelation(A)
+    with pytest.raises(numpy.linalg.LinAlgError):
+        Km.logdet(0.0)
+
+
+# ---------------------------------------------------------------------------------------------- likelihood
+@pytest.mark.parametrize('case', [0, 1, 2, 3])
+def test_likelihood_against_reference_vectors(gp, golden_likelihood, case):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import DirectLikelihood, ProfileLikelihood
+    g = golden_likelihood
+    nu, rho = g['cases'][case]
+    pts, z, X = g['points'], g['z'], g['X']
+    Km = MixedCorrelation(gp.generate_correlation(pts, rho, nu, device=True))
+    tag = 'c%d_cholesky_' % case
+    for i, h in enumerate(g['hyper_direct']):
+        eta = (h[1] / h[0]) ** 2
+        tol = RTOL if eta >= 1e-2 else 1e-7       # agreement between two FP64 algorithms ~ kappa*eps
+        ll = DirectLikelihood.log_likelihood(z, X, Km, False, list(h))
+        assert abs(ll - g[tag + 'direct_ll'][i]) <= tol * abs(g[tag + 'direct_ll'][i])
+        assert DirectLikelihood.log_likelihood(z, X, Km, True, list(h)) == -ll
+        jac = DirectLikelihood.log_likelihood_jacobian(z, X, Km, False, list(h))
+        assert rel(jac, g[tag + 'direct_jac'][i]) <= tol
+        hess = DirectLikelihood.log_likelihood_hessian(z, X, Km, False, list(h))
+        assert rel(hess, g[tag + 'direct_hess'][i]) <= max(tol, 1e-8)
+    for i, h in enumerate(g['hyper_profile']):
+        tol = RTOL if h[1] >= 1e-2 else 1e-7
+        ll = ProfileLikelihood.log_likelihood(z, X, Km, False, list(h))
+        assert abs(ll - g[tag + 'profile_ll'][i]) <= tol * abs(g[tag + 'profile_ll'][i])
+    for i, t in enumerate(g['log_etas']):
+        d = ProfileLikelihood.log_likelihood_der1_eta(z, X, Km, t)
+        ref = g[tag + 'profile_der1'][i]
+        assert abs(d - ref) <= (RTOL if t >= -1 else 1e-7) * max(abs(ref), 1.0)
+
+
+def test_profile_root_against_reference(gp, golden_likelihood):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    g = golden_likelihood
+    pts, z, X = g['points'], g['z'], g['X']
+    for case in (0, 1, 2):
+        ref = g['c%d_eigenvalue_root' % case]
+        if numpy.isnan(ref).any():
+            continue
+        nu, rho = g['cases'][case]
+        Km = MixedCorrelation(gp.generate_correlation(pts, rho, nu, device=True))
+        res = ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Km, [1e-4, 1e3])
+        got = numpy.array([res['sigma'], res['sigma0'], res['eta']])
+        assert rel(got, ref) <= 1e-7       # root tolerance is 1e-6 in log10(eta)
+
+
+def test_golden_pickle_cells_on_gpu(gp, golden_pickles):
+    """Shipped OptimalCovariance_WithoutPrior.pickle cells (general-nu Bessel branch, n = 900 grid): full GPU path
+    (device K_nu generator -> Cholesky -> root find -> profile l)."""
+    from oracle import data_utilities as du
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    pts = du.generate_points(30, 2, grid=True)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    for (i, j) in [(0, 0), (10, 7), (33, 20), (60, 59), (45, 3)]:
+        rho, nu = golden_pickles['rho'][i], golden_pickles['nu'][j]
+        Km = MixedCorrelation(gp.generate_correlation(pts, rho, nu, device=True))
+        res = ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Km, [1e-3, 1e3])
+        lp = ProfileLikelihood.log_likelihood(z, X, Km, False, [res['sigma'], res['eta']])
+        assert abs(lp - golden_pickles['Lp_noprior'][i, j]) <= 1e-9 * abs(lp)
+
+
+# ------------------------------------------------------------------------------- d/d rho (extension) + fused
+@pytest.mark.parametrize('nu', [0.5, 1.5, 2.5])
+def test_gradient_rho_matches_oracle(gp, problem, nu):
+    from oracle import matern, likelihood as L
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import DirectLikelihood, ProfileLikelihood
+    pts, z, X = problem
+    rho = 0.1
+    Kh = matern.generate_dense_correlation(pts, rho, nu)
+    dKh = matern.matern_derivative_rho(pts, rho, nu)
+    Ko = L.MixedCorrelation(Kh, 'cholesky')
+    Km = MixedCorrelation(gp.generate_correlation(pts, rho, nu, device=True))
+    for h in [(0.3, 0.2), (0.5, 0.5)]:
+        lp, jac, drho = DirectLikelihood.log_likelihood_and_gradient(z, X, Km, list(h))
+        assert abs(lp - L.DirectLikelihood.log_likelihood(z, X, Ko, False, list(h))) <= RTOL * abs(lp)
+        assert rel(jac, L.DirectLikelihood.log_likelihood_jacobian(z, X, Ko, False, list(h))) <= RTOL
+        assert rel(drho, L.DirectLikelihood.log_likelihood_der1_rho(z, X, Ko, dKh, list(h))) <= RTOL
+    for eta in (0.05, 1.0, 20.0):
+        lp, deta, drho = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
+        sig = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, eta)
+        assert abs(lp - L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [sig, eta])) <= RTOL * abs(lp)
+        assert rel(deta, L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(eta))) <= RTOL
+        assert rel(drho, L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dKh, eta)) <= RTOL
+
+
+def test_gradient_rho_set_kernel_and_errors(gp, problem):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    pts, z, X = problem
+    Kh = gp.generate_correlation(pts, 0.1, 1.5)              # plain ndarray: generator parameters unknown
+    Km = MixedCorrelation(Kh)
+    with pytest.raises(ValueError):
+        ProfileLikelihood.log_likelihood_der1_rho(z, X, Km, 0.5)
+    Km.set_kernel(pts, 0.1, 1.5)
+    a = ProfileLikelihood.log_likelihood_der1_rho(z, X, Km, 0.5)
+    Kd = MixedCorrelation(gp.generate_correlation(pts, 0.1, 1.5, device=True))
+    assert rel(a, ProfileLikelihood.log_likelihood_der1_rho(z, X, Kd, 0.5)) <= 1e-12
+
+
+def test_gaussian_process_train_profiled(gp, golden_likelihood):
+    g = golden_likelihood
+    pts, z, X = g['points'], g['z'], g['X']
+    nu, rho = g['cases'][1]
+    K = gp.generate_correlation(pts, rho, nu)
+    res = gp.GaussianProcess(X, K, likelihood_method='profiled').train(z)
+    ref = g['c1_eigenvalue_root']
+    assert rel([res['sigma'], res['sigma0'], res['eta']], ref) <= 1e-7
+
+
+# ------------------------------------------------------------------ full size (BASELINE config 2): properties
+def test_full_size_n20k_properties(gp):
+    """n = 20 000, nu = 2.5, rho = 0.1 (BASELINE.json configs[1]): size-independent identities instead of the oracle.
+    (a) solve residual ||Kn x - b|| / ||b||, (b) tr(Kn^-1 Kn) = n via tr Kn^-1 K = n - eta tr Kn^-1 with the SpMV-free
+    identity z^T M K M z + eta z^T M^2 z = z^T M z, (c) d l/d eta against a central difference of l."""
+    from oracle import data_utilities as du
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood, _fused
+    n = 20000
+    numpy.random.seed(0)
+    pts = numpy.random.rand(n, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    Km = MixedCorrelation(gp.generate_correlation(pts, 0.1, 2.5, device=True))
+    eta = 0.1
+    x = Km.solve(eta, z)
+    r = Km.dot(eta, x) - z
+    assert numpy.linalg.norm(r) / numpy.linalg.norm(z) <= 1e-10
+    q = _fused.evaluate(z, X, Km, eta, traceinv=True, drho=True)
+    assert abs(q.zMKMz + eta * q.zM2z - q.zMz) <= 1e-9 * abs(q.zMz)        # M Kn M = M
+    assert q.trace_Kninv > 0 and q.trace_Kninv2 > 0
+    assert abs(q.trace_Kninv - Km.traceinv(eta)) <= 1e-10 * q.trace_Kninv     # ||inv L||_F^2 == tr of explicit inverse
+    h = 1e-4
+    lp1 = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta * (1 + h), with_rho=False)[0]
+    lp0 = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta * (1 - h), with_rho=False)[0]
+    _, deta, drho = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
+    assert abs((lp1 - lp0) / (2 * h * eta) - deta) <= 1e-5 * abs(deta)
+    assert numpy.isfinite(drho)
