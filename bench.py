@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the GP log-likelihood hot path on B200.
+
+Metric (BASELINE.json): log-likelihood + gradient evaluations per second, dense Matern nu = 2.5, n = 20 000 random 2-D
+points (configs[1]), FP64. One STEP = one evaluation at a new (eta, rho): Matern correlation generation for that rho,
+one blocked Cholesky of K + eta I, the solves for [X z], the inverse for the traces, and every reduction needed for
+l^, d l^/d eta and d l^/d rho (n^3 flop).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (under torchrun for N > 1: one rank per
+                                                                GPU, independent (eta, rho) cells per rank, weak scaling,
+                                                                no data-path collective; results all-gathered at the end)
+  python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port; the
+                                                                reference's likelihood code is Python + imate and cannot
+                                                                travel) on the host cores, bounded sample
+Prints ONE JSON line on rank 0.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'gaussian-process-param-estimation_b200'))
+
+METRIC = 'loglik+grad evals/s (Matern nu=2.5 dense n=20k, FP64)'
+UNIT = 'evals/s'
+NU = 2.5
+ETAS = [1e-2, 1e-1, 1.0, 10.0]
+
+
+def cell(idx):
+    """(eta, rho) of the idx-th evaluation: eta cycles over the C2 set, rho moves every step so that the correlation
+    matrix really is regenerated each time."""
+    return ETAS[idx % 4], 0.1 * (1.0 + 0.01 * (idx % 11))
+
+
+def make_inputs(n):
+    """SURVEY 8d synthetic inputs: points = rand(n, 2) with seed 0; z = sin(pi x) + sin(pi y) + 0.2 randn with seed 31
+    (examples/_utilities/data_utilities.py:93-101); X = monomials of total degree <= 2 (m = 6, :150-173)."""
+    numpy.random.seed(0)
+    pts = numpy.random.rand(n, 2)
+    z = numpy.sin(numpy.pi * pts[:, 0]) + numpy.sin(numpy.pi * pts[:, 1])
+    numpy.random.seed(31)
+    z = z + 0.2 * numpy.random.randn(n)
+    x, y = pts[:, 0], pts[:, 1]
+    X = numpy.stack([numpy.ones(n), x, x * x, y, x * y, y * y], axis=1)
+    return pts, z, X
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------- CPU baseline
+def cpu_sample(n_sample, n_full, repeats=1):
+    """Times the reference's CPU algorithm for ONE loglik+grad evaluation (correlation
+    generation + DirectLikelihood.log_likelihood + log_likelihood_jacobian, Cholesky method, i.e. 4 dposv solves, one
+    logdet, one explicit-inverse trace) at n_sample points and extrapolates to n_full with n^2 (generation) and n^3
+    (factorisations). Generation uses the compiled reference (oracle/_ref, OpenMP) when it is there."""
+    from oracle import likelihood as L
+    from oracle import matern
+    pts, z, X = make_inputs(n_sample)
+    kind = 'port'
+    gen = lambda: matern.generate_dense_correlation(pts, numpy.array([0.1, 0.1]), NU)   # noqa: E731
+    try:
+        from oracle import ref_loader
+        cy = ref_loader.load_cython()
+        gen = lambda: cy.generate_dense_correlation(pts, numpy.array([0.1, 0.1]), NU, False)  # noqa: E731
+        kind = 'port (likelihood) + reference (compiled Cython generator)'
+    except Exception:  # noqa: BLE001
+        pass
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        K = gen()
+        t1 = time.perf_counter()
+        Km = L.MixedCorrelation(K, 'cholesky')
+        L.DirectLikelihood.log_likelihood(z, X, Km, False, [0.3, 0.3 * numpy.sqrt(0.1)])
+        L.DirectLikelihood.log_likelihood_jacobian(z, X, Km, False, [0.3, 0.3 * numpy.sqrt(0.1)])
+        t2 = time.perf_counter()
+        cur = (t1 - t0, t2 - t1)
+        best = cur if best is None or sum(cur) < sum(best) else best
+    s = n_full / float(n_sample)
+    t_full = best[0] * s ** 2 + best[1] * s ** 3
+    cores = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [i.get('num_threads') for i in threadpool_info() if i.get('user_api') == 'blas']
+        cores = max(blas) if blas else cores
+    except Exception:  # noqa: BLE001
+        pass
+    return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': 'one evaluation (Matern generation %.2fs + DirectLikelihood l and jacobian %.2fs, Cholesky method) '
+                      'at n=%d, extrapolated to n=%d with n^2 / n^3' % (best[0], best[1], n_sample, n_full),
+            'seconds_per_eval_extrapolated': t_full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n = int(os.environ.get('GP_BENCH_N', '20000'))
+    ns = int(os.environ.get('GP_BENCH_CPU_N', '3000'))
+    for _ in range(args.warmup):
+        cpu_sample(min(ns, 1000), n)
+    t0 = time.perf_counter()
+    vals = [cpu_sample(ns, n) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    v = statistics.mean([x['value'] for x in vals])
+    base = dict(vals[0])
+    base['value'] = v
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 / v, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: dense Matern nu=2.5, n=%d random 2-D points, m=6 (Poly-2)' % n,
+                       'sample_wall_s': wall},
+            'cpu_baseline': base,
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    from gaussian_proc import _device as dev
+    from gaussian_proc import generate_correlation
+    from gaussian_proc._dense import DeviceCorrelation, DenseEngine, FLAG_TRACEINV, FLAG_INVERSE, FLAG_DRHO
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    lib = dev.lib
+
+    n = int(os.environ.get('GP_BENCH_N', '20000'))
+    pts, z, X = make_inputs(n)
+    m = X.shape[1]
+    p = m + 1
+    npad = dev.padded_size(n)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    # ---- resident inputs -------------------------------------------------------------------------------------
+    dpts = torch.from_numpy(pts).cuda()
+    Kbuf = torch.empty((npad, npad), dtype=torch.float64, device='cuda')
+    Kdev = DeviceCorrelation(n, Kbuf, points=dpts, correlation_scale=numpy.array([0.1, 0.1]), nu=NU)
+    eng = DenseEngine(Kdev)
+    R, _ = eng.pad_rhs(numpy.c_[X, z])
+    flags = FLAG_TRACEINV | FLAG_INVERSE | FLAG_DRHO
+    results = []
+
+    def step(idx):
+        eta, rho = cell(idx)
+        scale = numpy.array([rho, rho])
+        Kdev.correlation_scale = scale
+        dev.check(lib.gp_matern_dense(P(dpts), n, 2, dev.host_ptr(scale), NU, P(Kbuf), npad, None, dev.stream_ptr()),
+                  'gp_matern_dense')
+        results.append(eng.fused(eta, R, p, flags))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(w * world + rank)
+    results.clear()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.gp_gemm_profile_enable(1)
+    launches0 = lib.gp_launch_count()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step((args.warmup + s) * world + rank)
+    stacked = torch.stack(results)
+    if world > 1:
+        gathered = [torch.empty_like(stacked) for _ in range(world)]
+        dist.all_gather(gathered, stacked)        # the only collective: the per-cell results
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = int(lib.gp_launch_count() - launches0)
+    gm, gf, gl = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.gp_gemm_profile_read(ctypes.byref(gm), ctypes.byref(gf), ctypes.byref(gl))
+    lib.gp_gemm_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    host = stacked.cpu().numpy()
+    if not numpy.isfinite(host[:, :4]).all() or (host[:, 4] != 0).any():
+        raise SystemExit('bench.py: non-finite result or Cholesky breakdown in the timed region')
+
+    value = args.steps * world / (ms * 1e-3)
+
+    # ---- FP64 GEMM ceiling measured in-run (MEASURED_PEAKS.json carries no FP64 entry) --------------------------
+    a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+    b = torch.randn(8192, 8192, dtype=torch.float64, device='cuda')
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(3):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(); torch.matmul(a, b); t1.record(); torch.cuda.synchronize()
+        best = min(best, t0.elapsed_time(t1))
+    peak_tflops = 2 * 8192.0 ** 3 / best * 1e-9
+    del a, b
+
+    gemm_ms_per_step = gm.value / args.steps
+    alg_flops = float(n) ** 3
+    achieved = alg_flops / (gemm_ms_per_step * 1e-3) * 1e-12
+    roofline = {'bound': 'tensor', 'kernel': 'gp::dgemm_dmma_kernel (DMMA.8x8x4, FP64 tensor pipe)',
+                'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
+                'traffic': None,
+                'peak_source': 'in-run cuBLAS DGEMM 8192^3 (torch.matmul f64, best of 3); MEASURED_PEAKS.json has no FP64 '
+                               'entry; raw DMMA issue peak measured by tools/microbench.cu = 37.1 TFLOP/s',
+                'algorithmic_flops_per_step': alg_flops,
+                'executed_tile_tflops': gf.value / (gm.value * 1e-3) * 1e-12,
+                'gemm_launches_per_step': gl.value / args.steps,
+                'gemm_ms_per_step': gemm_ms_per_step, 'gemm_share_of_step': gemm_ms_per_step / (ms / args.steps),
+                'step_tflops': alg_flops / (ms / args.steps * 1e-3) * 1e-12}
+
+    # ---- end-to-end through the public API with host (pinned) buffers ----------------------------------------------
+    del eng, Kdev, Kbuf, results, stacked
+    torch.cuda.empty_cache()
+    pin = lambda a: torch.from_numpy(numpy.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    hp, hz, hX = pin(pts), pin(z), pin(X)
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step(idx):
+        eta, rho = cell(idx)
+        K = generate_correlation(hp, rho, NU, device=True)                 # H2D: points
+        Km = MixedCorrelation(K)
+        return ProfileLikelihood.log_likelihood_and_gradient(hz, hX, Km, eta)   # H2D: [X z]; D2H: out[]
+    e2e_step(rank)
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        r = e2e_step((1 + s) * world + rank)
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {'value': e2e_steps * world / float(e2e_s.item()), 'unit': UNIT, 'steps': e2e_steps,
+           'h2d_bytes_per_step': int(hp.nbytes + npad * p * 8), 'd2h_bytes_per_step': int((8 + 3 * p * p) * 8),
+           'api': 'generate_correlation(points, rho, nu, device=True) -> MixedCorrelation(K) -> '
+                  'ProfileLikelihood.log_likelihood_and_gradient(z, X, K_mixed, eta)',
+           'last_result': [float(v) for v in r]}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'configs[1]: dense Matern nu=2.5, n=%d random 2-D points (seed 0), m=6 (Poly-2 basis), '
+                                       'one (eta, rho) cell per step per GPU, eta in {1e-2,1e-1,1,10}, rho ~ 0.1' % n,
+                           'l2': 'inputs larger than L2 (K = %.1f GB per evaluation)' % (npad * npad * 8e-9),
+                           'parallelism': 'independent cells per GPU (replicas), results all-gathered'},
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
+        if world == 1 and not args.no_cpu:
+            line['cpu_baseline'] = cpu_sample(int(os.environ.get('GP_BENCH_CPU_N', '3000')), n)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

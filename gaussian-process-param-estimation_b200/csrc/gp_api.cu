@@ -17,4 +17,13 @@ int gp_dgemm_f64(int at, int bt, double* C, int64_t ldc, const double* A, int64_
                             (cudaStream_t)stream);
 }
 
+unsigned long long gp_launch_count(void) { return gp::g_launch_count; }
+
+int gp_gemm_profile_enable(int on) { return gp::profile_enable(on); }
+
+int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launches_host) {
+    if (!ms_host || !flops_host || !launches_host) return -1;
+    return gp::profile_read(ms_host, flops_host, launches_host);
+}
+
 }  // extern "C"

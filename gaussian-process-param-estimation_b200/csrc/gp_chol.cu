@@ -243,6 +243,7 @@ int gp_shift_copy(const double* K, int64_t n, int64_t npad, double eta, double* 
     if (!K || !A || n <= 0 || npad != gp_padded_size(n)) return -1;
     dim3 grid((unsigned)(npad / 128), (unsigned)(npad / 128));
     shift_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(K, (int)n, (int)npad, eta, A);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -267,6 +268,7 @@ int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, vo
             double* Ajj = A + (int64_t)j * npad + j;
             double* Lj = linv + (int64_t)(j / DB) * DB * DB;
             chol_diag_block_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(Ajj, npad, Lj, info_dev, j, (int)n);
+            GP_COUNT(1);
             GP_LAUNCH_CHECK();
             int below = N - (j + DB);
             if (below <= 0) continue;
@@ -295,6 +297,7 @@ int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, vo
 int gp_logdet_from_chol(const double* L, int64_t n, int64_t npad, double* out_dev, void* stream) {
     if (!L || !out_dev || n <= 0 || n > npad) return -1;
     logdet_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(L, (int)n, npad, out_dev);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -309,6 +312,7 @@ int gp_potrs_f64(const double* L, int64_t npad, const void* potrf_ws, double* B,
         double* Bj = B + (int64_t)j * ldb;
         diag_apply_kernel<false><<<1, 256, 0, s>>>(linv + (int64_t)b * DB * DB, Bj, nr, ldb);
         int below = N - (j + DB);
+        GP_COUNT(below > 0 ? 2 : 1);
         if (below > 0) {
             if (nr <= 8) launch_fwd<8>(L, npad, j + DB, j, Bj, B, ldb, below, nr, s);
             else launch_fwd<16>(L, npad, j + DB, j, Bj, B, ldb, below, nr, s);
@@ -318,6 +322,7 @@ int gp_potrs_f64(const double* L, int64_t npad, const void* potrf_ws, double* B,
         int j = b * DB;
         double* Bj = B + (int64_t)j * ldb;
         diag_apply_kernel<true><<<1, 256, 0, s>>>(linv + (int64_t)b * DB * DB, Bj, nr, ldb);
+        GP_COUNT(j > 0 ? 2 : 1);
         if (j > 0) {
             if (nr <= 8) launch_bwd<8>(L, npad, j, Bj, B, ldb, nr, s);
             else launch_bwd<16>(L, npad, j, Bj, B, ldb, nr, s);
@@ -337,6 +342,7 @@ int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws,
     cudaStream_t s = (cudaStream_t)stream;
     int nb = (int)(npad / DB);
     place_diag_inverse_kernel<<<nb, 256, 0, s>>>((const double*)potrf_ws, W, npad);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return trtri_rec(L, W, npad, 0, nb, (double*)ws, s);
 }

@@ -19,6 +19,10 @@
 
 namespace gp {
 
+// number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+#define GP_COUNT(k) (gp::g_launch_count += (unsigned long long)(k))
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

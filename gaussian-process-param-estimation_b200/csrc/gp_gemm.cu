@@ -10,8 +10,33 @@
 // Triangular operands are exploited by restricting each tile's k-range, never by element masks.
 #include "gp_common.cuh"
 #include "gp_internal.h"
+#include <vector>
 
 namespace gp {
+
+unsigned long long g_launch_count = 0;
+
+// optional per-launch timing of the DMMA GEMM (bench.py's roofline leg): events around every launch
+struct GemmProfile {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    double flops = 0.0;       // executed tile flops (2 * 128 * 128 * k per computed tile)
+    long long launches = 0;
+};
+static GemmProfile g_prof;
+
+static double tile_flops(int tiles_m, int tiles_n, int K, int krange, int tmask) {
+    double kt = 0.0;  // sum over computed tiles of their k extent
+    for (int tm = 0; tm < tiles_m; ++tm) {
+        int ncols = (tmask == TM_LOWER) ? (tm + 1 < tiles_n ? tm + 1 : tiles_n) : tiles_n;
+        if (krange == KR_FULL) kt += (double)ncols * K;
+        else if (krange == KR_A_LOWER) kt += (double)ncols * ((tm + 1) * 128 < K ? (tm + 1) * 128 : K);
+        else if (krange == KR_TN_LOWER) kt += (double)ncols * (K - (tm * 128 < K ? tm * 128 : K));
+        else for (int tn = 0; tn < ncols; ++tn) kt += (double)(K - (tn * 128 < K ? tn * 128 : K));
+    }
+    return 2.0 * 128.0 * 128.0 * kt;
+}
 
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
 constexpr int WARPS_N = 4, WM = 64, WN = 32;
@@ -159,8 +184,23 @@ static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, con
     }
     int tiles_m = M / BM, tiles_n = N / BN;
     if (tiles_m == 0 || tiles_n == 0) return 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof.on) {
+        while (g_prof.pool.size() < g_prof.used + 2) {
+            cudaEvent_t e;
+            GP_CUDA_CHECK(cudaEventCreate(&e));
+            g_prof.pool.push_back(e);
+        }
+        e0 = g_prof.pool[g_prof.used++];
+        e1 = g_prof.pool[g_prof.used++];
+        g_prof.flops += tile_flops(tiles_m, tiles_n, K, krange, tmask);
+        g_prof.launches++;
+        cudaEventRecord(e0, stream);
+    }
     dgemm_dmma_kernel<AT, BT><<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM, stream>>>(
         C, ldc, A, lda, B, ldb, tiles_m, tiles_n, K, alpha, beta, krange, tmask);
+    if (e1) cudaEventRecord(e1, stream);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -175,6 +215,29 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
     if (at == 1 && bt == 1) return launch_inst<1, 1>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     if (at == 1 && bt == 0) return launch_inst<1, 0>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     return -4;
+}
+
+int profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    g_prof.flops = 0.0;
+    g_prof.launches = 0;
+    return 0;
+}
+
+// synchronises the device; returns summed GEMM kernel milliseconds, executed flops and launch count since enable
+int profile_read(double* ms, double* flops, long long* launches) {
+    GP_CUDA_CHECK(cudaDeviceSynchronize());
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        float t = 0.f;
+        GP_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.pool[i], g_prof.pool[i + 1]));
+        total += t;
+    }
+    *ms = total;
+    *flops = g_prof.flops;
+    *launches = g_prof.launches;
+    return 0;
 }
 
 }  // namespace gp

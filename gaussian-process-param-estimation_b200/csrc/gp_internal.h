@@ -25,4 +25,7 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
                  const double* B, int64_t ldb, int M, int N, int K, double alpha, double beta,
                  int krange, int tmask, cudaStream_t stream);
 
+int profile_enable(int on);
+int profile_read(double* ms, double* flops, long long* launches);
+
 }  // namespace gp

@@ -299,6 +299,7 @@ static int gram(const double* A, const double* B, int nrows, int p, int64_t ld, 
     int parts = 296;
     gram_partial_kernel<<<parts, 256, 0, s>>>(A, B, nrows, p, ld, partial);
     sum_partials_kernel<<<(p * p + 127) / 128, 128, 0, s>>>(partial, parts, p * p, out);
+    GP_COUNT(2);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -310,10 +311,12 @@ static int grad_reductions(const double* Ainv, int n, int npad, const double* pt
     if (with_dk) {
         trace_tiles_kernel<MODE, true><<<tiles, 256, 0, s>>>(Ainv, n, npad, pts, d, mp, w.tr);
         dk_apply_kernel<MODE><<<(n + 63) / 64, 256, 0, s>>>(pts, n, d, mp, w.S, p, p, w.V);
+        GP_COUNT(2);
         GP_LAUNCH_CHECK();
         return gram(w.S, w.V, n, p, p, w.gram, outQ, s);
     }
     trace_tiles_kernel<MODE, false><<<tiles, 256, 0, s>>>(Ainv, n, npad, pts, d, mp, w.tr);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -327,6 +330,7 @@ extern "C" {
 int gp_symm_skinny(const double* K, int64_t n, int64_t npad, const double* X, int64_t p, double* Y, void* stream) {
     if (!K || !X || !Y || n <= 0 || npad != gp_padded_size(n) || p <= 0 || p > MAXP) return -1;
     symm_skinny_kernel<<<(unsigned)(npad / 32), 256, 0, (cudaStream_t)stream>>>(K, (int)n, (int)npad, X, (int)p, Y);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -351,6 +355,7 @@ int gp_inverse_traces(const double* M, int64_t n, int64_t npad, int kind, double
     if (kind == 0) frob_lower_kernel<<<dim3(T, T), 256, 0, s>>>(M, (int)n, (int)npad, frob);
     else trace_tiles_kernel<MAT_05, false><<<tiles, 256, 0, s>>>(M, (int)n, (int)npad, nullptr, 0, mp, tr);
     finalize_out_kernel<<<1, 256, 0, s>>>(out_dev, misc, tr, tiles, frob, T * T, (const int*)(misc + 2), kind == 0 ? 1 : 2);
+    GP_COUNT(2);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -412,9 +417,11 @@ int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, i
         if (rc) return rc;
     } else if (flags & 1) {
         frob_lower_kernel<<<dim3(T, T), 256, 0, s>>>(W, N, NP, w.frob);
+        GP_COUNT(1);
         GP_LAUNCH_CHECK();
     }
     finalize_out_kernel<<<1, 256, 0, s>>>(out, w.logdet, w.tr, T * (T + 1) / 2, w.frob, T * T, w.info, flags);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }

@@ -125,6 +125,7 @@ static int launch_mode(const double* pts, int n, int d, int npad, double* K, dou
         GP_CUDA_CHECK(cudaFuncSetAttribute(matern_dense_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         matern_dense_kernel<MODE, false><<<tiles, 256, smem, s>>>(pts, n, d, npad, K, nullptr, mp);
     }
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }

@@ -31,6 +31,13 @@ extern "C" {
 int gp_abi_version(void);
 /* npad for a matrix of size n */
 int64_t gp_padded_size(int64_t n);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+unsigned long long gp_launch_count(void);
+/* Measurement hooks for bench.py's roofline leg: while enabled, every DMMA GEMM launch is bracketed by CUDA events on
+ * its own stream; gp_gemm_profile_read synchronises the device and returns the summed kernel milliseconds, the tile
+ * flops those launches executed and their count (host pointers). */
+int gp_gemm_profile_enable(int on);
+int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launches_host);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Correlation generation  (reference: generate_correlation/_kernels.pyx:17-136,

@@ -1,0 +1,103 @@
+"""CPU tests of the host-side logic of the product: the root finder against the reference-pinned oracle restatement,
+and the (m+1)x(m+1) algebra of _fused.FusedQuantities fed with device outputs simulated in NumPy."""
+
+import numpy
+import pytest
+
+from oracle import likelihood as L
+from oracle import matern
+from oracle import data_utilities as du
+
+
+def test_bracketing_matches_oracle_on_all_branches():
+    from gaussian_proc._likelihood._root_finding import find_interval_with_sign_change as prod
+    fns = [lambda x: x - 0.3,                       # immediate sign change
+           lambda x: (x - 0.6) ** 2 - 0.01,         # midpoint brackets
+           lambda x: (x - 2.5) * 0.1,               # extrapolate right
+           lambda x: -(x + 1.7) * 0.2,              # extrapolate left
+           lambda x: x * x + 1.0,                   # never
+           lambda x: (x - 0.45) ** 2 + 0.01]        # shrink, never
+    for f in fns:
+        calls_p, calls_o = [], []
+        rp = prod(lambda x: (calls_p.append(x), f(x))[1], [0.0, 1.0], 3)
+        ro = L.find_interval_with_sign_change(lambda x: (calls_o.append(x), f(x))[1], [0.0, 1.0], 3)
+        assert rp[0] == ro[0] and rp[1] == ro[1] and rp[2] == ro[2]
+        assert calls_p == calls_o                   # same evaluation sequence = same number of factorizations
+
+
+def test_chandrupatla_matches_oracle():
+    from gaussian_proc._likelihood._root_finding import chandrupatla_method as prod
+    fns = [(lambda x: numpy.cos(x) - x, [0.0, 1.0]), (lambda x: x ** 3 - 2 * x - 5, [2.0, 3.0]),
+           (lambda x: numpy.tanh(5 * (x - 0.123)), [-4.0, 3.0]), (lambda x: numpy.exp(-x) - 1e-3, [-4.0, 9.0])]
+    for f, br in fns:
+        vals = [f(br[0]), f(br[1])]
+        cp, co = [], []
+        rp = prod(lambda x: (cp.append(x), f(x))[1], br, vals, eps_m=1e-6, eps_a=1e-6, maxiter=100)
+        ro = L.chandrupatla_method(lambda x: (co.append(x), f(x))[1], br, vals, eps_m=1e-6, eps_a=1e-6, maxiter=100)
+        assert cp == co and rp['root'] == ro['root'] and rp['iterations'] == ro['iterations']
+        assert abs(f(rp['root'])) < 1e-4
+    with pytest.raises(AssertionError):
+        prod(lambda x: x * x + 1, [0.0, 1.0], None)
+    r = prod(lambda x: x - 0.25, [0.0, 1.0], None, eps_m=1e-12, eps_a=1e-12)
+    assert abs(r['root'] - 0.25) < 1e-10
+
+
+def _simulate_device_out(K, dK, X, z, eta):
+    """What gp_loglik_dense returns (include/gpgp.h), computed in NumPy."""
+    n, m = X.shape
+    p = m + 1
+    Kn = K + eta * numpy.eye(n)
+    Kinv = numpy.linalg.inv(Kn)
+    R = numpy.c_[X, z]
+    S = Kinv @ R
+    out = numpy.zeros(8 + 3 * p * p)
+    out[0] = numpy.linalg.slogdet(Kn)[1]
+    out[1] = numpy.trace(Kinv)
+    out[2] = numpy.sum(Kinv * Kinv)
+    out[3] = numpy.sum(Kinv * dK)
+    out[8:8 + p * p] = (R.T @ S).ravel()
+    out[8 + p * p:8 + 2 * p * p] = (S.T @ S).ravel()
+    out[8 + 2 * p * p:] = (S.T @ dK @ S).ravel()
+    return out
+
+
+def test_fused_algebra_reproduces_reference_formulas():
+    from gaussian_proc._likelihood._fused import FusedQuantities
+    numpy.random.seed(2)
+    pts = numpy.random.rand(150, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    n, m = X.shape
+    K = matern.generate_dense_correlation(pts, 0.1, 1.5)
+    dK = matern.matern_derivative_rho(pts, 0.1, 1.5)
+    Ko = L.MixedCorrelation(K, 'cholesky')
+    for sigma, sigma0 in [(0.3, 0.2), (0.7, 0.1)]:
+        eta = (sigma0 / sigma) ** 2
+        q = FusedQuantities(_simulate_device_out(K, dK, X, z, eta), n, m, eta, 7)
+        # direct likelihood and jacobian, assembled exactly as gaussian_proc/_likelihood/_direct_likelihood.py does
+        lp = -0.5 * (n - m) * numpy.log(2 * numpy.pi) - 0.5 * (n * numpy.log(sigma ** 2) + q.logdet_Kn) \
+            - 0.5 * numpy.log(numpy.linalg.det(q.B / sigma ** 2)) - 0.5 * q.zMz / sigma ** 2
+        assert abs(lp - L.DirectLikelihood.log_likelihood(z, X, Ko, False, [sigma, sigma0])) <= 1e-10 * abs(lp)
+        trace_M = q.trace_M / sigma ** 2
+        jac = [-0.5 * ((n - m) / sigma ** 2 - eta * trace_M) + 0.5 * q.zMKMz / sigma ** 4,
+               -0.5 * trace_M + 0.5 * q.zM2z / sigma ** 4]
+        ref = L.DirectLikelihood.log_likelihood_jacobian(z, X, Ko, False, [sigma, sigma0])
+        assert numpy.max(numpy.abs(jac - ref)) <= 1e-9 * numpy.max(numpy.abs(ref))
+        drho = -0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sigma ** 2
+        ref = L.DirectLikelihood.log_likelihood_der1_rho(z, X, Ko, dK, [sigma, sigma0])
+        assert abs(drho - ref) <= 1e-9 * abs(ref)
+        # profile quantities
+        sig2 = q.zMz / (n - m)
+        d = -0.5 * (q.trace_M - q.zM2z / sig2)
+        assert abs(d - L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(eta))) <= 1e-9 * abs(d)
+        ref = L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dK, eta)
+        assert abs(-0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sig2 - ref) <= 1e-9 * abs(ref)
+
+
+def test_bench_inputs_equal_reference_generators():
+    import bench
+    pts, z, X = bench.make_inputs(400)
+    numpy.random.seed(0)
+    p2 = numpy.random.rand(400, 2)
+    assert (pts == p2).all() and (z == du.generate_data(p2, 0.2)).all()
+    assert numpy.max(numpy.abs(X - du.generate_basis_functions(p2, 2))) == 0.0
