@@ -20,42 +20,157 @@ constexpr int DIAG_THREADS = 512;
 constexpr int OUTER_NB = 512;
 
 // Factor the 128x128 diagonal block at `Ajj` (lower, in place) and write inv(L_jj) (lower, zero above) to `Linv`.
-// Shared array S[128][129]: lower triangle holds A/L, W[i][c] (c <= i) lives at S[c][i+1] (strict upper).
+//
+// Shared array S[128][129]: the lower triangle holds A / L; W = inv(L) is kept transposed in the strict upper
+// triangle (W[i][c], c <= i, lives at S[c][i+1]) so that one 132 KB array serves both. Algorithm, 32-wide sub-blocks:
+//   for each block column J: (1) warp 0 factors the 32x32 diagonal sub-block in registers (lane = row) with
+//   warp shuffles, (2) one thread per row below solves its 32 unknowns against that sub-block (axpy form, the
+//   L_D entries are shared-memory broadcasts), (3) all threads apply the rank-32 update to the trailing part with
+//   4x4 register micro-tiles.  Then inv(L): (4) four warps invert the four diagonal sub-blocks, (5) the
+//   off-diagonal blocks follow by block distance d = 1, 2, 3:  W_IJ = -inv(L_II) * sum_K L_IK W_KJ.
+constexpr int SB = 32;
+constexpr int TPITCH = SB + 1;
+
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0, int nvalid) {
-    extern __shared__ double S[];
+    extern __shared__ double S[];                  // [128][129]
+    double* dinv = S + DB * DPITCH;                // [128]   1 / L_ii
+    double* T = dinv + DB;                         // [3][32][33] scratch for the inverse assembly
     __shared__ int bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = DIAG_THREADS / 32;
     if (tid == 0) bad = 0;
     for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
         int i = idx >> 7, k = idx & 127;
-        if (k <= i) S[i * DPITCH + k] = Ajj[(int64_t)i * lda + k];
-        else S[i * DPITCH + k + 0] = 0.0;  // W region (shifted by one column below) starts at zero
+        S[i * DPITCH + k] = (k <= i) ? Ajj[(int64_t)i * lda + k] : 0.0;
     }
     if (tid < DB) S[tid * DPITCH + DB] = 0.0;
     __syncthreads();
 
-    for (int j = 0; j < DB; ++j) {
-        double ajj = S[j * DPITCH + j];
-        if (!(ajj > 0.0)) {  // also catches NaN
-            if (tid == 0 && !bad) { bad = 1; if (j0 + j < nvalid) atomicCAS(info, 0, j0 + j + 1); }
+    for (int J = 0; J < DB / SB; ++J) {
+        const int J0 = J * SB;
+        // ---- (1) 32x32 diagonal sub-block: lane = row, registers hold the row, columns broadcast by shuffle
+        if (warp == 0) {
+            double a[SB];
+            const int row = J0 + lane;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) a[k] = S[row * DPITCH + J0 + k];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                double ajj = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(ajj > 0.0)) {  // also catches NaN
+                    if (lane == 0 && !bad) { bad = 1; if (j0 + J0 + j < nvalid) atomicCAS(info, 0, j0 + J0 + j + 1); }
+                }
+                double inv = rsqrt(ajj);
+                double lj = (lane == j) ? ajj * inv : a[j] * inv;   // l_ij for lanes i >= j
+                a[j] = lj;
+                if (lane == j) dinv[J0 + j] = inv;
+#pragma unroll
+                for (int k = j + 1; k < SB; ++k) {
+                    double lk = __shfl_sync(0xffffffffu, lj, k);
+                    a[k] -= lj * lk;                                  // meaningful for lanes i >= k
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                if (k <= lane) S[row * DPITCH + J0 + k] = a[k];
         }
-        double d = sqrt(ajj), inv = 1.0 / d;
-        __syncthreads();  // everyone has read the pivot
-        // phase A: scale column j of L (rows > j), row j of W (cols < j); set L_jj, W_jj
-        for (int i = j + 1 + tid; i < DB; i += DIAG_THREADS) S[i * DPITCH + j] *= inv;
-        for (int c = tid; c < j; c += DIAG_THREADS) S[c * DPITCH + j + 1] *= inv;
-        if (tid == 0) { S[j * DPITCH + j] = d; S[j * DPITCH + j + 1] = inv; }
         __syncthreads();
-        // phase B: rank-1 updates of the trailing A (cols j+1..i) and of W rows i > j (cols 0..j)
-        for (int i = j + 1 + warp; i < DB; i += NW) {
-            double lij = S[i * DPITCH + j];
-            for (int k = j + 1 + lane; k <= i; k += 32) S[i * DPITCH + k] -= lij * S[k * DPITCH + j];
-            for (int c = lane; c <= j; c += 32) S[c * DPITCH + i + 1] -= lij * S[c * DPITCH + j + 1];
+        const int r = DB - J0 - SB;   // rows below the sub-block
+        if (r == 0) break;
+        // ---- (2) panel solve, one thread per row: x = p * inv(L_D)^T in axpy form
+        if (tid < r) {
+            const int i = J0 + SB + tid;
+            double pr[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) pr[c] = S[i * DPITCH + J0 + c];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                double x = pr[c] * dinv[J0 + c];
+                pr[c] = x;
+#pragma unroll
+                for (int k = c + 1; k < SB; ++k) pr[k] -= x * S[(J0 + k) * DPITCH + J0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < SB; ++c) S[i * DPITCH + J0 + c] = pr[c];
+        }
+        __syncthreads();
+        // ---- (3) trailing rank-32 update on lower 4x4 micro-tiles
+        {
+            const int mt = r / 4, cnt = mt * (mt + 1) / 2;
+            if (tid < cnt) {
+                int mi = (int)((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f);
+                while ((mi + 1) * (mi + 2) / 2 <= tid) ++mi;
+                while (mi * (mi + 1) / 2 > tid) --mi;
+                int mk = tid - mi * (mi + 1) / 2;
+                const int i0 = J0 + SB + 4 * mi, k0 = J0 + SB + 4 * mk;
+                double acc[4][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < SB; ++c) {
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { av[e] = S[(i0 + e) * DPITCH + J0 + c]; bv[e] = S[(k0 + e) * DPITCH + J0 + c]; }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) acc[e][f] += av[e] * bv[f];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+                        if (k0 + f <= i0 + e) S[(i0 + e) * DPITCH + k0 + f] -= acc[e][f];
+            }
         }
         __syncthreads();
     }
+
+    // ---- (4) inverses of the four diagonal sub-blocks: warp J, lane = column c of inv(L_JJ)
+    if (warp < DB / SB) {
+        const int J0 = warp * SB;
+        double acc[SB];
+#pragma unroll
+        for (int i = 0; i < SB; ++i) acc[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+            double w = acc[k] * dinv[J0 + k];
+            acc[k] = w;
+#pragma unroll
+            for (int i = k + 1; i < SB; ++i) acc[i] -= S[(J0 + i) * DPITCH + J0 + k] * w;
+        }
+#pragma unroll
+        for (int i = 0; i < SB; ++i)
+            if (i >= lane) S[(J0 + lane) * DPITCH + J0 + i + 1] = acc[i];   // W[J0+i][J0+lane]
+    }
+    __syncthreads();
+    // ---- (5) off-diagonal blocks of W by block distance
+    for (int d = 1; d < DB / SB; ++d) {
+        const int nblk = DB / SB - d;
+        // T_b[i][c] = sum_{g >= 32J + c}^{32I - 1} L[32I + i][g] * W[g][32J + c]
+        for (int o = tid; o < nblk * SB * SB; o += DIAG_THREADS) {
+            int b = o >> 10, i = (o >> 5) & 31, c = o & 31;
+            int Jb = b, Ib = b + d;
+            const double* lrow = S + (Ib * SB + i) * DPITCH;
+            const double* wcol = S + (Jb * SB + c) * DPITCH + 1;
+            double sum = 0.0;
+            for (int g = Jb * SB + c; g < Ib * SB; ++g) sum += lrow[g] * wcol[g];
+            T[(b * SB + i) * TPITCH + c] = sum;
+        }
+        __syncthreads();
+        // W_IJ[i][c] = - sum_{k <= i} inv(L_II)[i][k] * T[k][c]
+        for (int o = tid; o < nblk * SB * SB; o += DIAG_THREADS) {
+            int b = o >> 10, i = (o >> 5) & 31, c = o & 31;
+            int Jb = b, Ib = b + d;
+            double sum = 0.0;
+            for (int k = 0; k <= i; ++k) sum += S[(Ib * SB + k) * DPITCH + Ib * SB + i + 1] * T[(b * SB + k) * TPITCH + c];
+            S[(Jb * SB + c) * DPITCH + Ib * SB + i + 1] = -sum;
+        }
+        __syncthreads();
+    }
+
     for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
         int i = idx >> 7, k = idx & 127;
         if (k <= i) {
@@ -202,14 +317,53 @@ __global__ void place_diag_inverse_kernel(const double* __restrict__ Linv, doubl
     for (int idx = threadIdx.x; idx < DB * DB; idx += blockDim.x) dst[(int64_t)(idx >> 7) * ldw + (idx & 127)] = src[idx];
 }
 
-// recursive inverse of the lower-triangular L over block range [lo, hi) (units of 128); T = scratch
-static int trtri_rec(const double* L, double* W, int64_t ld, int lo, int hi, double* T, cudaStream_t s) {
+// ---- helper streams (one process drives one GPU): independent sub-problems of the recursive inverse and the
+// look-ahead panel of the factorisation run beside the caller's stream, ordered with events ---------------------
+struct SidePool {
+    cudaStream_t s[3];
+    bool ready = false;
+};
+static SidePool g_side;
+
+static int side_streams_init() {
+    if (g_side.ready) return 0;
+    int lo = 0, hi = 0;
+    GP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < 3; ++i) GP_CUDA_CHECK(cudaStreamCreateWithPriority(&g_side.s[i], cudaStreamNonBlocking, hi));
+    g_side.ready = true;
+    return 0;
+}
+
+// make `to` wait for everything enqueued on `from` so far
+static int stream_order(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e;
+    GP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    GP_CUDA_CHECK(cudaEventRecord(e, from));
+    GP_CUDA_CHECK(cudaStreamWaitEvent(to, e, 0));
+    GP_CUDA_CHECK(cudaEventDestroy(e));  // released once the recorded work completes
+    return 0;
+}
+
+static int64_t trtri_need(int nb) { return (int64_t)(nb / 2) * (nb - nb / 2) * DB * DB; }
+
+// recursive inverse of the lower-triangular L over block range [lo, hi) (units of 128); T = scratch of
+// trtri_need(hi - lo) doubles. The two halves are independent: down to depth 2 the right half runs on a side stream.
+static int trtri_rec(const double* L, double* W, int64_t ld, int lo, int hi, double* T, cudaStream_t s, int depth, int slot) {
     if (hi - lo <= 1) return 0;
     int mid = lo + (hi - lo) / 2;  // first half has floor((hi-lo)/2) blocks
-    int rc = trtri_rec(L, W, ld, lo, mid, T, s);
-    if (rc) return rc;
-    rc = trtri_rec(L, W, ld, mid, hi, T, s);
-    if (rc) return rc;
+    int rc;
+    bool fork = depth < 2 && (hi - lo) >= 8;
+    double* Tr = T + trtri_need(mid - lo);
+    if (fork) {
+        cudaStream_t side = g_side.s[slot];
+        if ((rc = stream_order(s, side))) return rc;
+        if ((rc = trtri_rec(L, W, ld, mid, hi, Tr, side, depth + 1, slot == 0 ? 2 : slot))) return rc;
+        if ((rc = trtri_rec(L, W, ld, lo, mid, T, s, depth + 1, 1))) return rc;
+        if ((rc = stream_order(side, s))) return rc;
+    } else {
+        if ((rc = trtri_rec(L, W, ld, lo, mid, T, s, 2, slot))) return rc;
+        if ((rc = trtri_rec(L, W, ld, mid, hi, Tr, s, 2, slot))) return rc;
+    }
     int M = (hi - mid) * DB, N = (mid - lo) * DB;
     // T (M x N) = L21 * W11      (W11 lower: k >= n0)
     rc = launch_dgemm(0, 1, T, N, L + (int64_t)mid * DB * ld + (int64_t)lo * DB, ld,
@@ -250,45 +404,73 @@ int gp_shift_copy(const double* K, int64_t n, int64_t npad, double eta, double* 
 
 int64_t gp_potrf_workspace_bytes(int64_t npad) { return (npad / DB) * (int64_t)DB * DB * sizeof(double); }
 
+// factor one outer panel [J, Jend): diagonal blocks, panel solves and the updates that stay inside the panel
+static int factor_panel(double* A, int64_t npad, int n, int J, int Jend, double* linv, int* info_dev, int diag_smem,
+                        cudaStream_t s) {
+    const int N = (int)npad;
+    for (int j = J; j < Jend; j += DB) {
+        double* Ajj = A + (int64_t)j * npad + j;
+        double* Lj = linv + (int64_t)(j / DB) * DB * DB;
+        chol_diag_block_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(Ajj, npad, Lj, info_dev, j, n);
+        GP_COUNT(1);
+        GP_LAUNCH_CHECK();
+        int below = N - (j + DB);
+        if (below <= 0) continue;
+        double* A21 = A + (int64_t)(j + DB) * npad + j;
+        // panel solve L21 = A21 * inv(L_jj)^T  (in place: each CTA reads exactly the tile it overwrites)
+        int rc = launch_dgemm(0, 0, A21, npad, A21, npad, Lj, DB, below, DB, DB, 1.0, 0.0, KR_FULL, TM_ALL, s);
+        if (rc) return rc;
+        int ncols = Jend - (j + DB);
+        if (ncols > 0) {
+            rc = launch_dgemm(0, 0, A + (int64_t)(j + DB) * npad + (j + DB), npad, A21, npad, A21, npad, below, ncols, DB,
+                              -1.0, 1.0, KR_FULL, TM_LOWER, s);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
 int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, void* stream) {
     if (!A || !info_dev || !ws || npad <= 0 || (npad % DB) || npad > INT32_MAX || n > npad) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     double* linv = (double*)ws;
     static bool configured = false;
-    const int diag_smem = DB * DPITCH * sizeof(double);
+    const int diag_smem = (DB * DPITCH + DB + 3 * SB * TPITCH) * sizeof(double);
     if (!configured) {
         GP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         configured = true;
     }
+    int rc = side_streams_init();
+    if (rc) return rc;
+    cudaStream_t ps = g_side.s[0];  // high-priority panel stream (look-ahead)
     GP_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
     const int N = (int)npad;
+    // Right-looking with look-ahead 1: after panel J, the trailing update is split into (i) the block column of the
+    // next panel and (ii) the rest; panel J+1 is factored on the panel stream while (ii) still runs on `s`.
+    if ((rc = factor_panel(A, npad, (int)n, 0, OUTER_NB < N ? OUTER_NB : N, linv, info_dev, diag_smem, s))) return rc;
     for (int J = 0; J < N; J += OUTER_NB) {
         int Jend = (J + OUTER_NB < N) ? J + OUTER_NB : N;
-        for (int j = J; j < Jend; j += DB) {
-            double* Ajj = A + (int64_t)j * npad + j;
-            double* Lj = linv + (int64_t)(j / DB) * DB * DB;
-            chol_diag_block_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(Ajj, npad, Lj, info_dev, j, (int)n);
-            GP_COUNT(1);
-            GP_LAUNCH_CHECK();
-            int below = N - (j + DB);
-            if (below <= 0) continue;
-            double* A21 = A + (int64_t)(j + DB) * npad + j;
-            // panel solve L21 = A21 * inv(L_jj)^T  (in place: each CTA reads exactly the tile it overwrites)
-            int rc = launch_dgemm(0, 0, A21, npad, A21, npad, Lj, DB, below, DB, DB, 1.0, 0.0, KR_FULL, TM_ALL, s);
-            if (rc) return rc;
-            int ncols = Jend - (j + DB);
-            if (ncols > 0) {
-                rc = launch_dgemm(0, 0, A + (int64_t)(j + DB) * npad + (j + DB), npad, A21, npad, A21, npad, below, ncols,
-                                  DB, -1.0, 1.0, KR_FULL, TM_LOWER, s);
-                if (rc) return rc;
-            }
-        }
         int rows = N - Jend;
-        if (rows > 0) {
-            const double* P = A + (int64_t)Jend * npad + J;
-            int rc = launch_dgemm(0, 0, A + (int64_t)Jend * npad + Jend, npad, P, npad, P, npad, rows, rows, Jend - J, -1.0,
-                                  1.0, KR_FULL, TM_LOWER, s);
+        if (rows <= 0) break;
+        int K = Jend - J;
+        int nextw = (OUTER_NB < rows) ? OUTER_NB : rows;           // width of panel J+1
+        const double* P = A + (int64_t)Jend * npad + J;              // L[Jend:, J:Jend]
+        // (i) block column of the next panel: rows x nextw, lower-masked
+        rc = launch_dgemm(0, 0, A + (int64_t)Jend * npad + Jend, npad, P, npad, P, npad, rows, nextw, K, -1.0, 1.0, KR_FULL,
+                          TM_LOWER, s);
+        if (rc) return rc;
+        int rest = rows - nextw;
+        if (rest > 0) {
+            if ((rc = stream_order(s, ps))) return rc;
+            if ((rc = factor_panel(A, npad, (int)n, Jend, Jend + nextw, linv, info_dev, diag_smem, ps))) return rc;
+            // (ii) the remaining trailing matrix
+            const double* P2 = A + (int64_t)(Jend + nextw) * npad + J;
+            rc = launch_dgemm(0, 0, A + (int64_t)(Jend + nextw) * npad + (Jend + nextw), npad, P2, npad, P2, npad, rest, rest,
+                              K, -1.0, 1.0, KR_FULL, TM_LOWER, s);
             if (rc) return rc;
+            if ((rc = stream_order(ps, s))) return rc;
+        } else {
+            if ((rc = factor_panel(A, npad, (int)n, Jend, Jend + nextw, linv, info_dev, diag_smem, s))) return rc;
         }
     }
     return 0;
@@ -344,7 +526,9 @@ int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws,
     place_diag_inverse_kernel<<<nb, 256, 0, s>>>((const double*)potrf_ws, W, npad);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
-    return trtri_rec(L, W, npad, 0, nb, (double*)ws, s);
+    int rc = side_streams_init();
+    if (rc) return rc;
+    return trtri_rec(L, W, npad, 0, nb, (double*)ws, s, 0, 0);
 }
 
 int gp_lauum_f64(const double* W, double* Ainv, int64_t npad, void* stream) {

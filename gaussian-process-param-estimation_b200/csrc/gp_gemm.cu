@@ -107,6 +107,17 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    if (beta != 0.0) {
+        // the epilogue read-modify-writes a 128 KB tile of C that streams from HBM: pull it into L2 now so those
+        // loads cost an L2 hit instead of a DRAM round trip each (1024 lines of 128 B, 4 per thread)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int line = tid + i * GEMM_THREADS;  // row = line >> 3, 128-byte segment = line & 7
+            const double* pc = C + (int64_t)(m0 + (line >> 3)) * ldc + n0 + ((line & 7) << 4);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
+        }
+    }
+
     // prologue: fill STAGES-1 slabs
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -148,6 +159,28 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
 
     // epilogue: each thread owns (row, 2 consecutive cols) of every 8x8 fragment -> 16-byte accesses
     const bool diag = (tmask == TM_LOWER) && (tm == tn);
+    if (beta != 0.0 && !diag) {
+        // full tile with accumulate: issue all loads of a row group before using them (memory-level parallelism)
+#pragma unroll
+        for (int i = 0; i < MI; i += 2) {
+            double2 o[2][NI];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                    o[ii][j] = *reinterpret_cast<const double2*>(C + (int64_t)(m0 + wm + (i + ii) * 8 + g) * ldc + n0 + wn + j * 8 + 2 * t);
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    double2 v;
+                    v.x = alpha * acc[i + ii][j][0] + beta * o[ii][j].x;
+                    v.y = alpha * acc[i + ii][j][1] + beta * o[ii][j].y;
+                    *reinterpret_cast<double2*>(C + (int64_t)(m0 + wm + (i + ii) * 8 + g) * ldc + n0 + wn + j * 8 + 2 * t) = v;
+                }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         int row = wm + i * 8 + g;

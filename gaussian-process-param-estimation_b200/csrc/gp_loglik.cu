@@ -235,6 +235,100 @@ symm_skinny_kernel(const double* __restrict__ K, int n, int npad, const double* 
             }
 }
 
+// ---- solves through the explicit triangular inverse: S = W^T (W R), W = inv(L) lower ----------------------------
+// Y = W X : like symm_skinny_kernel but only columns j <= i are read (32 rows per CTA, 4 rows per warp).
+__global__ void __launch_bounds__(256)
+tril_skinny_kernel(const double* __restrict__ W, int npad, const double* __restrict__ X, int p, double* __restrict__ Y) {
+    __shared__ double xs[128 * SSP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rb = blockIdx.x * 32, r0 = rb + warp * 4;
+    double acc[4][MAXP];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < MAXP; ++c) acc[r][c] = 0.0;
+    for (int j0 = 0; j0 < rb + 32; j0 += 128) {
+        __syncthreads();
+        for (int idx = tid; idx < 128 * p; idx += 256) {
+            int r = idx / p, c = idx - r * p;
+            xs[r * SSP + c] = X[(int64_t)(j0 + r) * p + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int j = lane + 32 * q;
+            double kv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) kv[r] = (j0 + j <= r0 + r) ? W[(int64_t)(r0 + r) * npad + j0 + j] : 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXP; ++c)
+                if (c < p) {
+                    double x = xs[j * SSP + c];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r][c] += kv[r] * x;
+                }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < MAXP; ++c)
+            if (c < p) {
+                double v = warp_sum(acc[r][c]);
+                if (lane == 0) Y[(int64_t)(r0 + r) * p + c] = v;
+            }
+}
+
+// partial[kc][i][c] = sum_{k in chunk kc, k >= i} W[k][i] X[k][c]; 128 columns i per CTA, 1024-row k chunks
+constexpr int TCH = 1024;
+__global__ void __launch_bounds__(256)
+trilT_skinny_partial_kernel(const double* __restrict__ W, int npad, const double* __restrict__ X, int p, double* __restrict__ partial) {
+    __shared__ double xs[128 * SSP];
+    __shared__ double comb[128 * SSP];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * 128, kc = blockIdx.y;
+    const int il = tid & 127, half = tid >> 7, i = i0 + il;
+    int kbeg = kc * TCH, kend = min(npad, kbeg + TCH);
+    double acc[MAXP];
+#pragma unroll
+    for (int c = 0; c < MAXP; ++c) acc[c] = 0.0;
+    if (kend > i0) {   // uniform per CTA
+        if (kbeg < i0) kbeg = i0;
+        for (int k0 = kbeg; k0 < kend; k0 += 128) {
+            __syncthreads();
+            for (int idx = tid; idx < 128 * p; idx += 256) {
+                int r = idx / p, c = idx - r * p;
+                xs[r * SSP + c] = X[(int64_t)(k0 + r) * p + c];
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int kk = half; kk < 128; kk += 2) {
+                int k = k0 + kk;
+                double w = (k >= i) ? W[(int64_t)k * npad + i] : 0.0;
+#pragma unroll
+                for (int c = 0; c < MAXP; ++c)
+                    if (c < p) acc[c] += w * xs[kk * SSP + c];
+            }
+        }
+    }
+    __syncthreads();
+    if (half == 1)
+#pragma unroll
+        for (int c = 0; c < MAXP; ++c) comb[il * SSP + c] = acc[c];
+    __syncthreads();
+    if (half == 0)
+        for (int c = 0; c < p; ++c) partial[((int64_t)kc * npad + i) * p + c] = acc[c] + comb[il * SSP + c];
+}
+
+__global__ void trilT_reduce_kernel(const double* __restrict__ partial, int npad, int p, int nchunks, double* __restrict__ Y) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)npad * p) return;
+    int i = (int)(t / p);
+    double s = 0.0;
+    for (int kc = i / TCH; kc < nchunks; ++kc) s += partial[(int64_t)kc * npad * p + t];
+    Y[t] = s;
+}
+
 __global__ void __launch_bounds__(256)
 finalize_out_kernel(double* out, const double* logdet, const double* tr_parts, int ntiles, const double* frob_parts,
                     int nfrob, const int* info, int flags) {
@@ -272,6 +366,7 @@ struct LoglikWs {
     double* tr;       // ntiles x 3
     double* frob;     // T x T
     int* info;
+    double* tpart;    // (npad / 1024 + 1) x npad x MAXP
     void* potri;
     size_t total;
 };
@@ -289,6 +384,7 @@ static LoglikWs carve(void* ws, int64_t npad, int p) {
     w.tr = (double*)take(sizeof(double) * (T * (T + 1) / 2) * 3);
     w.frob = (double*)take(sizeof(double) * T * T);
     w.info = (int*)take(sizeof(int) * 4);
+    w.tpart = (double*)take(sizeof(double) * (npad / TCH + 1) * npad * MAXP);
     w.potri = (void*)take((size_t)gp_potri_workspace_bytes(npad));
     w.total = off;
     (void)p;
@@ -300,6 +396,17 @@ static int gram(const double* A, const double* B, int nrows, int p, int64_t ld, 
     gram_partial_kernel<<<parts, 256, 0, s>>>(A, B, nrows, p, ld, partial);
     sum_partials_kernel<<<(p * p + 127) / 128, 128, 0, s>>>(partial, parts, p * p, out);
     GP_COUNT(2);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+// S := W^T (W S) in place (S: npad x p), tmp: npad x p
+static int solve_with_inverse(const double* W, int npad, double* S, double* tmp, int p, double* tpart, cudaStream_t s) {
+    int nchunks = (npad + TCH - 1) / TCH;
+    tril_skinny_kernel<<<npad / 32, 256, 0, s>>>(W, npad, S, p, tmp);
+    trilT_skinny_partial_kernel<<<dim3(npad / 128, nchunks), 256, 0, s>>>(W, npad, tmp, p, tpart);
+    trilT_reduce_kernel<<<(unsigned)(((int64_t)npad * p + 255) / 256), 256, 0, s>>>(tpart, npad, p, nchunks, S);
+    GP_COUNT(3);
     GP_LAUNCH_CHECK();
     return 0;
 }
@@ -378,17 +485,21 @@ int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, i
     if ((rc = gp_potrf_f64(A, n, npad, w.info, potrf_ws, stream))) return rc;
     if ((rc = gp_logdet_from_chol(A, n, npad, w.logdet, stream))) return rc;
     GP_CUDA_CHECK(cudaMemcpyAsync(w.S, R, sizeof(double) * npad * p, cudaMemcpyDeviceToDevice, s));
-    if ((rc = gp_potrs_f64(A, npad, potrf_ws, w.S, p, p, stream))) return rc;
+    int T = NP / 128;
+    if (flags & 3) {
+        // the triangular inverse is needed anyway: solve through it (two skinny triangular products) instead of
+        // the latency-bound block substitution
+        if ((rc = gp_trtri_f64(A, W, npad, potrf_ws, w.potri, stream))) return rc;
+        if ((rc = solve_with_inverse(W, NP, w.S, w.V, P, w.tpart, s))) return rc;
+    } else {
+        if ((rc = gp_potrs_f64(A, npad, potrf_ws, w.S, p, p, stream))) return rc;
+    }
     double* G = out + 8;
     double* H = G + p * p;
     double* Q = H + p * p;
     if ((rc = gram(R, w.S, N, P, p, w.gram, G, s))) return rc;
     if ((rc = gram(w.S, w.S, N, P, p, w.gram, H, s))) return rc;
     GP_CUDA_CHECK(cudaMemsetAsync(Q, 0, sizeof(double) * p * p, s));
-    int T = NP / 128;
-    if (flags & 3) {
-        if ((rc = gp_trtri_f64(A, W, npad, potrf_ws, w.potri, stream))) return rc;
-    }
     if (flags & 2) {
         if ((rc = gp_lauum_f64(W, A, npad, stream))) return rc;
         bool with_dk = (flags & 4) != 0;
