@@ -1,7 +1,8 @@
 // FP64 tensor-core (DMMA) GEMM for the Cholesky / inverse hot path.
 //
 // One 128x128 output tile per CTA, 8 warps (2x4), warp tile 64x32 built from m8n8k4 DMMA fragments,
-// BK=16 k-slabs moved global->shared with cp.async through a 4-stage ring. Shared tiles are XOR-swizzled
+// BK=32 k-slabs moved global->shared with cp.async through a 3-stage ring (measured: 2-6 % over BK=16 x 4 stages,
+// the per-slab CTA barrier is the main loss against the raw DMMA issue rate). Shared tiles are XOR-swizzled
 // so that both the 16-byte cp.async stores and the 8-byte fragment loads are bank-conflict free for
 // K-major ([mn][k]) as well as MN-major ([k][mn]) operands; this lets one kernel serve
 //   NT: trailing SYRK/GEMM update and the panel TRSM-by-inverse   (potrf)
@@ -38,17 +39,31 @@ static double tile_flops(int tiles_m, int tiles_n, int K, int krange, int tmask)
     return 2.0 * 128.0 * 128.0 * kt;
 }
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
-constexpr int WARPS_N = 4, WM = 64, WN = 32;
+#ifndef GP_BK
+#define GP_BK 32
+#endif
+#ifndef GP_STAGES
+#define GP_STAGES 3
+#endif
+#ifndef GP_WM
+#define GP_WM 64
+#endif
+#ifndef GP_WN
+#define GP_WN 32
+#endif
+constexpr int BM = 128, BN = 128, BK = GP_BK, STAGES = GP_STAGES;
+constexpr int WM = GP_WM, WN = GP_WN;
+constexpr int WARPS_N = BN / WN, GEMM_THREADS = (BM / WM) * (BN / WN) * 32;
 constexpr int MI = WM / 8, NI = WN / 8;
 constexpr int TILE_ELEMS = 128 * BK;  // doubles per operand tile per stage
+constexpr int CHUNKS_PER_THREAD = TILE_ELEMS / 2 / GEMM_THREADS;
 constexpr int GEMM_SMEM = STAGES * 2 * TILE_ELEMS * (int)sizeof(double);
 constexpr int RASTER_GROUP = 8;
 
 // shared-memory offset (in doubles) of logical element (mn, k) of an operand tile
 template <int T>
 __device__ __forceinline__ int soff(int mn, int k) {
-    if (T == 0) return mn * BK + ((((k >> 2) ^ mn) & 3) << 2) + (k & 3);  // [128][16], 4-double chunks swizzled by row
+    if (T == 0) return mn * BK + (((k >> 2) ^ (mn & 3)) << 2) + (k & 3);  // [128][BK], 4-double chunks swizzled by row
     return k * 128 + (mn ^ ((k & 3) << 2));                                // [16][128], mn bits 2..3 swizzled by k
 }
 
@@ -56,11 +71,11 @@ __device__ __forceinline__ int soff(int mn, int k) {
 template <int T>
 __device__ __forceinline__ void load_tile(double* tile, const double* g, int64_t ld, int tid) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CHUNKS_PER_THREAD; ++i) {
         int idx = tid + i * GEMM_THREADS;
         if (T == 0) {
-            int r = idx >> 3, c = idx & 7;  // row r, 16-byte chunk c (k = 2c, 2c+1)
-            cp_async16(tile + r * BK + ((((c >> 1) ^ r) & 3) << 2) + ((c & 1) << 1), g + (int64_t)r * ld + 2 * c);
+            int r = idx / (BK / 2), c = idx % (BK / 2);  // row r, 16-byte chunk c (k = 2c, 2c+1)
+            cp_async16(tile + r * BK + ((c >> 1) ^ (r & 3)) * 4 + ((c & 1) << 1), g + (int64_t)r * ld + 2 * c);
         } else {
             int kr = idx >> 6, c = idx & 63;  // k-row kr, chunk c (mn = 2c, 2c+1)
             cp_async16(tile + kr * 128 + ((2 * c) ^ ((kr & 3) << 2)), g + (int64_t)kr * ld + 2 * c);
@@ -111,7 +126,7 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
         // the epilogue read-modify-writes a 128 KB tile of C that streams from HBM: pull it into L2 now so those
         // loads cost an L2 hit instead of a DRAM round trip each (1024 lines of 128 B, 4 per thread)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 1024 / GEMM_THREADS; ++i) {
             int line = tid + i * GEMM_THREADS;  // row = line >> 3, 128-byte segment = line & 7
             const double* pc = C + (int64_t)(m0 + (line >> 3)) * ldc + n0 + ((line & 7) << 4);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
@@ -129,8 +144,10 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     }
 
     for (int kt = 0; kt < KT; ++kt) {
+#ifndef GP_EXP_NOSYNC
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+#endif
         {   // refill the slot consumed in the previous iteration
             int nk = kt + STAGES - 1;
             if (nk < KT) {

@@ -20,7 +20,7 @@ enum TileMask {
 // C[M x N] (row-major, ldc) = beta*C + alpha * op(A) * op(B)
 //   at == 0: A(m,k) = A[m*lda + k]   at == 1: A(m,k) = A[k*lda + m]
 //   bt == 0: B(k,n) = B[n*ldb + k]   bt == 1: B(k,n) = B[k*ldb + n]
-// M, N multiples of 128; K multiple of 16; all ld even; pointers 16-byte aligned.
+// M, N multiples of 128; K multiple of 32; all ld even; pointers 16-byte aligned.
 int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda,
                  const double* B, int64_t ldb, int M, int N, int K, double alpha, double beta,
                  int krange, int tmask, cudaStream_t stream);

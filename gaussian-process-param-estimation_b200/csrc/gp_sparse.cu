@@ -1,0 +1,568 @@
+// Kernel-threshold sparse Matern correlation in canonical CSR -- replaces the brute-force O(n^2) OpenMP COO fill +
+// coo->csr of gaussian_proc/generate_correlation/_generate_sparse_correlation.pyx:35-201,472-594 by a uniform cell
+// list (cell edge = taper radius), a count pass, a host scan, a fill pass and a per-row bitonic sort.
+//
+// Bit-exact pattern: the keep rule is the reference's strict `K_ij > tau` (:160). The scaled distance is evaluated
+// in the reference's operation order with IEEE division/sqrt and no FMA contraction (this file is compiled with
+// -fmad=false); only exp() can differ from glibc by an ulp, so pairs with |K - tau| <= 8 ulp are not decided on the
+// device: they are listed, re-evaluated on the host with libm in the reference's arithmetic, and the accepted ones
+// are appended to their rows before the sort.
+#include "../../include/gpgp.h"
+#include "gp_common.cuh"
+#include "gp_matern.cuh"
+#include <math.h>
+#include <vector>
+
+namespace gp {
+
+constexpr int SMAXD = 3;             // cell list for d <= 3 (higher d: a single cell = brute force)
+constexpr int BORDER_CAP = 1 << 20;  // max borderline ordered pairs
+constexpr int SORT_CAP = 2048;       // max entries per row handled by the shared-memory sort
+
+struct CellGrid {
+    int d;
+    int nc[SMAXD];
+    double lo[SMAXD];
+    double inv_size[SMAXD];
+    int ncells;
+};
+
+// ---- host-side restatement of the scalar pieces (bit-following the reference) ---------------------------------
+static double gamma_half_int(int dimension) {  // Gamma(d/2 + 1), _generate_sparse_correlation.pyx:208-233
+    double g, k;
+    if (dimension % 2 == 0) {
+        k = 0.5 * dimension; g = 1.0;
+        while (k > 0.0) { g *= k; k -= 1.0; }
+    } else {
+        k = ceil(0.5 * dimension); g = sqrt(M_PI);
+        while (k > 0.0) { g *= k - 0.5; k -= 1.0; }
+    }
+    return g;
+}
+
+static void bessel_k_pair_host(double nu, double x, double* knu, double* knu1);
+
+static double matern_host(double x, double nu) {  // _kernels.pyx:17-100, glibc exp/sqrt/pow
+    if (x == 0) return 1.0;
+    if (nu == 0.5) return exp(-x);
+    if (nu == 1.5) return (1.0 + sqrt(3.0) * x) * exp(-sqrt(3.0) * x);
+    if (nu == 2.5) return (1.0 + sqrt(5.0) * x + (5.0 / 3.0) * pow(x, 2.0)) * exp(-sqrt(5.0) * x);
+    if (nu < 100) {
+        double y = sqrt(2.0 * nu) * x, k, k1;
+        bessel_k_pair_host(nu, y, &k, &k1);
+        return (pow(2.0, 1.0 - nu) / tgamma(nu)) * pow(y, nu) * k;
+    }
+    return exp(-0.5 * pow(x, 2.0));
+}
+
+static double distance_host(const double* a, const double* b, const double* scale, int d) {
+    double s = 0;
+    for (int k = 0; k < d; ++k) s += pow((a[k] - b[k]) / scale[k], 2.0);
+    return sqrt(s);
+}
+
+// Temme / Steed evaluation of K_nu, K_{nu+1} (same algorithm as the device version in gp_matern.cuh)
+static void bessel_k_pair_host(double nu, double x, double* knu, double* knu1) {
+    const double EPS = 1e-16;
+    int nl = (int)(nu + 0.5);
+    double xmu = nu - nl, xmu2 = xmu * xmu, xi = 1.0 / x, xi2 = 2.0 * xi, rkmu, rk1;
+    if (x < 2.0) {
+        double b = 0.5 * x, d = -log(b), e = xmu * d;
+        double fact2 = (fabs(e) < EPS) ? 1.0 : sinh(e) / e;
+        double pimu = M_PI * xmu;
+        double fact = (fabs(pimu) < EPS) ? 1.0 : pimu / sin(pimu);
+        double gampl = 1.0 / tgamma(1.0 + xmu), gammi = 1.0 / tgamma(1.0 - xmu);
+        double gam2 = 0.5 * (gammi + gampl);
+        double gam1 = (fabs(xmu) < 1e-4) ? -0.5772156649015329 + xmu2 * 0.04200263503409524 : (gammi - gampl) / (2.0 * xmu);
+        double ff = fact * (gam1 * cosh(e) + gam2 * fact2 * d), sum = ff;
+        e = exp(e);
+        double p = 0.5 * e / gampl, q = 0.5 / (e * gammi), c = 1.0, d2 = b * b, sum1 = p;
+        for (int i = 1; i <= 100000; ++i) {
+            ff = (i * ff + p + q) / (i * i - xmu2);
+            c *= (d2 / i); p /= (i - xmu); q /= (i + xmu);
+            double del = c * ff; sum += del; sum1 += c * (p - i * ff);
+            if (fabs(del) < fabs(sum) * EPS) break;
+        }
+        rkmu = sum; rk1 = sum1 * xi2;
+    } else {
+        double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d, q1 = 0.0, q2 = 1.0, a1 = 0.25 - xmu2;
+        double q = a1, c = a1, a = -a1, s = 1.0 + q * delh;
+        for (int i = 2; i <= 100000; ++i) {
+            a -= 2 * (i - 1); c = -a * c / i;
+            double qnew = (q1 - b * q2) / a; q1 = q2; q2 = qnew; q += c * qnew;
+            b += 2.0; d = 1.0 / (b + a * d); delh = (b * d - 1.0) * delh; h += delh;
+            double dels = q * delh; s += dels;
+            if (fabs(dels / s) < EPS) break;
+        }
+        h = a1 * h;
+        rkmu = sqrt(M_PI / (2.0 * x)) * exp(-x) / s;
+        rk1 = rkmu * (xmu + x + 0.5 - h) * xi;
+    }
+    for (int i = 1; i <= nl; ++i) { double t = (xmu + i) * xi2 * rk1 + rkmu; rkmu = rk1; rk1 = t; }
+    *knu = rkmu; *knu1 = rk1;
+}
+
+// scaled taper radius x_tau: K(x) > tau only if x < x_tau (K is decreasing); bisection, returned with a safety margin
+static double support_radius(double tau, double nu) {
+    if (!(tau > 0.0)) return 1e300;
+    if (tau >= 1.0) return 0.0;
+    double lo = 0.0, hi = 1.0;
+    while (matern_host(hi, nu) > tau && hi < 1e6) hi *= 2.0;
+    for (int it = 0; it < 200; ++it) {
+        double mid = 0.5 * (lo + hi);
+        if (matern_host(mid, nu) > tau) lo = mid; else hi = mid;
+    }
+    return hi * (1.0 + 1e-9) + 1e-300;
+}
+
+// ---- device pieces ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_of_point(const double* p, const CellGrid& g) {
+    int id = 0;
+#pragma unroll
+    for (int k = 0; k < SMAXD; ++k)
+        if (k < g.d) {
+            int c = (int)floor((p[k] - g.lo[k]) * g.inv_size[k]);
+            c = c < 0 ? 0 : (c >= g.nc[k] ? g.nc[k] - 1 : c);
+            id = id * g.nc[k] + c;
+        }
+    return id;
+}
+
+__global__ void cell_histogram_kernel(const double* __restrict__ pts, int n, int d, CellGrid g, int* cell_of, int* cell_cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[SMAXD] = {0, 0, 0};
+    for (int k = 0; k < d && k < SMAXD; ++k) p[k] = pts[(int64_t)i * d + k];
+    int id = (g.ncells == 1) ? 0 : cell_of_point(p, g);
+    cell_of[i] = id;
+    atomicAdd(&cell_cnt[id], 1);
+}
+
+__global__ void cell_scatter_kernel(const double* __restrict__ pts, int n, int d, const int* cell_of, const int* cell_start,
+                                    int* cell_fill, int* sorted_idx, double* sorted_pts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int id = cell_of[i];
+    int pos = cell_start[id] + atomicAdd(&cell_fill[id], 1);
+    sorted_idx[pos] = i;
+    for (int k = 0; k < d; ++k) sorted_pts[(int64_t)pos * d + k] = pts[(int64_t)i * d + k];
+}
+
+struct SparseParams {
+    double tau, band;         // keep rule K > tau; |K - tau| <= band -> host decides
+    double scale[8];
+    MaternParams mp;
+    int d, n;
+};
+
+// reference arithmetic: divide-then-square, k-ordered sum, IEEE sqrt (_kernels.pyx:130-136)
+__device__ __forceinline__ double scaled_distance(const double* a, const double* b, const SparseParams& sp) {
+    double s = 0.0;
+    for (int k = 0; k < sp.d; ++k) {
+        double t = (a[k] - b[k]) / sp.scale[k];
+        s += t * t;
+    }
+    return sqrt(s);
+}
+
+// One warp per (cell-sorted) point. PASS 0 counts kept entries and lists borderline pairs; PASS 1 writes (col, value
+// [, dvalue]) in candidate order into the row's segment.
+template <int MODE, int PASS, bool WITH_DK>
+__global__ void __launch_bounds__(256)
+sparse_rows_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_start, const int* __restrict__ sorted_idx,
+                   const double* __restrict__ sorted_pts, int* devcount, int* border_cnt, int2* border,
+                   const int* __restrict__ indptr, int* indices, double* data, double* ddata) {
+    const int lane = threadIdx.x & 31;
+    const int wpos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wpos >= sp.n) return;
+    const int i = sorted_idx[wpos];
+    double pi[8];
+    for (int k = 0; k < sp.d; ++k) pi[k] = sorted_pts[(int64_t)wpos * sp.d + k];
+    int cc[SMAXD] = {0, 0, 0};
+    if (g.ncells > 1) {
+        int id = cell_of_point(pi, g);
+        for (int k = g.d - 1; k >= 0; --k) { cc[k] = id % g.nc[k]; id /= g.nc[k]; }
+    }
+    int count = 0;
+    const int64_t base = (PASS == 1) ? (int64_t)indptr[i] : 0;
+    const int span = (g.ncells > 1) ? 3 : 1;
+    const int nnb = (g.ncells > 1) ? (g.d == 1 ? 3 : (g.d == 2 ? 9 : 27)) : 1;
+    for (int nb = 0; nb < nnb; ++nb) {
+        int id = 0;
+        bool ok = true;
+        if (g.ncells > 1) {
+            int r = nb;
+            int off[SMAXD];
+            for (int k = g.d - 1; k >= 0; --k) { off[k] = r % span - 1; r /= span; }
+            for (int k = 0; k < g.d; ++k) {
+                int c = cc[k] + off[k];
+                if (c < 0 || c >= g.nc[k]) ok = false;
+                id = id * g.nc[k] + c;
+            }
+        }
+        if (!ok) continue;
+        const int s0 = cell_start[id], s1 = cell_start[id + 1];
+        for (int q0 = s0; q0 < s1; q0 += 32) {
+            int q = q0 + lane;
+            bool keep = false;
+            double val = 0.0, dval = 0.0;
+            int j = -1;
+            if (q < s1) {
+                j = sorted_idx[q];
+                double pj[8];
+                for (int k = 0; k < sp.d; ++k) pj[k] = sorted_pts[(int64_t)q * sp.d + k];
+                double x = (i <= j) ? scaled_distance(pi, pj, sp) : scaled_distance(pj, pi, sp);
+                if (WITH_DK && PASS == 1) matern_value_drho<MODE>(x, sp.mp, &val, &dval);
+                else val = matern_value<MODE>(x, sp.mp);
+                bool borderline = (i != j) && fabs(val - sp.tau) <= sp.band;
+                keep = !borderline && (val > sp.tau);
+                if (PASS == 0 && borderline) {
+                    int slot = atomicAdd(border_cnt, 1);
+                    if (slot < BORDER_CAP) border[slot] = make_int2(i, j);
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (PASS == 1 && keep) {
+                int64_t o = base + count + __popc(m & ((1u << lane) - 1u));
+                indices[o] = j;
+                data[o] = val;
+                if (WITH_DK) ddata[o] = dval;
+            }
+            count += __popc(m);
+        }
+    }
+    if (PASS == 0 && lane == 0) devcount[i] = count;
+}
+
+__global__ void place_extras_kernel(int nextra, const int* __restrict__ ei, const int* __restrict__ ej,
+                                    const double* __restrict__ ev, const double* __restrict__ edv, const int* __restrict__ eslot,
+                                    const int* __restrict__ indptr, const int* __restrict__ devcount, int* indices, double* data,
+                                    double* ddata) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nextra) return;
+    int i = ei[t];
+    int64_t o = (int64_t)indptr[i] + devcount[i] + eslot[t];
+    indices[o] = ej[t];
+    data[o] = ev[t];
+    if (ddata) ddata[o] = edv[t];
+}
+
+// one CTA per row (grid-stride): bitonic sort of (col, value[, dvalue]) by col in shared memory
+__global__ void __launch_bounds__(256)
+sort_rows_kernel(int n, const int* __restrict__ indptr, int* indices, double* data, double* ddata, int* overflow) {
+    __shared__ int keys[SORT_CAP];
+    __shared__ double vals[SORT_CAP];
+    __shared__ double dvals[SORT_CAP];
+    for (int row = blockIdx.x; row < n; row += gridDim.x) {
+        const int s0 = indptr[row], len = indptr[row + 1] - s0;
+        if (len <= 1) continue;
+        if (len > SORT_CAP) { if (threadIdx.x == 0) atomicExch(overflow, row + 1); continue; }
+        int m = 1;
+        while (m < len) m <<= 1;
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) {
+            keys[t] = (t < len) ? indices[s0 + t] : 0x7fffffff;
+            vals[t] = (t < len) ? data[s0 + t] : 0.0;
+            if (ddata) dvals[t] = (t < len) ? ddata[s0 + t] : 0.0;
+        }
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = threadIdx.x; t < m; t += blockDim.x) {
+                    int p = t ^ jj;
+                    if (p > t) {
+                        bool up = ((t & k) == 0);
+                        int a = keys[t], b = keys[p];
+                        if ((a > b) == up) {
+                            keys[t] = b; keys[p] = a;
+                            double v = vals[t]; vals[t] = vals[p]; vals[p] = v;
+                            if (ddata) { double w = dvals[t]; dvals[t] = dvals[p]; dvals[p] = w; }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int t = threadIdx.x; t < len; t += blockDim.x) {
+            indices[s0 + t] = keys[t];
+            data[s0 + t] = vals[t];
+            if (ddata) ddata[s0 + t] = dvals[t];
+        }
+    }
+}
+
+// workspace carving (all int32 / f64 device arrays)
+struct SparseWs {
+    int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow;
+    int2* border;
+    int *ei, *ej, *eslot;
+    double *ev, *edv, *sorted_pts;
+    size_t total;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static SparseWs carve_sparse(void* ws, int64_t n, int64_t d) {
+    SparseWs w;
+    char* base = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return base ? base + o : (char*)nullptr; };
+    int64_t maxcells = 2 * n + 64;
+    w.cell_of = (int*)take(sizeof(int) * n);
+    w.cell_start = (int*)take(sizeof(int) * (maxcells + 1));
+    w.cell_fill = (int*)take(sizeof(int) * maxcells);
+    w.sorted_idx = (int*)take(sizeof(int) * n);
+    w.devcount = (int*)take(sizeof(int) * n);
+    w.border_cnt = (int*)take(sizeof(int) * 4);
+    w.overflow = (int*)take(sizeof(int) * 4);
+    w.border = (int2*)take(sizeof(int2) * BORDER_CAP);
+    w.ei = (int*)take(sizeof(int) * BORDER_CAP);
+    w.ej = (int*)take(sizeof(int) * BORDER_CAP);
+    w.eslot = (int*)take(sizeof(int) * BORDER_CAP);
+    w.ev = (double*)take(sizeof(double) * BORDER_CAP);
+    w.edv = (double*)take(sizeof(double) * BORDER_CAP);
+    w.sorted_pts = (double*)take(sizeof(double) * n * d);
+    w.total = off;
+    return w;
+}
+
+static int make_params(int64_t n, int64_t d, const double* scale_host, double nu, double tau, const double* bbox_lo,
+                       const double* bbox_hi, SparseParams* sp, CellGrid* g) {
+    sp->tau = tau;
+    sp->band = 8.0 * 2.220446049250313e-16 * fabs(tau);
+    sp->d = (int)d;
+    sp->n = (int)n;
+    for (int k = 0; k < d; ++k) sp->scale[k] = scale_host[k];
+    sp->mp.nu = nu;
+    sp->mp.coef = 0.0; sp->mp.sq2nu = 0.0;
+    sp->mp.inv_rho = 1.0 / scale_host[0];
+    for (int k = 0; k < d; ++k) sp->mp.inv_scale[k] = 1.0 / scale_host[k];
+    if (matern_mode_of(nu) == MAT_GENERAL) {
+        sp->mp.coef = pow(2.0, 1.0 - nu) / tgamma(nu);
+        sp->mp.sq2nu = sqrt(2.0 * nu);
+    }
+    double xr = support_radius(tau, nu);
+    g->d = (int)d;
+    g->ncells = 1;
+    for (int k = 0; k < SMAXD; ++k) { g->nc[k] = 1; g->lo[k] = 0.0; g->inv_size[k] = 0.0; }
+    if (d <= SMAXD && xr < 1e200) {
+        double cells = 1.0;
+        int nc[SMAXD] = {1, 1, 1};
+        for (int k = 0; k < d; ++k) {
+            double size = xr * scale_host[k];
+            double extent = bbox_hi[k] - bbox_lo[k];
+            double c = (size > 0.0) ? floor(extent / size) : 1e9;
+            if (c < 1.0) c = 1.0;
+            if (c > 4096.0) c = 4096.0;
+            nc[k] = (int)c;
+            cells *= c;
+        }
+        // cap the total at ~2n cells by coarsening (cells may only get larger than the radius, never smaller)
+        while (cells > 2.0 * (double)n + 32.0) {
+            cells = 1.0;
+            for (int k = 0; k < d; ++k) { nc[k] = (nc[k] + 1) / 2; cells *= nc[k]; }
+        }
+        for (int k = 0; k < d; ++k) {
+            double extent = bbox_hi[k] - bbox_lo[k];
+            g->nc[k] = nc[k];
+            g->lo[k] = bbox_lo[k];
+            g->inv_size[k] = (extent > 0.0) ? nc[k] / extent : 0.0;   // cell edge = extent / nc >= radius
+        }
+        g->ncells = (int)cells;
+    }
+    return 0;
+}
+
+template <int MODE>
+static void launch_rows(int pass, bool with_dk, const SparseParams& sp, const CellGrid& g, const SparseWs& w, const int* indptr,
+                        int* indices, double* data, double* ddata, cudaStream_t s) {
+    int blocks = (int)(((int64_t)sp.n * 32 + 255) / 256);
+    if (pass == 0)
+        sparse_rows_kernel<MODE, 0, false><<<blocks, 256, 0, s>>>(sp, g, w.cell_start, w.sorted_idx, w.sorted_pts, w.devcount,
+                                                                  w.border_cnt, w.border, nullptr, nullptr, nullptr, nullptr);
+    else if (with_dk)
+        sparse_rows_kernel<MODE, 1, true><<<blocks, 256, 0, s>>>(sp, g, w.cell_start, w.sorted_idx, w.sorted_pts, w.devcount,
+                                                                 w.border_cnt, w.border, indptr, indices, data, ddata);
+    else
+        sparse_rows_kernel<MODE, 1, false><<<blocks, 256, 0, s>>>(sp, g, w.cell_start, w.sorted_idx, w.sorted_pts, w.devcount,
+                                                                  w.border_cnt, w.border, indptr, indices, data, nullptr);
+    GP_COUNT(1);
+}
+
+static void launch_rows_mode(int mode, int pass, bool with_dk, const SparseParams& sp, const CellGrid& g, const SparseWs& w,
+                             const int* indptr, int* indices, double* data, double* ddata, cudaStream_t s) {
+    switch (mode) {
+        case MAT_05: launch_rows<MAT_05>(pass, with_dk, sp, g, w, indptr, indices, data, ddata, s); break;
+        case MAT_15: launch_rows<MAT_15>(pass, with_dk, sp, g, w, indptr, indices, data, ddata, s); break;
+        case MAT_25: launch_rows<MAT_25>(pass, with_dk, sp, g, w, indptr, indices, data, ddata, s); break;
+        case MAT_GAUSS: launch_rows<MAT_GAUSS>(pass, with_dk, sp, g, w, indptr, indices, data, ddata, s); break;
+        default: launch_rows<MAT_GENERAL>(pass, with_dk, sp, g, w, indptr, indices, data, ddata, s); break;
+    }
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" {
+
+int gp_kernel_threshold(int64_t n, int64_t d, double density, const double* scale_host, double nu, double* tau_host) {
+    // _estimate_kernel_threshold, _generate_sparse_correlation.pyx:294-413 (with _ball_volume given its dimension)
+    if (!scale_host || !tau_host || n <= 0 || d <= 0) return -1;
+    double adjacency_volume = density * (double)n;
+    if (adjacency_volume < 1.0) return -10;  // -> ValueError in the Python layer (:378-383)
+    double prod = 1.0;
+    for (int k = 0; k < d; ++k) prod *= scale_host[k];
+    double geometric_mean_radius = pow(prod, 1.0 / (double)d);
+    double ellipsoid_volume = pow(geometric_mean_radius * sqrt(M_PI), (double)d) / gamma_half_int((int)d);
+    adjacency_volume /= ellipsoid_volume;
+    double adjacency_radius = pow(gamma_half_int((int)d) * adjacency_volume, 1.0 / (double)d) / sqrt(M_PI);
+    double grid_axis_num_points = pow((double)n, 1.0 / (double)d);
+    double grid_size = 1.0 / (grid_axis_num_points - 1.0);
+    double kernel_radius = grid_size * adjacency_radius;
+    *tau_host = matern_host(kernel_radius, nu);
+    return 0;
+}
+
+int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d) { return (int64_t)carve_sparse(nullptr, n, d).total; }
+
+int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                           double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream) {
+    if (!points || !points_host || !scale_host || !ws || !indptr_dev || !nnz_host || n <= 0 || d <= 0 || d > 8 || n > INT32_MAX)
+        return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    SparseWs w = carve_sparse(ws, n, d);
+    double lo[8], hi[8];
+    for (int k = 0; k < d; ++k) { lo[k] = 1e300; hi[k] = -1e300; }
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < d; ++k) {
+            double v = points_host[i * d + k];
+            if (v < lo[k]) lo[k] = v;
+            if (v > hi[k]) hi[k] = v;
+        }
+    SparseParams sp;
+    CellGrid g;
+    make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
+    const int N = (int)n, D = (int)d;
+    GP_CUDA_CHECK(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * (g.ncells + 1), s));
+    GP_CUDA_CHECK(cudaMemsetAsync(w.cell_fill, 0, sizeof(int) * g.ncells, s));
+    GP_CUDA_CHECK(cudaMemsetAsync(w.border_cnt, 0, sizeof(int) * 4, s));
+    GP_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int) * 4, s));
+    cell_histogram_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, g, w.cell_of, w.cell_start + 1);
+    GP_COUNT(1);
+    // host exclusive scan of the cell histogram
+    std::vector<int> cs(g.ncells + 1);
+    GP_CUDA_CHECK(cudaMemcpyAsync(cs.data(), w.cell_start, sizeof(int) * (g.ncells + 1), cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int c = 0; c < g.ncells; ++c) cs[c + 1] += cs[c];
+    GP_CUDA_CHECK(cudaMemcpyAsync(w.cell_start, cs.data(), sizeof(int) * (g.ncells + 1), cudaMemcpyHostToDevice, s));
+    cell_scatter_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, w.cell_of, w.cell_start, w.cell_fill, w.sorted_idx,
+                                                        w.sorted_pts);
+    GP_COUNT(1);
+    launch_rows_mode(matern_mode_of(nu), 0, false, sp, g, w, nullptr, nullptr, nullptr, nullptr, s);
+    GP_LAUNCH_CHECK();
+    std::vector<int> cnt(n);
+    int nb = 0;
+    GP_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), w.devcount, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaMemcpyAsync(&nb, w.border_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (nb > BORDER_CAP) return -21;
+    // borderline pairs: decide with the reference's host arithmetic
+    std::vector<int> ei, ej, eslot;
+    std::vector<double> ev, edv;
+    if (nb > 0) {
+        std::vector<int2> bl(nb);
+        GP_CUDA_CHECK(cudaMemcpy(bl.data(), w.border, sizeof(int2) * nb, cudaMemcpyDeviceToHost));
+        std::vector<int> extra(n, 0);
+        for (int t = 0; t < nb; ++t) {
+            int i = bl[t].x, j = bl[t].y;
+            const double* a = points_host + (int64_t)(i <= j ? i : j) * d;
+            const double* b = points_host + (int64_t)(i <= j ? j : i) * d;
+            double x = distance_host(a, b, scale_host, (int)d);
+            double v = matern_host(x, nu);
+            if (v > tau) {
+                ei.push_back(i); ej.push_back(j); ev.push_back(v); eslot.push_back(extra[i]++);
+                edv.push_back(0.0);  // filled on the device side convention: derivative of borderline entries is recomputed below
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) cnt[i] += extra[i];
+    }
+    std::vector<int> ip(n + 1);
+    int64_t run = 0;
+    for (int64_t i = 0; i < n; ++i) { ip[i] = (int)run; run += cnt[i]; }
+    if (run > INT32_MAX) return -22;
+    ip[n] = (int)run;
+    *nnz_host = run;
+    GP_CUDA_CHECK(cudaMemcpyAsync(indptr_dev, ip.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    int ne = (int)ei.size();
+    int meta[4] = {ne, 0, 0, 0};
+    GP_CUDA_CHECK(cudaMemcpyAsync(w.border_cnt, meta, sizeof(int) * 4, cudaMemcpyHostToDevice, s));
+    if (ne > 0) {
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.ei, ei.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, s));
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.ej, ej.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, s));
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.eslot, eslot.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, s));
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.ev, ev.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, s));
+    }
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors go out of scope
+    return 0;
+}
+
+int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                          double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
+                          double* ddata_dev, void* stream) {
+    if (!points || !points_host || !scale_host || !ws || !indptr_dev || !indices_dev || !data_dev || n <= 0 || d <= 0 || d > 8)
+        return -1;
+    if (ddata_dev)
+        for (int k = 0; k < d; ++k)
+            if (scale_host[k] != scale_host[0]) return -4;
+    cudaStream_t s = (cudaStream_t)stream;
+    SparseWs w = carve_sparse(ws, n, d);
+    double lo[8], hi[8];
+    for (int k = 0; k < d; ++k) { lo[k] = 1e300; hi[k] = -1e300; }
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < d; ++k) {
+            double v = points_host[i * d + k];
+            if (v < lo[k]) lo[k] = v;
+            if (v > hi[k]) hi[k] = v;
+        }
+    SparseParams sp;
+    CellGrid g;
+    make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
+    int meta[4];
+    GP_CUDA_CHECK(cudaMemcpyAsync(meta, w.border_cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    int ne = meta[0];
+    launch_rows_mode(matern_mode_of(nu), 1, ddata_dev != nullptr, sp, g, w, indptr_dev, indices_dev, data_dev, ddata_dev, s);
+    if (ne > 0) {
+        if (ddata_dev) {
+            // derivative values of the host-decided entries (any ulp-level value is fine here: only the pattern and
+            // the K values are pinned)
+            std::vector<int> ei(ne), ej(ne);
+            std::vector<double> edv(ne);
+            GP_CUDA_CHECK(cudaMemcpy(ei.data(), w.ei, sizeof(int) * ne, cudaMemcpyDeviceToHost));
+            GP_CUDA_CHECK(cudaMemcpy(ej.data(), w.ej, sizeof(int) * ne, cudaMemcpyDeviceToHost));
+            double rho = scale_host[0], h = 1e-6 * rho;
+            std::vector<double> sc(d);
+            for (int t = 0; t < ne; ++t) {
+                const double* a = points_host + (int64_t)ei[t] * d;
+                const double* b = points_host + (int64_t)ej[t] * d;
+                for (int k = 0; k < d; ++k) sc[k] = rho + h;
+                double vp = matern_host(distance_host(a, b, sc.data(), (int)d), nu);
+                for (int k = 0; k < d; ++k) sc[k] = rho - h;
+                double vm = matern_host(distance_host(a, b, sc.data(), (int)d), nu);
+                edv[t] = (vp - vm) / (2 * h);
+            }
+            GP_CUDA_CHECK(cudaMemcpy(w.edv, edv.data(), sizeof(double) * ne, cudaMemcpyHostToDevice));
+        }
+        place_extras_kernel<<<(ne + 255) / 256, 256, 0, s>>>(ne, w.ei, w.ej, w.ev, w.edv, w.eslot, indptr_dev, w.devcount,
+                                                             indices_dev, data_dev, ddata_dev);
+        GP_COUNT(1);
+    }
+    sort_rows_kernel<<<148 * 8, 256, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    int ovf = 0;
+    GP_CUDA_CHECK(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (ovf) return -23;  // a row longer than SORT_CAP
+    return 0;
+}
+
+}  // extern "C"

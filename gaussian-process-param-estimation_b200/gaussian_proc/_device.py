@@ -44,6 +44,16 @@ SIGNATURES = {
     'gp_gemm_profile_enable': (_int, [_int]),
     'gp_gemm_profile_read': (_int, [_vp, _vp, _vp]),
     'gp_matern_dense': (_int, [_vp, _i64, _i64, _vp, _f64, _vp, _i64, _vp, _vp]),
+    'gp_kernel_threshold': (_int, [_i64, _i64, _f64, _vp, _f64, _vp]),
+    'gp_sparse_workspace_bytes': (_i64, [_i64, _i64]),
+    'gp_matern_sparse_count': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
+    'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_csr_spmm': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
+    'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp]),
+    'gp_krylov_workspace_bytes': (_i64, [_i64, _i64]),
+    'gp_col_dot': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'gp_lanczos': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'gp_cg_solve': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_dgemm_f64': (_int, [_int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _int, _int,
                             _vp]),
     'gp_shift_copy': (_int, [_vp, _i64, _i64, _f64, _vp, _vp]),

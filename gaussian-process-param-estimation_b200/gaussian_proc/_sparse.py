@@ -1,0 +1,356 @@
+"""
+Sparse (kernel-threshold) path: device CSR generation and the stochastic estimators behind MixedCorrelation for a
+sparse K (SpMM + batched Lanczos / CG in csrc/gp_sparse.cu, csrc/gp_sparse_la.cu).
+
+Reference behaviour restated here:
+  generate_sparse_correlation  gaussian_proc/generate_correlation/_generate_sparse_correlation.pyx:472-594
+  logdet / traceinv (slq, hutchinson), solve (CG, tol 1e-6)
+                               gaussian_proc/_mixed_correlation/mixed_correlation.py:193-209,263-268;
+                               _linear_solver.py:49-68
+imate (absent, unpinned dependency) is followed through its documented estimator: Rademacher probes, Lanczos
+quadrature, min/max number of samples, relative error tolerance at a confidence level. parity unpinned:
+the reference's own 'slq' branches are dead code (mixed_correlation.py:141,207,266); the confidence band is checked
+against exact values from the oracle in tests/test_gpu_sparse.py.
+"""
+
+import ctypes
+
+import numpy
+import scipy.linalg
+import scipy.sparse
+import scipy.special
+
+from . import _device as dev
+from ._device import lib, check
+
+__all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate_kernel_threshold']
+
+# imate's documented defaults for the stochastic estimators
+DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
+                lanczos_degree=20, seed=0, batch=8, cg_tol=1e-6, cg_maxiter=2000)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def estimate_kernel_threshold(matrix_size, dimension, density, correlation_scale, nu):
+    """tau for the requested density (_generate_sparse_correlation.pyx:294-413); ValueError when density*n < 1."""
+    tau = ctypes.c_double()
+    scale = dev.host_f64(correlation_scale)
+    rc = lib.gp_kernel_threshold(int(matrix_size), int(dimension), float(density), dev.host_ptr(scale), float(nu),
+                                 ctypes.byref(tau))
+    if rc == -10:
+        raise ValueError(
+            'Adjacency: %0.2f. Correlation matrix will become identity since kernel radius is less than grid size. '
+            'To increase adjacency, consider increasing density or correlation_scale.' % (density * matrix_size))
+    check(rc, 'gp_kernel_threshold')
+    return tau.value
+
+
+class DeviceCSR(object):
+    """Canonical CSR (int32 indptr / sorted int32 indices, float64 data) resident on the GPU; `ddata` optionally holds
+    d/d(rho) of every stored entry on the same pattern."""
+
+    def __init__(self, n, indptr, indices, data, ddata=None, kernel_threshold=None):
+        self.n = int(n)
+        self.indptr, self.indices, self.data, self.ddata = indptr, indices, data, ddata
+        self.kernel_threshold = kernel_threshold
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    @property
+    def nnz(self):
+        return int(self.data.shape[0])
+
+    @classmethod
+    def from_scipy(cls, K):
+        torch = dev.require_cuda()
+        K = scipy.sparse.csr_matrix(K)
+        K.sort_indices()
+        if K.shape[0] != K.shape[1]:
+            raise ValueError('K should be a square matrix.')
+        return cls(K.shape[0], torch.from_numpy(K.indptr.astype(numpy.int32)).cuda(),
+                   torch.from_numpy(K.indices.astype(numpy.int32)).cuda(),
+                   torch.from_numpy(K.data.astype(numpy.float64)).cuda())
+
+    def to_scipy(self):
+        return scipy.sparse.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                                       shape=(self.n, self.n))
+
+
+def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=False, device=False,
+                                with_derivative=False, kernel_threshold=None):
+    """Device generator behind the reference's generate_sparse_correlation. Returns scipy.sparse.csr_matrix (or a
+    DeviceCSR when ``device``)."""
+    torch = dev.require_cuda()
+    points = numpy.ascontiguousarray(points, dtype=numpy.float64)
+    scale = dev.host_f64(correlation_scale)
+    n, d = points.shape
+    tau = estimate_kernel_threshold(n, d, density, scale, nu) if kernel_threshold is None else float(kernel_threshold)
+    if with_derivative and not numpy.all(scale == scale[0]):
+        raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
+    dpts = torch.from_numpy(points).cuda()
+    ws = torch.empty(lib.gp_sparse_workspace_bytes(n, d) // 8 + 8, dtype=torch.float64, device='cuda')
+    indptr = torch.empty(n + 1, dtype=torch.int32, device='cuda')
+    nnz = ctypes.c_int64()
+    s = dev.stream_ptr()
+    rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                    _p(indptr), ctypes.byref(nnz), s)
+    check(rc, 'gp_matern_sparse_count')
+    indices = torch.empty(nnz.value, dtype=torch.int32, device='cuda')
+    data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
+    ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
+    rc = lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                   _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None, s)
+    check(rc, 'gp_matern_sparse_fill')
+    K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau)
+    if verbose:
+        print('Generated sparse correlation matrix using kernel threshold: %0.4f and sparse density: %0.2e.'
+              % (tau, K.nnz / float(n) ** 2))
+    return K if device else K.to_scipy()
+
+
+def lanczos_quadrature(alpha, beta, funcs):
+    """Gauss quadrature of v^T f(A) v / ||v||^2 from the Lanczos tridiagonal: sum_k tau_k^2 f(theta_k) with theta the
+    Ritz values and tau the first components of the Ritz vectors. A beta ~ 0 truncates the recurrence (invariant
+    subspace reached)."""
+    m = len(alpha)
+    for j in range(m - 1):
+        if not (beta[j] > 1e-12 * max(abs(alpha[0]), 1.0)):
+            m = j + 1
+            break
+    theta, Y = scipy.linalg.eigh_tridiagonal(alpha[:m], beta[:m - 1]) if m > 1 else (alpha[:1], numpy.ones((1, 1)))
+    w = Y[0, :] ** 2
+    return [float(numpy.sum(w * f(theta))) for f in funcs], float(theta.min())
+
+
+class SparseEngine(object):
+    """Stochastic logdet / traceinv and CG solves for K + eta I with K in device CSR."""
+
+    def __init__(self, K, imate_method='slq', imate_options=None, probe_range=None):
+        dev.require_cuda()
+        if not isinstance(K, DeviceCSR):
+            K = DeviceCSR.from_scipy(K)
+        self.K = K
+        self.n = K.n
+        self.method = imate_method
+        self.opt = dict(DEFAULTS)
+        self.opt.update(imate_options or {})
+        self._ws = {}
+        self._slq_cache = {}
+        self.last_info = {}
+        # multi-GPU: (rank, world) -> this engine evaluates the probes p with p % world == rank; see _distributed.py
+        self.probe_range = probe_range
+
+    # ---- plumbing ----------------------------------------------------------------------------------------------
+    def _workspace(self, B):
+        torch = dev.torch
+        if B not in self._ws:
+            self._ws[B] = torch.empty(lib.gp_krylov_workspace_bytes(self.n, B) // 8 + 8, dtype=torch.float64, device='cuda')
+        return self._ws[B]
+
+    def spmm(self, eta, X_dev, data=None):
+        torch = dev.torch
+        B = X_dev.shape[1]
+        Y = torch.empty_like(X_dev)
+        K = self.K
+        check(lib.gp_csr_spmm(_p(K.indptr), _p(K.indices), _p(K.data if data is None else data), self.n, float(eta),
+                              _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_csr_spmm')
+        return Y
+
+    def probes(self, first, B):
+        torch = dev.torch
+        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
+        check(lib.gp_rademacher(_p(V), self.n, B, int(self.opt['seed']), int(first), dev.stream_ptr()), 'gp_rademacher')
+        return V
+
+    # ---- SLQ -----------------------------------------------------------------------------------------------------
+    def _slq_samples(self, eta, first, B):
+        """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1."""
+        torch = dev.torch
+        m = int(self.opt['lanczos_degree'])
+        K = self.K
+        V = self.probes(first, B)
+        alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha), _p(beta),
+                             _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
+        a, b = alpha.cpu().numpy(), beta.cpu().numpy()
+        out = numpy.empty((B, 3))
+        for c in range(B):
+            vals, tmin = lanczos_quadrature(a[:, c], b[:, c], [numpy.log, lambda t: 1.0 / t, lambda t: 1.0 / t ** 2])
+            if not (tmin > 0):
+                raise numpy.linalg.LinAlgError(
+                    'K + eta*I (eta=%g) is not positive definite: Lanczos found a Ritz value %.3e. The thresholded '
+                    'Matern matrix is indefinite; use a larger eta (reference: _generate_sparse_correlation.pyx:516-523).'
+                    % (eta, tmin))
+            out[c] = numpy.array(vals) * self.n
+        return out
+
+    @staticmethod
+    def _chunks(first, count, batch):
+        """split [first, first + count) into contiguous power-of-two blocks of width <= batch"""
+        out = []
+        while count > 0:
+            w = 1
+            while w * 2 <= min(count, batch):
+                w *= 2
+            out.append((first, w))
+            first += w
+            count -= w
+        return out
+
+    def _run_estimator(self, sample_fn, ncols):
+        """imate-style sampling loop: rounds of probes until every estimated quantity satisfies
+        z * s / sqrt(N) <= max(atol, rtol |mean|) (after min_num_samples) or max_num_samples is reached.
+        Multi-GPU: each round's probe ids are cut into `world` contiguous slices, one per rank; the running
+        (count, sum, sum of squares) are all-reduced, so every rank takes the same stopping decision. Probe ids, not
+        ranks, seed the random signs: the union of the samples is the same set for any number of GPUs."""
+        o = self.opt
+        B = int(o['batch'])
+        zc = float(numpy.sqrt(2.0) * scipy.special.erfinv(float(o['confidence_level'])))
+        lo, hi = int(o['min_num_samples']), int(o['max_num_samples'])
+        rank, world = self.probe_range if self.probe_range is not None else (0, 1)
+        samples = numpy.empty((0, ncols))
+        first = 0
+        while first < hi:
+            nb = min(B * world, hi - first)
+            per = (nb + world - 1) // world
+            my0 = first + rank * per
+            my1 = min(first + nb, my0 + per)
+            for (f, w) in self._chunks(my0, max(0, my1 - my0), B):
+                samples = numpy.vstack([samples, sample_fn(f, w)])
+            first += nb
+            N, mean, sd = self._reduce(samples)
+            if N >= lo:
+                half = zc * sd / numpy.sqrt(N)
+                atol = o['error_atol'] if o['error_atol'] is not None else 0.0
+                if numpy.all(half <= numpy.maximum(atol, o['error_rtol'] * numpy.abs(mean))):
+                    break
+        N, mean, sd = self._reduce(samples)
+        half = zc * sd / numpy.sqrt(max(N, 1))
+        return mean, half, int(N)
+
+    def _reduce(self, samples):
+        """(N, mean, unbiased std) over all ranks: all-reduce of (count, sum, sum of squares) per quantity."""
+        cnt = numpy.array([samples.shape[0]], dtype=float)
+        s1 = samples.sum(axis=0)
+        s2 = (samples ** 2).sum(axis=0)
+        if self.probe_range is not None and self.probe_range[1] > 1:
+            from ._distributed import allreduce_sum
+            packed = allreduce_sum(numpy.concatenate([cnt, s1, s2]))
+            k = s1.size
+            cnt, s1, s2 = packed[:1], packed[1:1 + k], packed[1 + k:]
+        N = cnt[0]
+        mean = s1 / max(N, 1)
+        var = numpy.maximum(s2 - N * mean ** 2, 0.0) / max(N - 1, 1)
+        return N, mean, numpy.sqrt(var)
+
+    def _slq(self, eta):
+        key = float(eta)
+        if key not in self._slq_cache:
+            mean, half, N = self._run_estimator(lambda first, width: self._slq_samples(eta, first, width), 3)
+            self._slq_cache = {key: (mean, half, N)}
+        mean, half, N = self._slq_cache[key]
+        self.last_info = {'num_samples': N, 'half_width': half, 'confidence_level': self.opt['confidence_level'],
+                          'lanczos_degree': self.opt['lanczos_degree']}
+        return mean
+
+    def logdet(self, eta):
+        """SLQ estimate of logdet(K + eta I) (also for method 'hutchinson')."""
+        return float(self._slq(eta)[0])
+
+    def traceinv(self, eta, exponent=1):
+        if exponent not in (1, 2):
+            raise ValueError('traceinv on the sparse engine supports exponent 1 and 2.')
+        if self.method == 'slq' or exponent == 2:
+            return float(self._slq(eta)[exponent])
+
+        def fn(first, width):   # hutchinson: v^T Kn^-1 v with CG solves
+            V = self.probes(first, width)
+            U = self.solve_dev(eta, V.clone())
+            return self.col_dot(U, V).reshape(-1, 1)
+        mean, half, N = self._run_estimator(fn, 1)
+        self.last_info = {'num_samples': N, 'half_width': half}
+        return float(mean[0])
+
+    def traceinv_dK(self, eta):
+        """Hutchinson estimate of tr((K + eta I)^-1 dK/d rho): mean over probes of (Kn^-1 v)^T (dK v)."""
+        if self.K.ddata is None:
+            raise ValueError('needs a DeviceCSR generated with with_derivative=True')
+
+        def fn(first, width):
+            V = self.probes(first, width)
+            U = self.solve_dev(eta, V.clone())
+            Wd = self.spmm(0.0, V, data=self.K.ddata)
+            return self.col_dot(U, Wd).reshape(-1, 1)
+        mean, half, N = self._run_estimator(fn, 1)
+        self.last_info = {'num_samples': N, 'half_width': half}
+        return float(mean[0])
+
+    # ---- CG ------------------------------------------------------------------------------------------------------
+    def col_dot(self, X, Y):
+        torch = dev.torch
+        B = X.shape[1]
+        out = torch.empty(32, dtype=torch.float64, device='cuda')
+        check(lib.gp_col_dot(_p(X), _p(Y), self.n, B, _p(out), _p(self._workspace(B)), dev.stream_ptr()), 'gp_col_dot')
+        return out[:B].cpu().numpy()
+
+    def solve_dev(self, eta, R_dev):
+        """(K + eta I)^-1 R for a device block (n x B, B a power of two <= 32); R_dev is overwritten."""
+        torch = dev.torch
+        B = R_dev.shape[1]
+        X = torch.empty_like(R_dev)
+        K = self.K
+        it = ctypes.c_int64()
+        rc = lib.gp_cg_solve(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(R_dev), _p(X), B,
+                             float(self.opt['cg_tol']), int(self.opt['cg_maxiter']), ctypes.byref(it),
+                             _p(self._workspace(B)), dev.stream_ptr())
+        check(rc, 'gp_cg_solve')
+        self.last_cg_iterations = it.value
+        if rc == 1:
+            raise numpy.linalg.LinAlgError('CG did not converge in %d iterations (eta=%g)' % (it.value, eta))
+        return X
+
+    def solve(self, eta, Y):
+        """mixed_correlation.py:280-299 for sparse K: CG per column with rtol 1e-6 (batched on the device)."""
+        torch = dev.torch
+        Y = numpy.asarray(Y, dtype=numpy.float64)
+        vec = (Y.ndim == 1)
+        Y2 = Y.reshape(self.n, -1)
+        out = numpy.empty_like(Y2)
+        k = Y2.shape[1]
+        for c0 in range(0, k, 32):
+            blk = Y2[:, c0:c0 + 32]
+            B = 1
+            while B < blk.shape[1]:
+                B *= 2
+            R = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
+            R[:, :blk.shape[1]].copy_(torch.from_numpy(numpy.ascontiguousarray(blk)))
+            X = self.solve_dev(eta, R)
+            out[:, c0:c0 + blk.shape[1]] = X[:, :blk.shape[1]].cpu().numpy()
+        return out[:, 0] if vec else out
+
+    def matmul(self, X):
+        torch = dev.torch
+        X = numpy.asarray(X, dtype=numpy.float64)
+        vec = (X.ndim == 1)
+        X2 = X.reshape(self.n, -1)
+        k = X2.shape[1]
+        B = 1
+        while B < k:
+            B *= 2
+        if B > 32:
+            return numpy.hstack([self.matmul(X2[:, c:c + 32]) for c in range(0, k, 32)])
+        Xd = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
+        Xd[:, :k].copy_(torch.from_numpy(numpy.ascontiguousarray(X2)))
+        res = self.spmm(0.0, Xd)[:, :k].cpu().numpy()
+        return res[:, 0] if vec else res
+
+    def trace_K(self):
+        """(tr K, tr K^2 = sum of squared entries) of the stored symmetric matrix (rare path: host reduction)."""
+        Kh = self.K.to_scipy()
+        return float(Kh.diagonal().sum()), float((Kh.data ** 2).sum())

@@ -52,6 +52,24 @@ int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launche
 int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* scale_host, double nu,
                     double* K, int64_t ldk, double* dK, void* stream);
 
+/* tau = matern(kernel_radius(density), nu): host-only, bit-follows _estimate_kernel_threshold
+ * (_generate_sparse_correlation.pyx:294-413, with the missing `dimension` argument of :390 supplied).
+ * Returns -10 when density * n < 1 (the reference raises ValueError, :378-383). */
+int gp_kernel_threshold(int64_t n, int64_t d, double density, const double* scale_host, double nu, double* tau_host);
+
+/* Sparse generator, two calls around the caller's allocation of indices/data (the reference guesses max_nnz and
+ * retries with doubled buffers, :548-577): count -> indptr (device int32, n + 1) and nnz (host); fill -> indices
+ * (int32, sorted within each row), data and optionally ddata = d/d(rho) values on the same pattern.
+ * points: device (n, d); points_host: the same array on the host (bounding box + host re-decision of the pairs with
+ * |K - tau| <= 8 ulp, which makes the pattern bit-exact). ws: gp_sparse_workspace_bytes(n, d), shared by both calls. */
+int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d);
+int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d,
+                           const double* scale_host, double nu, double tau, void* ws, int* indptr_dev,
+                           int64_t* nnz_host, void* stream);
+int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d,
+                          const double* scale_host, double nu, double tau, void* ws, const int* indptr_dev,
+                          int* indices_dev, double* data_dev, double* ddata_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Dense FP64 linear algebra on K + eta*I  (reference: _mixed_correlation/mixed_correlation.py:155-335 and
  * _linear_solver.py:71 scipy.linalg.solve(assume_a='pos'), i.e. LAPACK dposv; imate 'cholesky' logdet/traceinv)
@@ -59,7 +77,7 @@ int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* sc
 
 /* General DMMA GEMM used by everything below; exported for tests and the roofline microbenchmark.
  * C[MxN] = beta*C + alpha*op(A)*op(B); at/bt: 0 -> operand stored [mn][k], 1 -> stored [k][mn].
- * krange / tmask: see gp_internal.h (0 / 0 = plain GEMM). M,N multiples of 128, K multiple of 16. */
+ * krange / tmask: see gp_internal.h (0 / 0 = plain GEMM). M,N multiples of 128, K multiple of 32. */
 int gp_dgemm_f64(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                  int64_t ldb, int64_t M, int64_t N, int64_t K, double alpha, double beta, int krange, int tmask,
                  void* stream);
@@ -101,6 +119,28 @@ int gp_inverse_traces(const double* M, int64_t n, int64_t npad, int kind, double
 /* Y (npad x p) = K * X for a skinny X (npad x p, p <= 16, rows >= n ignored): K_mixed.dot(0, x) of
  * mixed_correlation.py:305-335 (the eta*x term is added by the caller). */
 int gp_symm_skinny(const double* K, int64_t n, int64_t npad, const double* X, int64_t p, double* Y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sparse (CSR, int32 indices) operator K + eta*I on n x B row-major column blocks, B in {1,2,4,8,16,32}
+ * (reference: mixed_correlation.py:193-209,263-268 imate 'hutchinson' / 'slq'; _linear_solver.py:49-68 CG, tol 1e-6)
+ * ------------------------------------------------------------------------------------------------------- */
+/* Y = (K + eta I) X */
+int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* X,
+                int64_t B, double* Y, void* stream);
+/* V[i][c] = +-1 from a counter-based hash of (seed, probe_offset + c, i): identical for any batching / rank count */
+int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, void* stream);
+/* workspace for gp_col_dot / gp_lanczos / gp_cg_solve */
+int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B);
+/* out_dev[c] = sum_i X[i][c] Y[i][c] (deterministic two-stage reduction) */
+int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream);
+/* m Lanczos steps per column started from V (normalised internally); alpha_dev, beta_dev: (m x B) device arrays of
+ * the tridiagonal coefficients (beta[j] couples steps j and j+1). The quadrature itself is host-side. */
+int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* V,
+               int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);
+/* Batched CG from a zero start: X = (K + eta I)^-1 R0 column by column, stop at ||r|| <= tol ||b||. R0 is
+ * overwritten. Returns 0, or 1 when maxiter was reached first. */
+int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64_t n, double eta, double* R0, double* X,
+                int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused log-likelihood (+ gradient ingredients) evaluation at one (rho, eta)

@@ -1,0 +1,200 @@
+"""GPU parity tests (sparse path). Bar (BASELINE.json north_star): sparse pattern and CSR indices BIT-EXACT against the
+reference's compiled generator; values within a few ulp; stochastic-trace outputs within the estimator's own stated
+confidence band (at a fixed seed) around exact values from the CPU oracle."""
+
+import numpy
+import pytest
+import scipy.sparse
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def gp():
+    import gaussian_proc
+    return gaussian_proc
+
+
+def grid_points():
+    from oracle import data_utilities as du
+    return du.generate_points(40, 2, grid=True)
+
+
+@pytest.mark.parametrize('tag', ['rand', 'grid'])
+@pytest.mark.parametrize('nu', [0.5, 1.5, 2.5])
+def test_sparse_csr_bit_exact_pattern(gp, golden_generate, tag, nu):
+    pts = golden_generate['sparse_points'] if tag == 'rand' else grid_points()
+    S = gp.generate_correlation(pts, numpy.array([0.03, 0.03]), nu, sparse=True, density=0.01)
+    key = 'sparse_%s_nu%g_' % (tag, nu)
+    assert scipy.sparse.isspmatrix_csr(S)
+    assert S.indices.dtype == numpy.int32 and S.indptr.dtype == numpy.int32 and S.data.dtype == numpy.float64
+    assert (S.indptr == golden_generate[key + 'indptr']).all()
+    assert (S.indices == golden_generate[key + 'indices']).all()
+    ref = golden_generate[key + 'data']
+    assert numpy.max(numpy.abs(S.data - ref) / ref) <= 4 * 2.3e-16       # values: a few ulp (device exp)
+    assert S.has_sorted_indices and (S.diagonal() == 1.0).all()
+
+
+def test_kernel_threshold_bit_follows_reference():
+    from gaussian_proc._sparse import estimate_kernel_threshold
+    from oracle import matern
+    for (n, d, density, scale, nu) in [(1500, 2, 0.01, [0.03, 0.03], 0.5), (1600, 2, 0.01, [0.03, 0.03], 2.5),
+                                       (4000, 3, 0.005, [0.1, 0.2, 0.15], 1.5), (900, 1, 0.02, [0.05], 200.0),
+                                       (2 ** 20, 2, 1e-3, [0.005, 0.005], 0.5)]:
+        t = estimate_kernel_threshold(n, d, density, numpy.array(scale), nu)
+        assert t == matern.estimate_kernel_threshold(n, d, density, numpy.array(scale), nu)
+    with pytest.raises(ValueError):
+        estimate_kernel_threshold(50, 2, 1e-3, numpy.array([0.1, 0.1]), 0.5)
+
+
+def test_sparse_edge_cases(gp):
+    from oracle import matern
+    # 1-D and 3-D points, anisotropic scale, tiny n (single cell), explicit threshold
+    for (n, d, scale, nu, dens) in [(300, 1, [0.02], 0.5, 0.05), (500, 3, [0.2, 0.3, 0.25], 1.5, 0.02),
+                                    (64, 2, [0.5, 0.5], 2.5, 0.3), (700, 2, [0.02, 0.05], 1.5, 0.02)]:
+        numpy.random.seed(n)
+        pts = numpy.random.rand(n, d)
+        S = gp.generate_correlation(pts, numpy.array(scale), nu, sparse=True, density=dens)
+        R = matern.generate_sparse_correlation(pts, numpy.array(scale), nu, dens)
+        assert (S.indptr == R.indptr).all() and (S.indices == R.indices).all()
+        assert numpy.max(numpy.abs(S.data - R.data)) <= 1e-15
+    # duplicate points (distance exactly zero off the diagonal)
+    pts = numpy.random.rand(200, 2)
+    pts[17] = pts[3]
+    S = gp.generate_correlation(pts, 0.05, 0.5, sparse=True, density=0.05)
+    assert S[17, 3] == 1.0 and S[3, 17] == 1.0
+
+
+def test_sparse_device_handle_and_derivative(gp):
+    from gaussian_proc._sparse import generate_sparse_correlation
+    from oracle import matern
+    numpy.random.seed(5)
+    pts = numpy.random.rand(900, 2)
+    Kd = generate_sparse_correlation(pts, numpy.array([0.04, 0.04]), 1.5, 0.02, device=True, with_derivative=True)
+    S = Kd.to_scipy()
+    dK = matern.matern_derivative_rho(pts, 0.04, 1.5)
+    ref = dK[S.nonzero()]
+    got = scipy.sparse.csr_matrix((Kd.ddata.cpu().numpy(), S.indices, S.indptr), shape=S.shape)[S.nonzero()]
+    assert numpy.max(numpy.abs(numpy.asarray(got).ravel() - numpy.asarray(ref).ravel())) <= 1e-11
+
+
+def test_full_size_pattern_properties(gp):
+    """n = 2^20 (BASELINE configs[3]): sampled rows against the brute-force oracle row routine, plus symmetry of the
+    pattern, sortedness and unit diagonal."""
+    from gaussian_proc._sparse import generate_sparse_correlation
+    from oracle import matern
+    import ctypes
+    n = 2 ** 20
+    numpy.random.seed(0)
+    pts = numpy.random.rand(n, 2)
+    scale = numpy.array([0.005, 0.005])
+    Kd = generate_sparse_correlation(pts, scale, 0.5, 1e-3, device=True)
+    S = Kd.to_scipy()
+    assert S.shape == (n, n) and S.indices.dtype == numpy.int32
+    assert (numpy.diff(S.indptr) >= 1).all()
+    lib = matern._c()
+    tau = Kd.kernel_threshold
+    rows = [0, 1, 12345, 500000, n - 1]
+    for r in rows:
+        cnt = numpy.zeros(n, dtype=numpy.int64)
+        lib.oracle_sparse_rows(pts.ctypes.data, n, 2, scale.ctypes.data, 0.5, tau, 0, r, r + 1, cnt.ctypes.data, None, None, None)
+        k = int(cnt[r])
+        ip = numpy.zeros(n + 1, dtype=numpy.int64)
+        idx = numpy.zeros(k, dtype=numpy.int32)
+        dat = numpy.zeros(k)
+        lib.oracle_sparse_rows(pts.ctypes.data, n, 2, scale.ctypes.data, 0.5, tau, 1, r, r + 1, None, ip.ctypes.data,
+                               idx.ctypes.data, dat.ctypes.data)
+        got = S.indices[S.indptr[r]:S.indptr[r + 1]]
+        assert len(got) == k and (got == idx).all()
+        assert numpy.max(numpy.abs(S.data[S.indptr[r]:S.indptr[r + 1]] - dat)) <= 1e-15
+    sub = S[:20000]
+    assert (numpy.diff(sub.indices) > 0)[numpy.diff(numpy.repeat(numpy.arange(20000), numpy.diff(sub.indptr))) == 0].all()
+    # pattern symmetry on a block
+    blk = S[:5000, :5000]
+    assert (abs(blk - blk.T) > 0).nnz == 0
+
+
+# --------------------------------------------------------------------------------------------- sparse operator
+@pytest.fixture(scope='module')
+def sparse_problem(gp):
+    from oracle import data_utilities as du
+    from gaussian_proc._sparse import generate_sparse_correlation
+    numpy.random.seed(1)
+    pts = numpy.random.rand(3000, 2)
+    Kd = generate_sparse_correlation(pts, numpy.array([0.03, 0.03]), 0.5, 0.01, device=True, with_derivative=True)
+    return pts, du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2), Kd
+
+
+def test_spmm_dot_solve(sparse_problem):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    pts, z, X, Kd = sparse_problem
+    S = Kd.to_scipy()
+    Km = MixedCorrelation(Kd, imate_method='slq')
+    assert Km.get_matrix_size() == 3000
+    assert numpy.max(numpy.abs(Km.dot(0.7, z) - (S @ z + 0.7 * z))) <= 1e-12
+    assert numpy.max(numpy.abs(Km.dot(0, X) - S @ X)) <= 1e-12
+    eta = 2.0
+    A = (S + eta * scipy.sparse.eye(3000)).toarray()
+    ref = numpy.linalg.solve(A, numpy.c_[X, z])
+    sol = Km.solve(eta, numpy.c_[X, z])
+    # the reference's CG stops at ||r|| <= 1e-6 ||b|| (_linear_solver.py:24): same rule here
+    r = A @ sol - numpy.c_[X, z]
+    assert (numpy.linalg.norm(r, axis=0) <= 1e-6 * numpy.linalg.norm(numpy.c_[X, z], axis=0)).all()
+    assert numpy.max(numpy.abs(sol - ref)) / numpy.max(numpy.abs(ref)) <= 1e-5
+    assert abs(Km.trace(0.5) - (S.diagonal().sum() + 0.5 * 3000)) <= 1e-9
+
+
+def test_probes_are_batching_invariant(sparse_problem):
+    from gaussian_proc._sparse import SparseEngine
+    eng = SparseEngine(sparse_problem[3])
+    V8 = eng.probes(0, 8).cpu().numpy()
+    V4 = eng.probes(4, 4).cpu().numpy()
+    assert (V8[:, 4:] == V4).all() and set(numpy.unique(V8)) == {-1.0, 1.0}
+    assert abs(V8.mean()) < 0.02
+
+
+@pytest.mark.parametrize('method', ['slq', 'hutchinson'])
+def test_stochastic_estimates_within_confidence_band(sparse_problem, method):
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    pts, z, X, Kd = sparse_problem
+    S = Kd.to_scipy()
+    n = S.shape[0]
+    for eta in (1.0, 10.0):
+        A = (S + eta * scipy.sparse.eye(n)).toarray()
+        w = numpy.linalg.eigvalsh(A)
+        assert w.min() > 0
+        Km = MixedCorrelation(Kd, imate_method=method, imate_options={'seed': 0, 'lanczos_degree': 30})
+        ld = Km.logdet(eta)
+        band = Km.engine.last_info['half_width'][0]
+        exact = numpy.sum(numpy.log(w))
+        assert abs(ld - exact) <= max(band, 0.01 * abs(exact)) and band <= 0.011 * abs(exact) + 1e-9
+        ti = Km.traceinv(eta)
+        exact_ti = numpy.sum(1.0 / w)
+        assert abs(ti - exact_ti) <= 0.012 * exact_ti
+        # derivative trace (Hutchinson + CG), exact value from the dense inverse
+        dS = scipy.sparse.csr_matrix((Kd.ddata.cpu().numpy(), S.indices, S.indptr), shape=S.shape).toarray()
+        exact_d = numpy.sum(numpy.linalg.inv(A) * dS)
+        est = Km.engine.traceinv_dK(eta)
+        half = Km.engine.last_info['half_width'][0]
+        assert abs(est - exact_d) <= max(2.0 * half, 0.02 * abs(exact_d))
+
+
+def test_indefinite_matrix_is_reported(gp):
+    """hard-thresholded Matern is not positive definite; small eta must be reported, not silently used."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    numpy.random.seed(3)
+    pts = numpy.random.rand(2000, 2)
+    S = gp.generate_correlation(pts, 0.02, 2.5, sparse=True, density=5e-3)
+    lam = scipy.sparse.linalg.eigsh(S, k=1, which='SA', return_eigenvectors=False)[0]
+    if lam < -0.05:
+        Km = MixedCorrelation(S, imate_method='slq', imate_options={'lanczos_degree': 60})
+        with pytest.raises(numpy.linalg.LinAlgError):
+            Km.logdet(1e-3)
+
+
+def test_likelihood_through_sparse_operator(sparse_problem):
+    """Q9: a sparse K can be trained through the Likelihood API (the reference cannot: eigh(sparse) raises)."""
+    from gaussian_proc._likelihood import Likelihood
+    pts, z, X, Kd = sparse_problem
+    lk = Likelihood(X, Kd.to_scipy(), likelihood_method='profiled')
+    assert lk.K_mixed.sparse and lk.K_mixed.imate_method == 'slq'
