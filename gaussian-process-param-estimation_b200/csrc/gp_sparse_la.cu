@@ -86,8 +86,9 @@ __global__ void col_final_kernel(const double* partial, int nparts, int B, int o
         s1[c] = bt;
         s2[c] = (bt > 1e-300) ? 1.0 / bt : 0.0;
     } else if (op == 3) {
-        // s1 = rr, s2 = active flag (1/0), out = alpha
-        out[c] = (s2[c] != 0.0 && s != 0.0) ? s1[c] / s : 0.0;
+        // s1 = rr, s2 = active flag (1/0), s3 = breakdown flag, out = alpha
+        if (s2[c] != 0.0 && !(s > 0.0)) { s3[0] = 1.0; s2[c] = 0.0; }   // p^T A p <= 0: A is not positive definite
+        out[c] = (s2[c] != 0.0) ? s1[c] / s : 0.0;
     } else {
         // s1 = rr (updated), s2 = active, s3 = bb, out = beta
         double rr_old = s1[c];
@@ -239,10 +240,11 @@ int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64
     double* AP = (double*)(base + vb);
     double* partial = (double*)(base + 4 * vb);
     double* sc = (double*)(base + 4 * vb + al256(sizeof(double) * RED_PARTS * 32));
-    double *rr = sc, *active = sc + 32, *bb = sc + 64, *alpha = sc + 96, *beta = sc + 128;
+    double *rr = sc, *active = sc + 32, *bb = sc + 64, *alpha = sc + 96, *beta = sc + 128, *flag = sc + 160;
     const unsigned eb = (unsigned)((total + 255) / 256);
     const double tol2 = tol * tol;
     GP_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(double) * total, s));
+    GP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(double) * 32, s));
     GP_CUDA_CHECK(cudaMemcpyAsync(Pd, R0, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, R0, R0, nullptr, nullptr, nullptr, nullptr, partial);
     col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 0, rr, nullptr, nullptr, nullptr, 0.0);
@@ -260,15 +262,18 @@ int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64
         int rc = spmm(indptr, indices, data, N, eta, Pd, Bc, AP, s);
         if (rc) return rc;
         col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, Pd, AP, nullptr, nullptr, nullptr, nullptr, partial);
-        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 3, alpha, rr, active, nullptr, 0.0);
+        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 3, alpha, rr, active, flag, 0.0);
         col_fused_kernel<2><<<RED_PARTS, 256, 0, s>>>(total, Bc, Pd, AP, R0, X, alpha, nullptr, partial);
         col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 4, beta, rr, active, bb, tol2);
         cg_direction_kernel<<<eb, 256, 0, s>>>(total, Bc, R0, beta, Pd);
         GP_COUNT(5);
         ++it;
         if (it % check_every == 0 || it == maxiter) {
+            double brk = 0.0;
             GP_CUDA_CHECK(cudaMemcpyAsync(act, active, sizeof(double) * 32, cudaMemcpyDeviceToHost, s));
+            GP_CUDA_CHECK(cudaMemcpyAsync(&brk, flag, sizeof(double), cudaMemcpyDeviceToHost, s));
             GP_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (brk != 0.0) { if (iters_host) *iters_host = it; return 2; }
             bool any = false;
             for (int c = 0; c < B; ++c) any = any || (act[c] != 0.0);
             if (!any) { converged = true; break; }
@@ -276,7 +281,7 @@ int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64
     }
     GP_LAUNCH_CHECK();
     if (iters_host) *iters_host = it;
-    return converged ? 0 : 1;
+    return converged ? 0 : 1;  // 2 (above): negative curvature met, K + eta I is not positive definite
 }
 
 }  // extern "C"

@@ -311,6 +311,10 @@ class SparseEngine(object):
                              _p(self._workspace(B)), dev.stream_ptr())
         check(rc, 'gp_cg_solve')
         self.last_cg_iterations = it.value
+        if rc == 2:
+            raise numpy.linalg.LinAlgError(
+                'K + eta*I (eta=%g) is not positive definite (CG met p^T A p <= 0). The thresholded Matern matrix is '
+                'indefinite; use a larger eta (reference: _generate_sparse_correlation.pyx:516-523).' % eta)
         if rc == 1:
             raise numpy.linalg.LinAlgError('CG did not converge in %d iterations (eta=%g)' % (it.value, eta))
         return X

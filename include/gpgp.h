@@ -138,7 +138,8 @@ int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* o
 int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* V,
                int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);
 /* Batched CG from a zero start: X = (K + eta I)^-1 R0 column by column, stop at ||r|| <= tol ||b||. R0 is
- * overwritten. Returns 0, or 1 when maxiter was reached first. */
+ * overwritten. Returns 0; 1 when maxiter was reached first; 2 when p^T A p <= 0 was met (K + eta I not positive
+ * definite: the hard-thresholded Matern matrix is indefinite, _generate_sparse_correlation.pyx:516-523). */
 int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64_t n, double eta, double* R0, double* X,
                 int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream);
 
