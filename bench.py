@@ -169,6 +169,77 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------- secondary workloads (reported, not the metric)
+def secondary_measurements():
+    """Bounded (~20 s) measurements of the other BASELINE.json configs on one GPU: configs[2] grid sweep at n = 8000
+    (cells/s for one rho group) and configs[3] sparse n = 2^20 (generation, SpMM bandwidth, SLQ logdet + Hutchinson
+    tr(Kn^-1 dK) evaluation). HBM roofline fractions use MEASURED_PEAKS.json's hbm_gbs when present."""
+    import torch
+    from gaussian_proc.sweep import likelihood_grid
+    from gaussian_proc._sparse import generate_sparse_correlation, SparseEngine
+    hbm = 6536.7
+    try:
+        hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:  # noqa: BLE001
+        pass
+    out = {}
+    # configs[2]: one rho group (K generated once) x 8 eta values at n = 8000
+    pts, z, X = make_inputs(8000)
+    etas = numpy.logspace(-2, 2, 8)
+    likelihood_grid(pts, z, X, NU, [0.1], etas[:2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    G = likelihood_grid(pts, z, X, NU, [0.1, 0.2], etas)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['sweep_n8k'] = {'cells': int(G.shape[0] * G.shape[1]), 'cells_per_s': G.shape[0] * G.shape[1] / dt,
+                        'workload': 'configs[2] slice: n=8000, 2 rho x 8 eta, l^ + d/d eta + d/d rho per cell',
+                        'tflops': G.shape[0] * G.shape[1] * 8000.0 ** 3 / dt * 1e-12}
+    # configs[3]: sparse n = 2^20, nu = 0.5, rho = 0.005, density 1e-3
+    n = 2 ** 20
+    numpy.random.seed(0)
+    sp = numpy.random.rand(n, 2)
+    scale = numpy.array([0.005, 0.005])
+    generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    K = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
+    torch.cuda.synchronize()
+    tg = time.perf_counter() - t0
+    eng = SparseEngine(K, 'slq', {'seed': 0, 'lanczos_degree': 30})
+    spm = {}
+    for B in (1, 8):
+        V = eng.probes(0, B)
+        eng.spmm(1.0, V)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            eng.spmm(1.0, V)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = (12.0 * K.nnz + 4.0 * (n + 1) + 16.0 * n * B) / ms * 1e-6
+        spm['B%d' % B] = {'ms': ms, 'GBs': gbs, 'frac_of_measured_hbm': gbs / hbm}
+    eta = 10.0     # lambda_min(K) ~ -1.2 for this hard-thresholded matrix: eta = 1 is indefinite (SURVEY Q11)
+    eng.logdet(eta)
+    eng._slq_cache = {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ld = eng.logdet(eta)
+    info = dict(eng.last_info)
+    tr = eng.traceinv_dK(eta)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    out['sparse_n1M'] = {'workload': 'configs[3]: n=2^20 random 2-D points, nu=0.5, rho=0.005, density=1e-3, eta=10',
+                         'nnz': K.nnz, 'generate_s': tg, 'generate_GBs': (20.0 * K.nnz + 4.0 * (n + 1)) / tg * 1e-9,
+                         'spmm': spm, 'evals_per_s': 1.0 / te,
+                         'eval': 'SLQ logdet + traceinv (degree 30, <= 50 Rademacher probes, rtol 1e-2 @ 95 %) + Hutchinson/CG '
+                                 'tr(Kn^-1 dK/drho)',
+                         'logdet': ld, 'logdet_half_width': float(info['half_width'][0]), 'num_samples': info['num_samples'],
+                         'trace_Kninv_dK': tr}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -317,6 +388,13 @@ def run_ours(args):
                            'l2': 'inputs larger than L2 (K = %.1f GB per evaluation)' % (npad * npad * 8e-9),
                            'parallelism': 'independent cells per GPU (replicas), results all-gathered'},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
+        if world == 1 and not args.no_secondary:
+            del hp, hz, hX
+            torch.cuda.empty_cache()
+            try:
+                line['secondary'] = secondary_measurements()
+            except Exception as e:  # noqa: BLE001 -- the headline must still print
+                line['secondary'] = {'error': repr(e)[:300]}
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_sample(int(os.environ.get('GP_BENCH_CPU_N', '3000')), n)
         print(json.dumps(line))
@@ -331,6 +409,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the sparse / sweep secondary measurements')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -130,6 +130,56 @@ static int launch_mode(const double* pts, int n, int d, int npad, double* K, dou
     return 0;
 }
 
+// ---- rectangular cross-correlation block K(P_rows, P_cols) for distributed (block-cyclic) layouts -----------------
+// Global indices decide the special cases: identity padding for indices >= n, exactly 1 (+ eta) on the diagonal.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+matern_cross_kernel(const double* __restrict__ prow, const double* __restrict__ pcol, const int* __restrict__ rg,
+                    const int* __restrict__ cg, int n, int d, int64_t ld, double* __restrict__ out, double eta, MaternParams mp) {
+    __shared__ double sr[MAXD][64];
+    __shared__ double sc[MAXD][128];
+    __shared__ int gr[64], gc[128];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 128, tid = threadIdx.x;
+    for (int idx = tid; idx < 64 * d; idx += 256) { int r = idx / d, k = idx - r * d; sr[k][r] = prow[(int64_t)(r0 + r) * d + k]; }
+    for (int idx = tid; idx < 128 * d; idx += 256) { int r = idx / d, k = idx - r * d; sc[k][r] = pcol[(int64_t)(c0 + r) * d + k]; }
+    if (tid < 64) gr[tid] = rg[r0 + tid];
+    if (tid < 128) gc[tid] = cg[c0 + tid];
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int rr = ty; rr < 64; rr += 8) {
+        const int gi = gr[rr];
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cl = tx * 4 + e, gj = gc[cl];
+            double val;
+            if (gi >= n || gj >= n) val = (gi == gj) ? 1.0 : 0.0;
+            else if (gi == gj) val = 1.0 + eta;
+            else {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < MAXD; ++k)
+                    if (k < d) { double t = (sr[k][rr] - sc[k][cl]) * mp.inv_scale[k]; s += t * t; }
+                val = matern_value<MODE>(sqrt(s), mp);
+            }
+            v[e] = val;
+        }
+        double* dst = out + (int64_t)(r0 + rr) * ld + c0 + tx * 4;
+        reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
+        reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
+    }
+}
+
+template <int MODE>
+static int launch_cross(const double* prow, const double* pcol, const int* rg, const int* cg, int nr, int nc, int n, int d,
+                        int64_t ld, double* out, double eta, const MaternParams& mp, cudaStream_t s) {
+    dim3 grid(nc / 128, nr / 64);
+    matern_cross_kernel<MODE><<<grid, 256, 0, s>>>(prow, pcol, rg, cg, n, d, ld, out, eta, mp);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace gp
 
 extern "C" int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* scale_host, double nu,
@@ -161,5 +211,36 @@ extern "C" int gp_matern_dense(const double* points, int64_t n, int64_t d, const
         case MAT_25: return launch_mode<MAT_25>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
         case MAT_GAUSS: return launch_mode<MAT_GAUSS>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
         default: return launch_mode<MAT_GENERAL>(points, (int)n, (int)d, (int)npad, K, dK, mp, s);
+    }
+}
+
+// out[r][c] = K(p_row[r], p_col[c]) (+ eta on the global diagonal) for nr x nc blocks of a larger padded matrix;
+// row_gidx / col_gidx are the global indices of the rows / columns (device int32), n the unpadded global size.
+extern "C" int gp_matern_cross(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                               int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
+                               int64_t ld, void* stream) {
+    using namespace gp;
+    if (!prow || !pcol || !row_gidx || !col_gidx || !out || !scale_host || nr <= 0 || nc <= 0 || (nr % 64) || (nc % 128) || d <= 0 ||
+        d > MAXD || (ld & 1))
+        return -1;
+    MaternParams mp;
+    for (int k = 0; k < d; ++k) {
+        if (!(scale_host[k] > 0.0)) return -3;
+        mp.inv_scale[k] = 1.0 / scale_host[k];
+    }
+    mp.nu = nu; mp.coef = 0.0; mp.sq2nu = 0.0; mp.inv_rho = 1.0 / scale_host[0];
+    int mode = matern_mode_of(nu);
+    if (mode == MAT_GENERAL) {
+        if (!(nu > 0.0)) return -5;
+        mp.coef = pow(2.0, 1.0 - nu) / tgamma(nu);
+        mp.sq2nu = sqrt(2.0 * nu);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mode) {
+        case MAT_05: return launch_cross<MAT_05>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
+        case MAT_15: return launch_cross<MAT_15>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
+        case MAT_25: return launch_cross<MAT_25>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
+        case MAT_GAUSS: return launch_cross<MAT_GAUSS>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
+        default: return launch_cross<MAT_GENERAL>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
     }
 }

@@ -52,6 +52,13 @@ int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launche
 int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* scale_host, double nu,
                     double* K, int64_t ldk, double* dK, void* stream);
 
+/* Rectangular block out[r][c] = matern(||(prow_r - pcol_c) / scale||, nu) of a larger (block-cyclic distributed) padded
+ * matrix: row_gidx / col_gidx (device int32) carry the GLOBAL indices, n the unpadded global size; entries with a global
+ * index >= n form the identity padding, the global diagonal is exactly 1 + eta. nr % 64 == 0, nc % 128 == 0. */
+int gp_matern_cross(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                    int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
+                    int64_t ld, void* stream);
+
 /* tau = matern(kernel_radius(density), nu): host-only, bit-follows _estimate_kernel_threshold
  * (_generate_sparse_correlation.pyx:294-413, with the missing `dimension` argument of :390 supplied).
  * Returns -10 when density * n < 1 (the reference raises ValueError, :378-383). */

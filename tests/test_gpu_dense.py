@@ -257,3 +257,70 @@ def test_full_size_n20k_properties(gp):
     _, deta, drho = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
     assert abs((lp1 - lp0) / (2 * h * eta) - deta) <= 1e-5 * abs(deta)
     assert numpy.isfinite(drho)
+
+
+# ------------------------------------------------------------ configs[0]: ~1k points, nu = 1.5, full MLE drivers
+def test_config0_direct_and_profiled_training_match_oracle_drivers(gp):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): n = 1000 random 2-D points, nu = 1.5, rho = 0.1.
+    The same optimiser / root-finder code drives the GPU evaluations and the oracle's; results must agree."""
+    import scipy.optimize
+    from functools import partial
+    from oracle import data_utilities as du, likelihood as L, matern
+    numpy.random.seed(0)
+    pts = numpy.random.rand(1000, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    K = gp.generate_correlation(pts, 0.1, 1.5)
+    Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, 0.1, 1.5), 'cholesky')
+    # profiled: root of d l/d eta on [1e-4, 1e3] (likelihood.py:86-94)
+    res = gp.GaussianProcess(X, K, likelihood_method='profiled').train(z)
+    ref = L.ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Ko, [1e-4, 1e3])
+    assert rel([res['sigma'], res['sigma0'], res['eta']], [ref['sigma'], ref['sigma0'], ref['eta']]) <= 1e-7
+    # direct: trust-exact from (0.2, 0.2) with the (variance-space) jacobian and hessian, tol 1e-3 (:378-384)
+    res = gp.GaussianProcess(X, K, likelihood_method='direct').train(z)
+    o = scipy.optimize.minimize(partial(L.DirectLikelihood.log_likelihood, z, X, Ko, True), [0.2, 0.2], method='trust-exact',
+                                tol=1e-3, jac=partial(L.DirectLikelihood.log_likelihood_jacobian, z, X, Ko, True),
+                                hess=partial(L.DirectLikelihood.log_likelihood_hessian, z, X, Ko, True))
+    assert rel([res['sigma'], res['sigma0']], o.x) <= 1e-6 and abs(res['max_lp'] + o.fun) <= 1e-7 * abs(o.fun)
+
+
+def test_grid_sweep_matches_oracle(gp):
+    """configs[2] in miniature: (rho x eta) grid of profile likelihoods and both derivatives."""
+    from gaussian_proc.sweep import likelihood_grid
+    from oracle import data_utilities as du, likelihood as L, matern
+    numpy.random.seed(4)
+    pts = numpy.random.rand(400, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    rhos, etas = numpy.linspace(0.05, 0.3, 3), numpy.logspace(-1, 1, 3)
+    G = likelihood_grid(pts, z, X, 2.5, rhos, etas)
+    assert G.shape == (3, 3, 3) and numpy.isfinite(G).all()
+    for i, rho in enumerate(rhos):
+        Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, rho, 2.5), 'cholesky')
+        dK = matern.matern_derivative_rho(pts, rho, 2.5)
+        for j, eta in enumerate(etas):
+            sig = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, eta)
+            ref = [L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [sig, eta]),
+                   L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(eta)),
+                   L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dK, eta)]
+            assert rel(G[i, j], ref) <= 1e-8, (rho, eta)
+
+
+def test_block_cyclic_single_rank_matches_dense_engine(gp):
+    """The 2-D block-cyclic Cholesky on a 1x1 grid (the multi-rank algorithm itself is covered on CPU/gloo in
+    tests/test_blockcyclic_cpu.py and on 2/4 GPUs by tools/gpu_check_blockcyclic.py): GPU ops through the C ABI."""
+    from oracle import data_utilities as du, likelihood as L, matern
+    from gaussian_proc._blockcyclic import BlockCyclicCholesky
+    numpy.random.seed(0)
+    pts = numpy.random.rand(1000, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=256)
+    lp, sig = bc.profile_log_likelihood(z, X, 0.3)
+    Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, 0.1, 2.5), 'cholesky')
+    s0 = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, 0.3)
+    assert abs(lp - L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [s0, 0.3])) <= RTOL * abs(lp)
+    assert abs(bc.logdet() - Ko.logdet(0.3)) <= RTOL * abs(Ko.logdet(0.3))
+    assert rel(bc.solve(numpy.c_[X, z]), Ko.solve(0.3, numpy.c_[X, z])) <= RTOL
+    with pytest.raises(numpy.linalg.LinAlgError):
+        bc.factor(-2.0)

@@ -1,0 +1,63 @@
+"""Developer check (multi-GPU, run under torchrun): 2-D block-cyclic Cholesky vs the single-GPU dense engine, then a
+timed large-n factorisation.  torchrun --nproc-per-node N tools/gpu_check_blockcyclic.py [n_big] [nb]"""
+import json, os, sys, time
+import numpy
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'gaussian-process-param-estimation_b200'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch
+import torch.distributed as dist
+
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank = int(os.environ.get('RANK', '0'))
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+import bench
+from gaussian_proc._blockcyclic import BlockCyclicCholesky
+from gaussian_proc import generate_correlation
+from gaussian_proc._mixed_correlation import MixedCorrelation
+from gaussian_proc._likelihood import ProfileLikelihood
+
+out = {'world': world}
+# ---- correctness at n = 6000 against the single-GPU path ------------------------------------------------------
+n = 6000
+pts, z, X = bench.make_inputs(n)
+bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=512)
+out['grid'] = [bc.P_r, bc.P_c]
+lp, sig = bc.profile_log_likelihood(z, X, 0.1)
+ld = bc.logdet()
+sol = bc.solve(z)
+Km = MixedCorrelation(generate_correlation(pts, 0.1, 2.5, device=True))
+ref_lp = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1, with_rho=False)[0]
+ref_ld = Km.logdet(0.1)
+ref_sol = Km.solve(0.1, z)
+out['check'] = {'lp_rel': abs(lp - ref_lp) / abs(ref_lp), 'logdet_rel': abs(ld - ref_ld) / abs(ref_ld),
+                'solve_rel': float(numpy.max(numpy.abs(sol - ref_sol)) / numpy.max(numpy.abs(ref_sol)))}
+del Km, bc
+torch.cuda.empty_cache()
+# ---- timing ------------------------------------------------------------------------------------------------------
+nbig = int(sys.argv[1]) if len(sys.argv) > 1 else 40960
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+numpy.random.seed(0)
+pts = numpy.random.rand(nbig, 2)
+bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
+for rep in range(2):
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    t0 = time.perf_counter()
+    bc.generate(0.1)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    bc.factor(0.1)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    t2 = time.perf_counter()
+out['big'] = {'n': nbig, 'nb': nb, 't_generate_s': t1 - t0, 't_generate_factor_s': t2 - t1,
+              'potrf_tflops_total': (nbig ** 3 / 3.0) / (t2 - t1) * 1e-12, 'bytes_received_per_rank': bc.bytes_received,
+              'logdet': bc.logdet()}
+if rank == 0:
+    print(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()
