@@ -1,8 +1,8 @@
 // FP64 tensor-core (DMMA) GEMM for the Cholesky / inverse hot path.
 //
-// One 128x128 output tile per CTA, 8 warps (2x4), warp tile 64x32 built from m8n8k4 DMMA fragments,
-// BK=32 k-slabs moved global->shared with cp.async through a 3-stage ring (measured: 2-6 % over BK=16 x 4 stages,
-// the per-slab CTA barrier is the main loss against the raw DMMA issue rate). Shared tiles are XOR-swizzled
+// One 128 x BN output tile per CTA (BN = 64: 4 warps, two CTAs per SM; BN = 128: 8 warps), warp tile 64x32 built from
+// m8n8k4 DMMA fragments, k-slabs moved global->shared with cp.async through a multi-stage ring (measured: the per-slab
+// CTA barrier is the main loss against the raw DMMA issue rate, ~7 %; see Cfg below). Shared tiles are XOR-swizzled
 // so that both the 16-byte cp.async stores and the 8-byte fragment loads are bank-conflict free for
 // K-major ([mn][k]) as well as MN-major ([k][mn]) operands; this lets one kernel serve
 //   NT: trailing SYRK/GEMM update and the panel TRSM-by-inverse   (potrf)
@@ -11,6 +11,7 @@
 // Triangular operands are exploited by restricting each tile's k-range, never by element masks.
 #include "gp_common.cuh"
 #include "gp_internal.h"
+#include <stdlib.h>
 #include <vector>
 
 namespace gp {
@@ -27,66 +28,71 @@ struct GemmProfile {
 };
 static GemmProfile g_prof;
 
-static double tile_flops(int tiles_m, int tiles_n, int K, int krange, int tmask) {
+static double tile_flops(int tiles_m, int tiles_n, int bn, int K, int krange, int tmask) {
     double kt = 0.0;  // sum over computed tiles of their k extent
     for (int tm = 0; tm < tiles_m; ++tm) {
-        int ncols = (tmask == TM_LOWER) ? (tm + 1 < tiles_n ? tm + 1 : tiles_n) : tiles_n;
+        int lim = ((tm + 1) * 128) / bn;  // tiles with n0 < m0 + 128
+        int ncols = (tmask == TM_LOWER) ? (lim < tiles_n ? lim : tiles_n) : tiles_n;
         if (krange == KR_FULL) kt += (double)ncols * K;
         else if (krange == KR_A_LOWER) kt += (double)ncols * ((tm + 1) * 128 < K ? (tm + 1) * 128 : K);
-        else if (krange == KR_TN_LOWER) kt += (double)ncols * (K - (tm * 128 < K ? tm * 128 : K));
-        else for (int tn = 0; tn < ncols; ++tn) kt += (double)(K - (tn * 128 < K ? tn * 128 : K));
+        else for (int tn = 0; tn < ncols; ++tn) {
+            int kb = (krange == KR_B_LOWER) ? tn * bn : (tm * 128 > tn * bn ? tm * 128 : tn * bn);
+            kt += (double)(K - (kb < K ? kb : K));
+        }
     }
-    return 2.0 * 128.0 * 128.0 * kt;
+    return 2.0 * 128.0 * bn * kt;
 }
 
-#ifndef GP_BK
-#define GP_BK 32
-#endif
-#ifndef GP_STAGES
-#define GP_STAGES 3
-#endif
-#ifndef GP_WM
-#define GP_WM 64
-#endif
-#ifndef GP_WN
-#define GP_WN 32
-#endif
-constexpr int BM = 128, BN = 128, BK = GP_BK, STAGES = GP_STAGES;
-constexpr int WM = GP_WM, WN = GP_WN;
-constexpr int WARPS_N = BN / WN, GEMM_THREADS = (BM / WM) * (BN / WN) * 32;
-constexpr int MI = WM / 8, NI = WN / 8;
-constexpr int TILE_ELEMS = 128 * BK;  // doubles per operand tile per stage
-constexpr int CHUNKS_PER_THREAD = TILE_ELEMS / 2 / GEMM_THREADS;
-constexpr int GEMM_SMEM = STAGES * 2 * TILE_ELEMS * (int)sizeof(double);
+constexpr int BM = 128, WM = 64, WN = 32, MI = WM / 8, NI = WN / 8;
 constexpr int RASTER_GROUP = 8;
 
-// shared-memory offset (in doubles) of logical element (mn, k) of an operand tile
-template <int T>
+// Two tile shapes share one kernel body:
+//   BN = 128: 8 warps, BK = 32 x 3 stages (192 KB), one CTA per SM. Needed where C aliases an operand (in-place panel
+//             solve: a CTA must own the full row block it overwrites).
+//   BN = 64 : 4 warps, BK = 16 x 4 stages (96 KB), TWO CTAs per SM: while one CTA sits in its per-slab barrier, its
+//             prologue or its C read-modify-write epilogue, the other keeps the FP64 tensor pipe busy.
+template <int BN_>
+struct Cfg {
+    static constexpr int BN = BN_;
+    static constexpr int BK = (BN_ == 128) ? 32 : 16;
+    static constexpr int STAGES = (BN_ == 128) ? 3 : 4;
+    static constexpr int WARPS_N = BN_ / WN;
+    static constexpr int THREADS = (BM / WM) * WARPS_N * 32;
+    static constexpr int A_ELEMS = BM * BK, B_ELEMS = BN_ * BK, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr int SMEM = STAGES * STAGE_ELEMS * (int)sizeof(double);
+    static constexpr int MIN_CTAS = (BN_ == 128) ? 1 : 2;
+};
+
+// shared-memory offset (in doubles) of logical element (mn, k) of an operand tile with ROWS mn-rows
+template <int T, int ROWS, int BK>
 __device__ __forceinline__ int soff(int mn, int k) {
-    if (T == 0) return mn * BK + (((k >> 2) ^ (mn & 3)) << 2) + (k & 3);  // [128][BK], 4-double chunks swizzled by row
-    return k * 128 + (mn ^ ((k & 3) << 2));                                // [16][128], mn bits 2..3 swizzled by k
+    if (T == 0) return mn * BK + (((k >> 2) ^ (mn & 3)) << 2) + (k & 3);  // [ROWS][BK], 4-double chunks swizzled by row
+    return k * ROWS + (mn ^ ((k & 3) << 2));                               // [BK][ROWS], mn bits 2..3 swizzled by k
 }
 
-// copy one operand tile (128 mn x 16 k) into shared memory; g points at logical element (mn0, k0)
-template <int T>
+// copy one operand tile (ROWS mn x BK k) into shared memory; g points at logical element (mn0, k0)
+template <int T, int ROWS, int BK, int THREADS>
 __device__ __forceinline__ void load_tile(double* tile, const double* g, int64_t ld, int tid) {
+    constexpr int CHUNKS = ROWS * BK / 2;
 #pragma unroll
-    for (int i = 0; i < CHUNKS_PER_THREAD; ++i) {
-        int idx = tid + i * GEMM_THREADS;
+    for (int i = 0; i < CHUNKS / THREADS; ++i) {
+        int idx = tid + i * THREADS;
         if (T == 0) {
             int r = idx / (BK / 2), c = idx % (BK / 2);  // row r, 16-byte chunk c (k = 2c, 2c+1)
             cp_async16(tile + r * BK + ((c >> 1) ^ (r & 3)) * 4 + ((c & 1) << 1), g + (int64_t)r * ld + 2 * c);
         } else {
-            int kr = idx >> 6, c = idx & 63;  // k-row kr, chunk c (mn = 2c, 2c+1)
-            cp_async16(tile + kr * 128 + ((2 * c) ^ ((kr & 3) << 2)), g + (int64_t)kr * ld + 2 * c);
+            int kr = idx / (ROWS / 2), c = idx % (ROWS / 2);  // k-row kr, chunk c (mn = 2c, 2c+1)
+            cp_async16(tile + kr * ROWS + ((2 * c) ^ ((kr & 3) << 2)), g + (int64_t)kr * ld + 2 * c);
         }
     }
 }
 
-template <int AT, int BT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int AT, int BT, int BN_>
+__global__ void __launch_bounds__(Cfg<BN_>::THREADS, Cfg<BN_>::MIN_CTAS)
 dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                   int tiles_m, int tiles_n, int K, double alpha, double beta, int krange, int tmask) {
+    using G = Cfg<BN_>;
+    constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES, THREADS = G::THREADS;
     extern __shared__ __align__(16) double smem[];
 
     // grouped rasterisation: RASTER_GROUP tile-rows share each B tile while it is hot in L2
@@ -98,18 +104,19 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     int rem = bid - grp * group_sz;
     int tm = first_m + rem % rows_in_grp;
     int tn = rem / rows_in_grp;
-    if (tmask == TM_LOWER && tn > tm) return;
-
     const int m0 = tm * BM, n0 = tn * BN;
+    if (tmask == TM_LOWER && n0 >= m0 + BM) return;
+
     int kbeg = 0, kend = K;
     if (krange == KR_A_LOWER) kend = min(K, m0 + BM);
     else if (krange == KR_B_LOWER) kbeg = min(n0, K);
     else if (krange == KR_TN_LOWER) kbeg = min(max(m0, n0), K);
+    kbeg = (kbeg / BK) * BK;
     const int KT = (kend - kbeg) / BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp / WARPS_N) * WM, wn = (warp % WARPS_N) * WN;
+    const int wm = (warp / G::WARPS_N) * WM, wn = (warp % G::WARPS_N) * WN;
 
     const double* Ag = (AT == 0) ? A + (int64_t)m0 * lda + kbeg : A + (int64_t)kbeg * lda + m0;
     const double* Bg = (BT == 0) ? B + (int64_t)n0 * ldb + kbeg : B + (int64_t)kbeg * ldb + n0;
@@ -123,12 +130,13 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     if (beta != 0.0) {
-        // the epilogue read-modify-writes a 128 KB tile of C that streams from HBM: pull it into L2 now so those
-        // loads cost an L2 hit instead of a DRAM round trip each (1024 lines of 128 B, 4 per thread)
+        // the epilogue read-modify-writes a tile of C that streams from HBM: pull it into L2 now so those loads cost
+        // an L2 hit instead of a DRAM round trip each (128 rows x BN/16 lines of 128 B)
+        constexpr int LINES = BM * BN / 16;
 #pragma unroll
-        for (int i = 0; i < 1024 / GEMM_THREADS; ++i) {
-            int line = tid + i * GEMM_THREADS;  // row = line >> 3, 128-byte segment = line & 7
-            const double* pc = C + (int64_t)(m0 + (line >> 3)) * ldc + n0 + ((line & 7) << 4);
+        for (int i = 0; i < LINES / THREADS; ++i) {
+            int line = tid + i * THREADS;
+            const double* pc = C + (int64_t)(m0 + line / (BN / 16)) * ldc + n0 + ((line % (BN / 16)) << 4);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
         }
     }
@@ -137,35 +145,33 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < KT) {
-            load_tile<AT>(smem + s * 2 * TILE_ELEMS, Ag + s * a_step, lda, tid);
-            load_tile<BT>(smem + s * 2 * TILE_ELEMS + TILE_ELEMS, Bg + s * b_step, ldb, tid);
+            load_tile<AT, BM, BK, THREADS>(smem + s * G::STAGE_ELEMS, Ag + s * a_step, lda, tid);
+            load_tile<BT, BN, BK, THREADS>(smem + s * G::STAGE_ELEMS + G::A_ELEMS, Bg + s * b_step, ldb, tid);
         }
         cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; ++kt) {
-#ifndef GP_EXP_NOSYNC
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-#endif
         {   // refill the slot consumed in the previous iteration
             int nk = kt + STAGES - 1;
             if (nk < KT) {
                 int s = nk % STAGES;
-                load_tile<AT>(smem + s * 2 * TILE_ELEMS, Ag + nk * a_step, lda, tid);
-                load_tile<BT>(smem + s * 2 * TILE_ELEMS + TILE_ELEMS, Bg + nk * b_step, ldb, tid);
+                load_tile<AT, BM, BK, THREADS>(smem + s * G::STAGE_ELEMS, Ag + nk * a_step, lda, tid);
+                load_tile<BT, BN, BK, THREADS>(smem + s * G::STAGE_ELEMS + G::A_ELEMS, Bg + nk * b_step, ldb, tid);
             }
             cp_async_commit();
         }
-        const double* As = smem + (kt % STAGES) * 2 * TILE_ELEMS;
-        const double* Bs = As + TILE_ELEMS;
+        const double* As = smem + (kt % STAGES) * G::STAGE_ELEMS;
+        const double* Bs = As + G::A_ELEMS;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             double a[MI], b[NI];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = As[soff<AT>(wm + i * 8 + g, kk * 4 + t)];
+            for (int i = 0; i < MI; ++i) a[i] = As[soff<AT, BM, BK>(wm + i * 8 + g, kk * 4 + t)];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) b[j] = Bs[soff<BT>(wn + j * 8 + g, kk * 4 + t)];
+            for (int j = 0; j < NI; ++j) b[j] = Bs[soff<BT, BN, BK>(wn + j * 8 + g, kk * 4 + t)];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -175,7 +181,7 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     cp_async_wait<0>();
 
     // epilogue: each thread owns (row, 2 consecutive cols) of every 8x8 fragment -> 16-byte accesses
-    const bool diag = (tmask == TM_LOWER) && (tm == tn);
+    const bool diag = (tmask == TM_LOWER) && (n0 + BN - 1 > m0);   // tile crosses the diagonal: mask col > row
     if (beta != 0.0 && !diag) {
         // full tile with accumulate: issue all loads of a row group before using them (memory-level parallelism)
 #pragma unroll
@@ -200,23 +206,23 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-        int row = wm + i * 8 + g;
-        double* crow = C + (int64_t)(m0 + row) * ldc + n0;
+        const int grow = m0 + wm + i * 8 + g;
+        double* crow = C + (int64_t)grow * ldc;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
-            int col = wn + j * 8 + 2 * t;
-            if (diag && col > row) continue;
+            const int gcol = n0 + wn + j * 8 + 2 * t;
+            if (diag && gcol > grow) continue;
             double2 v;
             v.x = alpha * acc[i][j][0];
             v.y = alpha * acc[i][j][1];
-            double2* p = reinterpret_cast<double2*>(crow + col);
+            double2* p = reinterpret_cast<double2*>(crow + gcol);
             if (beta != 0.0) {
                 double2 o = *p;
                 v.x += beta * o.x;
                 v.y += beta * o.y;
             }
-            if (diag && col + 1 > row) {
-                crow[col] = v.x;  // keep the strictly-upper neighbour untouched
+            if (diag && gcol + 1 > grow) {
+                crow[gcol] = v.x;  // keep the strictly-upper neighbour untouched
             } else {
                 *p = v;
             }
@@ -224,15 +230,19 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     }
 }
 
-template <int AT, int BT>
+static int g_force_bn = -1;  // GP_GEMM_BN=64|128 overrides the tile-shape choice (tuning / A-B measurements)
+
+template <int AT, int BT, int BN_>
 static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                        int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
+    using G = Cfg<BN_>;
     static bool configured = false;
     if (!configured) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        GP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<AT, BT, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
         configured = true;
     }
-    int tiles_m = M / BM, tiles_n = N / BN;
+    if (K % G::BK) return -1;
+    int tiles_m = M / BM, tiles_n = N / BN_;
     if (tiles_m == 0 || tiles_n == 0) return 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_prof.on) {
@@ -243,11 +253,11 @@ static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, con
         }
         e0 = g_prof.pool[g_prof.used++];
         e1 = g_prof.pool[g_prof.used++];
-        g_prof.flops += tile_flops(tiles_m, tiles_n, K, krange, tmask);
+        g_prof.flops += tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask);
         g_prof.launches++;
         cudaEventRecord(e0, stream);
     }
-    dgemm_dmma_kernel<AT, BT><<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM, stream>>>(
+    dgemm_dmma_kernel<AT, BT, BN_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
         C, ldc, A, lda, B, ldb, tiles_m, tiles_n, K, alpha, beta, krange, tmask);
     if (e1) cudaEventRecord(e1, stream);
     GP_COUNT(1);
@@ -255,16 +265,30 @@ static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, con
     return 0;
 }
 
+template <int BN_>
+static int launch_bn(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                     int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
+    if (at == 0 && bt == 0) return launch_inst<0, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 0 && bt == 1) return launch_inst<0, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 1 && bt == 1) return launch_inst<1, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 1 && bt == 0) return launch_inst<1, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    return -4;
+}
+
 int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                  int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
-    if (M < 0 || N < 0 || K < 0 || (M % BM) || (N % BN) || (K % BK)) return -1;
+    if (M < 0 || N < 0 || K < 0 || (M % BM) || (N % 128) || (K % 32)) return -1;
     if ((lda & 1) || (ldb & 1) || (ldc & 1)) return -2;
     if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return -3;
-    if (at == 0 && bt == 0) return launch_inst<0, 0>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 0 && bt == 1) return launch_inst<0, 1>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 1 && bt == 1) return launch_inst<1, 1>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 1 && bt == 0) return launch_inst<1, 0>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    return -4;
+    if (g_force_bn < 0) {
+        const char* e = getenv("GP_GEMM_BN");
+        g_force_bn = e ? atoi(e) : 0;
+    }
+    // a CTA that overwrites an operand must own the whole row block it reads: the in-place panel solve needs BN = 128
+    bool aliased = (C == A) || (C == B);
+    int bn = aliased ? 128 : (g_force_bn == 128 ? 128 : 64);
+    if (bn == 128) return launch_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    return launch_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
 }
 
 int profile_enable(int on) {
