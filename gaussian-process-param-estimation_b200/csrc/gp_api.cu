@@ -21,9 +21,9 @@ unsigned long long gp_launch_count(void) { return gp::g_launch_count; }
 
 int gp_gemm_profile_enable(int on) { return gp::profile_enable(on); }
 
-int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launches_host) {
-    if (!ms_host || !flops_host || !launches_host) return -1;
-    return gp::profile_read(ms_host, flops_host, launches_host);
+int gp_gemm_profile_read(double* ms_sum_host, double* ms_union_host, double* flops_host, long long* launches_host) {
+    if (!ms_sum_host || !ms_union_host || !flops_host || !launches_host) return -1;
+    return gp::profile_read(ms_sum_host, ms_union_host, flops_host, launches_host);
 }
 
 }  // extern "C"

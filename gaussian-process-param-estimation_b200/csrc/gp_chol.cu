@@ -11,13 +11,14 @@
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_internal.h"
+#include <stdlib.h>
 
 namespace gp {
 
 constexpr int DB = 128;         // diagonal block
 constexpr int DPITCH = DB + 1;  // shared pitch (odd -> conflict-free column walks)
 constexpr int DIAG_THREADS = 512;
-constexpr int OUTER_NB = 512;
+static int OUTER_NB = 512;   // outer panel width (multiple of 128); GP_POTRF_NB overrides it for tuning
 
 // Factor the 128x128 diagonal block at `Ajj` (lower, in place) and write inv(L_jj) (lower, zero above) to `Linv`.
 //
@@ -442,6 +443,13 @@ int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, vo
     }
     int rc = side_streams_init();
     if (rc) return rc;
+    static bool nb_read = false;
+    if (!nb_read) {
+        const char* e = getenv("GP_POTRF_NB");
+        int v = e ? atoi(e) : 0;
+        if (v >= DB && v % DB == 0) OUTER_NB = v;
+        nb_read = true;
+    }
     cudaStream_t ps = g_side.s[0];  // high-priority panel stream (look-ahead)
     GP_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
     const int N = (int)npad;

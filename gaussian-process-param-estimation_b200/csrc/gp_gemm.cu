@@ -12,6 +12,8 @@
 #include "gp_common.cuh"
 #include "gp_internal.h"
 #include <stdlib.h>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 namespace gp {
@@ -23,8 +25,9 @@ struct GemmProfile {
     bool on = false;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
-    double flops = 0.0;       // executed tile flops (2 * 128 * 128 * k per computed tile)
+    double flops = 0.0;       // executed tile flops (2 * 128 * BN * k per computed tile)
     long long launches = 0;
+    cudaEvent_t ref = nullptr;  // time origin for the union of the (possibly concurrent) launch intervals
 };
 static GemmProfile g_prof;
 
@@ -296,19 +299,43 @@ int profile_enable(int on) {
     g_prof.used = 0;
     g_prof.flops = 0.0;
     g_prof.launches = 0;
+    if (g_prof.on) {
+        if (!g_prof.ref) GP_CUDA_CHECK(cudaEventCreate(&g_prof.ref));
+        GP_CUDA_CHECK(cudaDeviceSynchronize());
+        GP_CUDA_CHECK(cudaEventRecord(g_prof.ref, 0));
+        GP_CUDA_CHECK(cudaDeviceSynchronize());
+    }
     return 0;
 }
 
-// synchronises the device; returns summed GEMM kernel milliseconds, executed flops and launch count since enable
-int profile_read(double* ms, double* flops, long long* launches) {
+// synchronises the device; returns the summed GEMM kernel milliseconds, the length of the UNION of the launch
+// intervals (launches on different streams overlap), the executed tile flops and the launch count since enable
+int profile_read(double* ms_sum, double* ms_union, double* flops, long long* launches) {
     GP_CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<std::pair<float, float>> iv;
     double total = 0.0;
     for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
-        float t = 0.f;
-        GP_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.pool[i], g_prof.pool[i + 1]));
-        total += t;
+        float t0 = 0.f, t1 = 0.f;
+        GP_CUDA_CHECK(cudaEventElapsedTime(&t0, g_prof.ref, g_prof.pool[i]));
+        GP_CUDA_CHECK(cudaEventElapsedTime(&t1, g_prof.ref, g_prof.pool[i + 1]));
+        total += (double)t1 - (double)t0;
+        iv.push_back(std::make_pair(t0, t1));
     }
-    *ms = total;
+    std::sort(iv.begin(), iv.end());
+    double uni = 0.0;
+    float cur0 = 0.f, cur1 = -1.f;
+    for (size_t i = 0; i < iv.size(); ++i) {
+        if (cur1 < cur0 || iv[i].first > cur1) {
+            if (cur1 >= cur0) uni += (double)cur1 - (double)cur0;
+            cur0 = iv[i].first;
+            cur1 = iv[i].second;
+        } else if (iv[i].second > cur1) {
+            cur1 = iv[i].second;
+        }
+    }
+    if (cur1 >= cur0) uni += (double)cur1 - (double)cur0;
+    *ms_sum = total;
+    *ms_union = uni;
     *flops = g_prof.flops;
     *launches = g_prof.launches;
     return 0;

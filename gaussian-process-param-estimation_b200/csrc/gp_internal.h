@@ -26,6 +26,6 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
                  int krange, int tmask, cudaStream_t stream);
 
 int profile_enable(int on);
-int profile_read(double* ms, double* flops, long long* launches);
+int profile_read(double* ms_sum, double* ms_union, double* flops, long long* launches);
 
 }  // namespace gp

@@ -42,7 +42,7 @@ SIGNATURES = {
     'gp_padded_size': (_i64, [_i64]),
     'gp_launch_count': (ctypes.c_ulonglong, []),
     'gp_gemm_profile_enable': (_int, [_int]),
-    'gp_gemm_profile_read': (_int, [_vp, _vp, _vp]),
+    'gp_gemm_profile_read': (_int, [_vp, _vp, _vp, _vp]),
     'gp_matern_dense': (_int, [_vp, _i64, _i64, _vp, _f64, _vp, _i64, _vp, _vp]),
     'gp_matern_cross': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _f64, _vp, _i64, _vp]),
     'gp_kernel_threshold': (_int, [_i64, _i64, _f64, _vp, _f64, _vp]),

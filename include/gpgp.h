@@ -34,10 +34,11 @@ int64_t gp_padded_size(int64_t n);
 /* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long gp_launch_count(void);
 /* Measurement hooks for bench.py's roofline leg: while enabled, every DMMA GEMM launch is bracketed by CUDA events on
- * its own stream; gp_gemm_profile_read synchronises the device and returns the summed kernel milliseconds, the tile
- * flops those launches executed and their count (host pointers). */
+ * its own stream; gp_gemm_profile_read synchronises the device and returns the summed kernel milliseconds, the length
+ * of the union of the launch intervals (launches on the helper streams overlap), the tile flops those launches
+ * executed and their count (host pointers). */
 int gp_gemm_profile_enable(int on);
-int gp_gemm_profile_read(double* ms_host, double* flops_host, long long* launches_host);
+int gp_gemm_profile_read(double* ms_sum_host, double* ms_union_host, double* flops_host, long long* launches_host);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Correlation generation  (reference: generate_correlation/_kernels.pyx:17-136,
