@@ -17,7 +17,7 @@ namespace gp {
 
 constexpr int DB = 128;         // diagonal block
 constexpr int DPITCH = DB + 1;  // shared pitch (odd -> conflict-free column walks)
-constexpr int DIAG_THREADS = 512;
+constexpr int DIAG_THREADS = 256;  // 255 registers per thread: the unrolled warp-level factorisation must not spill
 static int OUTER_NB = 512;   // outer panel width (multiple of 128); GP_POTRF_NB overrides it for tuning
 
 // Factor the 128x128 diagonal block at `Ajj` (lower, in place) and write inv(L_jj) (lower, zero above) to `Linv`.
@@ -32,50 +32,85 @@ static int OUTER_NB = 512;   // outer panel width (multiple of 128); GP_POTRF_NB
 constexpr int SB = 32;
 constexpr int TPITCH = SB + 1;
 
+#ifdef GP_DIAG_TIMING
+__device__ long long g_diag_clk[32];
+#define DIAG_T(i) do { if (tid == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_T(i)
+#endif
+
+
+// Warp-level Cholesky of a 32x32 block (lane = row, a[] = this lane's row, a[0] = current column).
+// The column loop stays ROLLED and the register array is rotated by one each step so that every register index is
+// static: a single warp running ~3000 straight-line instructions is instruction-fetch bound (measured 1100 cycles per
+// column fully unrolled vs ~250 rolled). Column j is broadcast through `cb` with all loads issued before the FMAs.
+__device__ __forceinline__ int chol32_warp(double (&a)[SB], int lane, double* cb, double* dinv_out, double* Srow) {
+    int badcol = -1;
+#pragma unroll 1
+    for (int j = 0; j < SB; ++j) {
+        double ajj = __shfl_sync(0xffffffffu, a[0], j);
+        if (!(ajj > 0.0) && badcol < 0) badcol = j;   // also catches NaN
+        double inv = rsqrt(ajj);
+        double lj = (lane == j) ? ajj * inv : a[0] * inv;   // l_ij for lanes i >= j
+        if (lane >= j) Srow[j] = lj;
+        if (lane == j) dinv_out[j] = inv;
+        double* c = cb + (j & 1) * 2 * SB;
+        c[lane] = lj;
+        __syncwarp();
+        double t[SB - 1];
+#pragma unroll
+        for (int k = 0; k < SB - 1; ++k) t[k] = c[j + 1 + k];          // entries past 31 are never used by a valid lane
+#pragma unroll
+        for (int k = 0; k < SB - 1; ++k) a[k] = a[k + 1] - lj * t[k];  // update + rotate: new a[0] is column j + 1
+    }
+    return badcol;
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0, int nvalid) {
     extern __shared__ double S[];                  // [128][129]
     double* dinv = S + DB * DPITCH;                // [128]   1 / L_ii
     double* T = dinv + DB;                         // [3][32][33] scratch for the inverse assembly
+    double* colbuf = T;                            // [2][32] column broadcast buffer of the warp-level factorisation
     __shared__ int bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) bad = 0;
-    for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
-        int i = idx >> 7, k = idx & 127;
-        S[i * DPITCH + k] = (k <= i) ? Ajj[(int64_t)i * lda + k] : 0.0;
+    DIAG_T(0);
+    // 8 independent loads per thread in flight (the block usually sits in L2: latency, not bandwidth, matters)
+    for (int base = 0; base < DB * DB; base += 8 * DIAG_THREADS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int idx = base + u * DIAG_THREADS + tid, i = idx >> 7, k = idx & 127;
+            v[u] = (k <= i) ? Ajj[(int64_t)i * lda + k] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int idx = base + u * DIAG_THREADS + tid, i = idx >> 7, k = idx & 127;
+            S[i * DPITCH + k] = v[u];
+        }
     }
     if (tid < DB) S[tid * DPITCH + DB] = 0.0;
     __syncthreads();
 
+    DIAG_T(1);
     for (int J = 0; J < DB / SB; ++J) {
         const int J0 = J * SB;
+        DIAG_T(2 + 4 * J);
         // ---- (1) 32x32 diagonal sub-block: lane = row, registers hold the row, columns broadcast by shuffle
         if (warp == 0) {
             double a[SB];
             const int row = J0 + lane;
 #pragma unroll
             for (int k = 0; k < SB; ++k) a[k] = S[row * DPITCH + J0 + k];
-#pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                double ajj = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(ajj > 0.0)) {  // also catches NaN
-                    if (lane == 0 && !bad) { bad = 1; if (j0 + J0 + j < nvalid) atomicCAS(info, 0, j0 + J0 + j + 1); }
-                }
-                double inv = rsqrt(ajj);
-                double lj = (lane == j) ? ajj * inv : a[j] * inv;   // l_ij for lanes i >= j
-                a[j] = lj;
-                if (lane == j) dinv[J0 + j] = inv;
-#pragma unroll
-                for (int k = j + 1; k < SB; ++k) {
-                    double lk = __shfl_sync(0xffffffffu, lj, k);
-                    a[k] -= lj * lk;                                  // meaningful for lanes i >= k
-                }
+            int badcol = chol32_warp(a, lane, colbuf, dinv + J0, S + row * DPITCH + J0);
+            if (lane == 0 && badcol >= 0 && !bad) {
+                bad = 1;
+                if (j0 + J0 + badcol < nvalid) atomicCAS(info, 0, j0 + J0 + badcol + 1);
             }
-#pragma unroll
-            for (int k = 0; k < SB; ++k)
-                if (k <= lane) S[row * DPITCH + J0 + k] = a[k];
         }
         __syncthreads();
+        DIAG_T(3 + 4 * J);
         const int r = DB - J0 - SB;   // rows below the sub-block
         if (r == 0) break;
         // ---- (2) panel solve, one thread per row: x = p * inv(L_D)^T in axpy form
@@ -95,32 +130,35 @@ chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0
             for (int c = 0; c < SB; ++c) S[i * DPITCH + J0 + c] = pr[c];
         }
         __syncthreads();
-        // ---- (3) trailing rank-32 update on lower 4x4 micro-tiles
+        DIAG_T(4 + 4 * J);
+        // ---- (3) trailing rank-32 update on lower 8x4 register micro-tiles (tile row mi holds 2 mi + 2 tiles)
         {
-            const int mt = r / 4, cnt = mt * (mt + 1) / 2;
+            const int mr = r / 8, cnt = mr * (mr + 1);
             if (tid < cnt) {
-                int mi = (int)((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f);
-                while ((mi + 1) * (mi + 2) / 2 <= tid) ++mi;
-                while (mi * (mi + 1) / 2 > tid) --mi;
-                int mk = tid - mi * (mi + 1) / 2;
-                const int i0 = J0 + SB + 4 * mi, k0 = J0 + SB + 4 * mk;
-                double acc[4][4];
+                int mi = (int)((sqrtf(4.0f * tid + 1.0f) - 1.0f) * 0.5f);
+                while ((mi + 1) * (mi + 2) <= tid) ++mi;
+                while (mi * (mi + 1) > tid) --mi;
+                const int mk = tid - mi * (mi + 1);
+                const int i0 = J0 + SB + 8 * mi, k0 = J0 + SB + 4 * mk;
+                double acc[8][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 8; ++e)
 #pragma unroll
                     for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
-#pragma unroll 8
+#pragma unroll 4
                 for (int c = 0; c < SB; ++c) {
-                    double av[4], bv[4];
+                    double av[8], bv[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { av[e] = S[(i0 + e) * DPITCH + J0 + c]; bv[e] = S[(k0 + e) * DPITCH + J0 + c]; }
+                    for (int e = 0; e < 8; ++e) av[e] = S[(i0 + e) * DPITCH + J0 + c];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
+                    for (int f = 0; f < 4; ++f) bv[f] = S[(k0 + f) * DPITCH + J0 + c];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
 #pragma unroll
                         for (int f = 0; f < 4; ++f) acc[e][f] += av[e] * bv[f];
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 8; ++e)
 #pragma unroll
                     for (int f = 0; f < 4; ++f)
                         if (k0 + f <= i0 + e) S[(i0 + e) * DPITCH + k0 + f] -= acc[e][f];
@@ -129,6 +167,7 @@ chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0
         __syncthreads();
     }
 
+    DIAG_T(18);
     // ---- (4) inverses of the four diagonal sub-blocks: warp J, lane = column c of inv(L_JJ)
     if (warp < DB / SB) {
         const int J0 = warp * SB;
@@ -147,31 +186,51 @@ chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0
             if (i >= lane) S[(J0 + lane) * DPITCH + J0 + i + 1] = acc[i];   // W[J0+i][J0+lane]
     }
     __syncthreads();
+    DIAG_T(19);
     // ---- (5) off-diagonal blocks of W by block distance
     for (int d = 1; d < DB / SB; ++d) {
         const int nblk = DB / SB - d;
-        // T_b[i][c] = sum_{g >= 32J + c}^{32I - 1} L[32I + i][g] * W[g][32J + c]
-        for (int o = tid; o < nblk * SB * SB; o += DIAG_THREADS) {
-            int b = o >> 10, i = (o >> 5) & 31, c = o & 31;
-            int Jb = b, Ib = b + d;
-            const double* lrow = S + (Ib * SB + i) * DPITCH;
-            const double* wcol = S + (Jb * SB + c) * DPITCH + 1;
-            double sum = 0.0;
-            for (int g = Jb * SB + c; g < Ib * SB; ++g) sum += lrow[g] * wcol[g];
-            T[(b * SB + i) * TPITCH + c] = sum;
+        const int i0 = 2 * (tid >> 4), c0 = 2 * (tid & 15);   // 256 threads x (2 x 2) = one 32 x 32 block
+        // T_b = sum_K L_IK W_KJ over g in [32 J, 32 I): W[g][col] lives at S[col][g + 1] and is zero for g < col
+        // (those slots of the shared array hold L, hence the explicit mask)
+        for (int b = 0; b < nblk; ++b) {
+            const int Jb = b, Ib = b + d;
+            const double* l0p = S + (Ib * SB + i0) * DPITCH;
+            const double* l1p = l0p + DPITCH;
+            const int col0 = Jb * SB + c0;
+            const double* w0p = S + col0 * DPITCH + 1;
+            const double* w1p = w0p + DPITCH;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+            for (int g = Jb * SB; g < Ib * SB; ++g) {
+                double l0 = l0p[g], l1 = l1p[g];
+                double w0 = (g >= col0) ? w0p[g] : 0.0;
+                double w1 = (g >= col0 + 1) ? w1p[g] : 0.0;
+                a00 += l0 * w0; a01 += l0 * w1; a10 += l1 * w0; a11 += l1 * w1;
+            }
+            double* tp = T + (b * SB + i0) * TPITCH + c0;
+            tp[0] = a00; tp[1] = a01; tp[TPITCH] = a10; tp[TPITCH + 1] = a11;
         }
         __syncthreads();
-        // W_IJ[i][c] = - sum_{k <= i} inv(L_II)[i][k] * T[k][c]
-        for (int o = tid; o < nblk * SB * SB; o += DIAG_THREADS) {
-            int b = o >> 10, i = (o >> 5) & 31, c = o & 31;
-            int Jb = b, Ib = b + d;
-            double sum = 0.0;
-            for (int k = 0; k <= i; ++k) sum += S[(Ib * SB + k) * DPITCH + Ib * SB + i + 1] * T[(b * SB + k) * TPITCH + c];
-            S[(Jb * SB + c) * DPITCH + Ib * SB + i + 1] = -sum;
+        // W_IJ[i][c] = - sum_{k <= i} inv(L_II)[i][k] T[k][c];  inv(L_II)[i][k] lives at S[32 I + k][32 I + i + 1]
+        for (int b = 0; b < nblk; ++b) {
+            const int Jb = b, Ib = b + d;
+            const double* dp = S + (Ib * SB) * DPITCH + Ib * SB + i0 + 1;
+            const double* tp = T + (b * SB) * TPITCH + c0;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+            for (int k = 0; k <= i0 + 1; ++k) {
+                double d0 = (k <= i0) ? dp[k * DPITCH] : 0.0, d1 = dp[k * DPITCH + 1];
+                double t0 = tp[k * TPITCH], t1 = tp[k * TPITCH + 1];
+                a00 += d0 * t0; a01 += d0 * t1; a10 += d1 * t0; a11 += d1 * t1;
+            }
+            double* wp = S + (Jb * SB + c0) * DPITCH + Ib * SB + i0 + 1;
+            wp[0] = -a00; wp[1] = -a10; wp[DPITCH] = -a01; wp[DPITCH + 1] = -a11;
         }
         __syncthreads();
     }
 
+    DIAG_T(20);
     for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
         int i = idx >> 7, k = idx & 127;
         if (k <= i) {
@@ -181,6 +240,7 @@ chol_diag_block_kernel(double* Ajj, int64_t lda, double* Linv, int* info, int j0
             Linv[i * DB + k] = 0.0;
         }
     }
+    DIAG_T(21);
 }
 
 __global__ void logdet_kernel(const double* L, int n, int64_t ld, double* out) {
@@ -393,6 +453,12 @@ static void launch_bwd(const double* L, int64_t npad, int j0, const double* Zj, 
 using namespace gp;
 
 extern "C" {
+
+#ifdef GP_DIAG_TIMING
+int gp_diag_timing_read(long long* out32) {
+    return (int)cudaMemcpyFromSymbol(out32, gp::g_diag_clk, sizeof(long long) * 32);
+}
+#endif
 
 int gp_shift_copy(const double* K, int64_t n, int64_t npad, double eta, double* A, void* stream) {
     if (!K || !A || n <= 0 || npad != gp_padded_size(n)) return -1;

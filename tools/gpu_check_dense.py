@@ -154,7 +154,33 @@ def run(n, nu=2.5, rho=0.1, eta=0.1, verify=True):
     print(json.dumps(out))
 
 
+def time_diag_kernel():
+    """potrf of a single 128x128 block = one chol_diag_block_kernel launch (+ a 4-byte memset)"""
+    numpy.random.seed(1)
+    pts = numpy.random.rand(128, 2)
+    K = torch.from_numpy(matern_np(pts, 0.1, 2.5) + 0.1 * numpy.eye(128)).cuda()
+    A = K.clone()
+    info = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ws = torch.empty(lib.gp_potrf_workspace_bytes(128) // 8, dtype=torch.float64, device='cuda')
+    s = dev.stream_ptr()
+
+    def f():
+        lib.gp_potrf_f64(P(A), 128, 128, P(info), P(ws), s)
+    for _ in range(3):
+        A.copy_(K); f()
+    ts = []
+    for _ in range(20):
+        A.copy_(K)
+        ts.append(timed(f))
+    L = torch.tril(A)
+    print(json.dumps({'diag_block_kernel_us_median': float(numpy.median(ts)) * 1e3,
+                      'resid': float((L @ L.T - K).abs().max())}))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'diag':
+        time_diag_kernel()
+        sys.exit(0)
     sizes = [int(a) for a in sys.argv[1:]] or [1000]
     for n in sizes:
         run(n, verify=(n <= 6000))
