@@ -12,6 +12,7 @@
 #include "gp_common.cuh"
 #include "gp_internal.h"
 #include <stdlib.h>
+#include <map>
 
 namespace gp {
 
@@ -382,16 +383,23 @@ __global__ void place_diag_inverse_kernel(const double* __restrict__ Linv, doubl
 // look-ahead panel of the factorisation run beside the caller's stream, ordered with events ---------------------
 struct SidePool {
     cudaStream_t s[3];
-    bool ready = false;
 };
-static SidePool g_side;
+// one pool per caller stream: two evaluations driven on two streams (a sweep keeps two cells in flight to fill the
+// latency-bound phases of each other) must not serialise on shared helper streams
+static std::map<cudaStream_t, SidePool> g_pools;
+static thread_local SidePool* g_side_ptr = nullptr;
+#define g_side (*g_side_ptr)
 
-static int side_streams_init() {
-    if (g_side.ready) return 0;
-    int lo = 0, hi = 0;
-    GP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (int i = 0; i < 3; ++i) GP_CUDA_CHECK(cudaStreamCreateWithPriority(&g_side.s[i], cudaStreamNonBlocking, hi));
-    g_side.ready = true;
+static int side_streams_init(cudaStream_t caller) {
+    auto it = g_pools.find(caller);
+    if (it == g_pools.end()) {
+        int lo = 0, hi = 0;
+        GP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SidePool p;
+        for (int i = 0; i < 3; ++i) GP_CUDA_CHECK(cudaStreamCreateWithPriority(&p.s[i], cudaStreamNonBlocking, hi));
+        it = g_pools.insert(std::make_pair(caller, p)).first;
+    }
+    g_side_ptr = &it->second;
     return 0;
 }
 
@@ -507,7 +515,7 @@ int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, vo
         GP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         configured = true;
     }
-    int rc = side_streams_init();
+    int rc = side_streams_init(s);
     if (rc) return rc;
     static bool nb_read = false;
     if (!nb_read) {
@@ -600,7 +608,7 @@ int gp_trtri_f64(const double* L, double* W, int64_t npad, const void* potrf_ws,
     place_diag_inverse_kernel<<<nb, 256, 0, s>>>((const double*)potrf_ws, W, npad);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
-    int rc = side_streams_init();
+    int rc = side_streams_init(s);
     if (rc) return rc;
     return trtri_rec(L, W, npad, 0, nb, (double*)ws, s, 0, 0);
 }

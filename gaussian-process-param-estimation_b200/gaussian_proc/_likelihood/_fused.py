@@ -14,7 +14,7 @@ import numpy
 from .. import _device as dev
 from .._dense import FLAG_TRACEINV, FLAG_INVERSE, FLAG_DRHO
 
-__all__ = ['FusedQuantities', 'evaluate']
+__all__ = ['FusedQuantities', 'evaluate', 'evaluate_async', 'finish']
 
 
 class FusedQuantities(object):
@@ -56,8 +56,9 @@ def _rhs_device(K_mixed, X, z):
     return Rd
 
 
-def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
-    """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite."""
+def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
+    """Enqueues one fused evaluation on torch's current stream and returns a handle without synchronising; several
+    evaluations on different streams / operators can be in flight (see sweep.py). Complete it with finish()."""
     if K_mixed.sparse:
         raise TypeError('the fused dense evaluator needs a dense MixedCorrelation')
     n, m = X.shape
@@ -69,9 +70,22 @@ def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
     if drho:
         flags |= FLAG_DRHO
     Rd = _rhs_device(K_mixed, X, z)
-    out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags).cpu().numpy()
-    q = FusedQuantities(out, n, m, float(eta), flags)
+    out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags)
+    return (out, n, m, float(eta), flags, dev.torch.cuda.current_stream())
+
+
+def finish(handle):
+    """Waits for the evaluation's stream, reads out[] back (one small D2H) and does the host algebra; raises
+    numpy.linalg.LinAlgError if K + eta I was not positive definite."""
+    out, n, m, eta, flags, stream = handle
+    stream.synchronize()
+    q = FusedQuantities(out.cpu().numpy(), n, m, eta, flags)
     if q.info != 0:
         raise numpy.linalg.LinAlgError(
             '%d-th leading minor of K + eta*I (eta=%g) is not positive definite.' % (q.info, eta))
     return q
+
+
+def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
+    """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite."""
+    return finish(evaluate_async(z, X, K_mixed, eta, traceinv=traceinv, inverse=inverse, drho=drho))

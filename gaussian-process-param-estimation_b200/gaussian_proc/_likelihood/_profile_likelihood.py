@@ -44,11 +44,22 @@ class ProfileLikelihood(object):
         return ProfileLikelihood.log_likelihood_and_gradient(z, X, K_mixed, eta)[2]
 
     @staticmethod
+    def log_likelihood_and_gradient_async(z, X, K_mixed, eta, with_rho=True):
+        """Enqueues the evaluation on torch's current stream; returns a zero-argument callable that completes it and
+        returns (l^, d l^/d eta, d l^/d rho). Lets a sweep keep several cells in flight on different streams."""
+        h = _fused.evaluate_async(z, X, K_mixed, eta, traceinv=True, drho=with_rho)
+        return lambda: ProfileLikelihood._gradient_from(_fused.finish(h), X.shape, with_rho)
+
+    @staticmethod
     def log_likelihood_and_gradient(z, X, K_mixed, eta, with_rho=True):
         """(l^(sigma_hat, eta), d l^/d eta, d l^/d rho) from ONE factorisation -- the unit bench.py counts as a
         'loglik+grad evaluation'."""
-        n, m = X.shape
         q = _fused.evaluate(z, X, K_mixed, eta, traceinv=True, drho=with_rho)
+        return ProfileLikelihood._gradient_from(q, X.shape, with_rho)
+
+    @staticmethod
+    def _gradient_from(q, shape, with_rho):
+        n, m = shape
         sigma2 = q.zMz / (n - m)
         lp = -0.5 * (n - m) * numpy.log(sigma2) - 0.5 * q.logdet_Kn - 0.5 * numpy.log(numpy.linalg.det(q.B)) \
             - 0.5 * (n - m)

@@ -14,39 +14,73 @@ from . import _distributed as gpd
 __all__ = ['likelihood_grid']
 
 
-def _gpu_cell_evaluator(points, z, X, nu):
-    from .generate_correlation.generate_correlation import generate_dense_correlation
-    from ._mixed_correlation import MixedCorrelation
-    from ._likelihood import ProfileLikelihood
-    points = numpy.ascontiguousarray(points, dtype=float)
-    state = {}
+class _GpuRowEvaluator(object):
+    """All eta cells of one rho: K(rho) is generated once; `concurrency` operators (each with its own scratch, sharing
+    the read-only K) evaluate cells on their own CUDA streams so that the latency-bound phases of one evaluation
+    (diagonal blocks, small recursion levels) are filled by the GEMMs of another."""
 
-    def evaluate(rho, eta):
-        if state.get('rho') != rho:
-            state.clear()      # release the previous matrix before allocating the next one
-            K = generate_dense_correlation(points, numpy.repeat(float(rho), points.shape[1]), float(nu))
-            state.update(rho=rho, K_mixed=MixedCorrelation(K))
-        return ProfileLikelihood.log_likelihood_and_gradient(z, X, state['K_mixed'], eta)
-    return evaluate
+    def __init__(self, points, z, X, nu, concurrency):
+        from . import _device as dev
+        self.torch = dev.require_cuda()
+        self.points = numpy.ascontiguousarray(points, dtype=float)
+        self.z, self.X, self.nu = z, X, float(nu)
+        self.concurrency = max(1, int(concurrency))
+        self.streams = [self.torch.cuda.Stream() for _ in range(self.concurrency)]
+        self.ops = None
+        self.n_ops = -1
+
+    def row(self, rho, etas):
+        from .generate_correlation.generate_correlation import generate_dense_correlation
+        from ._mixed_correlation import MixedCorrelation
+        from ._likelihood import ProfileLikelihood
+        torch = self.torch
+        K = generate_dense_correlation(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu)
+        if self.ops is None or self.n_ops != K.n:
+            self.ops = [MixedCorrelation(K) for _ in range(self.concurrency)]
+            self.n_ops = K.n
+        else:
+            for op in self.ops:      # reuse the scratch buffers, swap the matrix
+                op.K = K
+                op.engine.K = K
+                op.engine.invalidate()
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+        out = numpy.empty((len(etas), 3))
+        pending = []
+        for j, eta in enumerate(etas):
+            slot = j % self.concurrency
+            if len(pending) >= self.concurrency:
+                jj, fin = pending.pop(0)
+                out[jj] = fin()
+            with torch.cuda.stream(self.streams[slot]):
+                fin = ProfileLikelihood.log_likelihood_and_gradient_async(self.z, self.X, self.ops[slot], eta)
+            pending.append((j, fin))
+        for jj, fin in pending:
+            out[jj] = fin()
+        for s in self.streams:
+            cur.wait_stream(s)
+        return out
 
 
-def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None):
+def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=2):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
-    on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator."""
+    on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
+    `concurrency` cells in flight per GPU."""
     rhos = numpy.asarray(rhos, dtype=float)
     etas = numpy.asarray(etas, dtype=float)
     rank, world = gpd.rank_world()
     begin, end = gpd.partition_cells(len(rhos), world, rank)
-    if evaluate is None:
-        evaluate = _gpu_cell_evaluator(points, z, X, nu)
+    rows = None if evaluate is not None else _GpuRowEvaluator(points, z, X, nu, concurrency)
     local = numpy.empty(((end - begin) * len(etas), 5))
     k = 0
     for i in range(begin, end):
-        for j, eta in enumerate(etas):
+        vals = rows.row(rhos[i], etas) if rows is not None else [evaluate(rhos[i], eta) for eta in etas]
+        for j in range(len(etas)):
             local[k, :2] = (i, j)
-            local[k, 2:] = evaluate(rhos[i], eta)
+            local[k, 2:] = vals[j]
             k += 1
-    rows = gpd.allgather_rows(local)
+    gathered = gpd.allgather_rows(local)
     out = numpy.full((len(rhos), len(etas), 3), numpy.nan)
-    out[rows[:, 0].astype(int), rows[:, 1].astype(int)] = rows[:, 2:]
+    out[gathered[:, 0].astype(int), gathered[:, 1].astype(int)] = gathered[:, 2:]
     return out
