@@ -345,7 +345,10 @@ def run_ours(args):
     achieved = alg_flops / (gemm_ms_per_step * 1e-3) * 1e-12
     roofline = {'bound': 'tensor', 'kernel': 'gp::dgemm_dmma_kernel (DMMA.8x8x4, FP64 tensor pipe)',
                 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
-                'traffic': None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (potrf trailing update, 19456^2 lower
+                # tiles, K = 512) from the ncu --set full capture summarised in profiles/r01_gemm_ncu_summary.md;
+                # algorithmic bytes of that launch: 3.12e9 (lower triangle of C read + written, plus the panel)
+                'traffic': 3.63e9,
                 'peak_source': 'in-run cuBLAS DGEMM 8192^3 (torch.matmul f64, best of 3); MEASURED_PEAKS.json has no FP64 '
                                'entry; raw DMMA issue peak measured by tools/microbench.cu = 37.1 TFLOP/s',
                 'algorithmic_flops_per_step': alg_flops,

@@ -1,7 +1,8 @@
 """
 Likelihood -- thin dispatcher, same as the reference's gaussian_proc/_likelihood/likelihood.py:23-102.
 The reference hard-codes imate_method='eigenvalue' (:40-43), which bars sparse K; here the method is a
-pass-through keyword. Default: 'cholesky' for dense K (same values as 'eigenvalue' to rounding), 'slq' for sparse.
+pass-through keyword. Default: 'cholesky' for dense K (same values as the reference's 'eigenvalue' to rounding, one
+factorisation per evaluation and no O(n^3) eigen-decomposition up front), 'slq' for sparse; 'eigenvalue' is accepted.
 """
 
 import scipy.sparse

@@ -13,7 +13,7 @@ from .._dense import DeviceCorrelation, DenseEngine
 
 __all__ = ['MixedCorrelation']
 
-_DENSE_METHODS = ('cholesky',)
+_DENSE_METHODS = ('cholesky', 'eigenvalue')
 _SPARSE_METHODS = ('slq', 'hutchinson')
 
 
@@ -21,8 +21,11 @@ class MixedCorrelation(object):
     """
     Same constructor and methods as the reference class (mixed_correlation.py:34-35). Differences, all documented
     in DESIGN.md: ``imate_method`` 'cholesky' (dense) and 'slq' / 'hutchinson' (sparse) are implemented natively;
-    'eigenvalue' raises NotImplementedError (next-round item) -- its values equal the Cholesky ones to
-    rounding; ``interpolate=True`` raises NotImplementedError (imate.InterpolateTraceInv).
+    'eigenvalue' (the method the reference's Likelihood hard-codes, likelihood.py:41) computes all eigenvalues of K once
+    in __init__ like mixed_correlation.py:76-79 -- here with the cuSOLVER symmetric eigensolver behind
+    torch.linalg.eigvalsh, a LIBRARY call (own kernel: next) -- after which logdet / traceinv / trace are
+    O(n) reductions over lambda + eta; solves still use the native Cholesky engine.
+    ``interpolate=True`` raises NotImplementedError (imate.InterpolateTraceInv).
     """
 
     def __init__(self, K, interpolate=False, interpolant_points=None, imate_method='cholesky', imate_options={}):
@@ -44,14 +47,16 @@ class MixedCorrelation(object):
             self.engine = SparseEngine(K, imate_method, self.imate_options)
             self.K = self.engine.K
         else:
-            if imate_method == 'eigenvalue':
-                raise NotImplementedError('imate_method="eigenvalue" is not built yet; use "cholesky" (same values).')
             if imate_method not in _DENSE_METHODS:
                 raise ValueError('Existing methods are "eigenvalue", "cholesky", "hutchinson", and "slq".')
             if not isinstance(K, DeviceCorrelation):
                 K = DeviceCorrelation.from_numpy(K)
             self.K = K
             self.engine = DenseEngine(K)
+            self.K_eigenvalues = None
+            if imate_method == 'eigenvalue':
+                from .. import _device as dev
+                self.K_eigenvalues = dev.torch.linalg.eigvalsh(K.data[:K.n, :K.n])
 
     # -- extension: generator parameters for d/d(correlation_scale) when K came in as a plain array
     def set_kernel(self, points, correlation_scale, nu):
@@ -78,14 +83,23 @@ class MixedCorrelation(object):
             return trK + eta * n if eta != 0 else trK
         if exponent == 2:
             return trK2 if eta == 0 else trK2 + 2.0 * eta * trK + eta ** 2 * n
+        if not self.sparse and self.imate_method == 'eigenvalue':
+            return float(((self.K_eigenvalues + eta) ** exponent).sum().item())           # :127-136
         raise ValueError('Existing methods are "exact", "eigenvalue", and "slq".')
 
     def traceinv(self, eta, exponent=1):
         """mixed_correlation.py:155-215"""
+        if not self.sparse and self.imate_method == 'eigenvalue':
+            return float(((self.K_eigenvalues + eta) ** (-exponent)).sum().item())     # :172-181
         return self.engine.traceinv(eta, exponent)
 
     def logdet(self, eta, exponent=1):
         """mixed_correlation.py:221-274; logdet(Kn^p) = p logdet(Kn)."""
+        if not self.sparse and self.imate_method == 'eigenvalue':
+            lam = self.K_eigenvalues + eta                                                # :239-248
+            if not bool((lam > 0).all().item()):
+                raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite.' % eta)
+            return exponent * float(lam.log().sum().item())
         return exponent * self.engine.logdet(eta)
 
     def solve(self, eta, Y):

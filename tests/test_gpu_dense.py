@@ -324,3 +324,24 @@ def test_block_cyclic_single_rank_matches_dense_engine(gp):
     assert rel(bc.solve(numpy.c_[X, z]), Ko.solve(0.3, numpy.c_[X, z])) <= RTOL
     with pytest.raises(numpy.linalg.LinAlgError):
         bc.factor(-2.0)
+
+
+def test_eigenvalue_method_matches_reference_vectors(gp, golden_likelihood):
+    """imate_method='eigenvalue' (what the reference's Likelihood hard-codes, likelihood.py:41)."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import DirectLikelihood, Likelihood
+    g = golden_likelihood
+    nu, rho = g['cases'][1]
+    pts, z, X = g['points'], g['z'], g['X']
+    K = gp.generate_correlation(pts, rho, nu, device=True)
+    Km = MixedCorrelation(K, imate_method='eigenvalue')
+    for i, t in enumerate(g['log_etas']):
+        eta = 10.0 ** t
+        assert rel(Km.logdet(eta), g['c1_eigenvalue_logdet'][i]) <= RTOL
+        assert rel(Km.traceinv(eta), g['c1_eigenvalue_traceinv'][i]) <= (1e-8 if t < 0 else RTOL)
+        assert rel(Km.traceinv(eta, exponent=2), g['c1_eigenvalue_traceinv2'][i]) <= (1e-7 if t < 0 else RTOL)
+    assert rel(Km.trace(0.5, exponent=3), numpy.sum((numpy.linalg.eigvalsh(K.to_numpy()) + 0.5) ** 3)) <= 1e-10
+    h = list(g['hyper_direct'][0])
+    lk = Likelihood(X, K, likelihood_method='direct', imate_method='eigenvalue')
+    assert rel(lk.likelihood(z, h), g['c1_eigenvalue_direct_ll'][0]) <= RTOL
+    assert rel(DirectLikelihood.log_likelihood_hessian(z, X, Km, False, h), g['c1_eigenvalue_direct_hess'][0]) <= 1e-8
