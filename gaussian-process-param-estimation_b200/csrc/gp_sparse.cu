@@ -504,6 +504,15 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     return 0;
 }
 
+// the cell-sorted order of the points computed by gp_matern_sparse_count (device int32, n): a spatially local
+// ordering that the sparse operator uses internally to make its SpMM gathers cache friendly
+int gp_sparse_cell_order(void* ws, int64_t n, int64_t d, int* order_dev, void* stream) {
+    if (!ws || !order_dev || n <= 0) return -1;
+    SparseWs w = carve_sparse(ws, n, d);
+    GP_CUDA_CHECK(cudaMemcpyAsync(order_dev, w.sorted_idx, sizeof(int) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
                           double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
                           double* ddata_dev, void* stream) {

@@ -113,10 +113,11 @@ __global__ void cg_direction_kernel(int64_t total, int B, const double* __restri
 }
 
 // Rademacher probes from a counter-based hash of (seed, probe id, row): independent of batching and rank count
-__global__ void rademacher_kernel(int64_t n, int B, uint64_t seed, int64_t probe0, double* V) {
+__global__ void rademacher_kernel(int64_t n, int B, uint64_t seed, int64_t probe0, const int* __restrict__ row_map, double* V) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * B) return;
-    uint64_t row = (uint64_t)(idx / B), pid = (uint64_t)(probe0 + idx % B);
+    int64_t r = idx / B;
+    uint64_t row = (uint64_t)(row_map ? row_map[r] : r), pid = (uint64_t)(probe0 + idx % B);
     uint64_t z = seed * 0x9E3779B97F4A7C15ull + pid * 0xBF58476D1CE4E5B9ull + row * 0x94D049BB133111EBull + 0x2545F4914F6CDD1Dull;
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
     z ^= z >> 27; z *= 0x94D049BB133111EBull;
@@ -141,6 +142,23 @@ static int spmm(const int* indptr, const int* indices, const double* data, int n
     return 0;
 }
 
+// new row r = old row order[r]; columns mapped through inv_order; one warp per new row
+__global__ void __launch_bounds__(256)
+csr_permute_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
+                   const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
+                   const int* __restrict__ new_indptr, int* new_indices, double* new_data, double* new_ddata) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int o = order[r];
+    const int s0 = indptr[o], len = indptr[o + 1] - s0, d0 = new_indptr[r];
+    for (int t = lane; t < len; t += 32) {
+        new_indices[d0 + t] = inv_order[indices[s0 + t]];
+        new_data[d0 + t] = data[s0 + t];
+        if (ddata) new_ddata[d0 + t] = ddata[s0 + t];
+    }
+}
+
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace gp
@@ -155,9 +173,21 @@ int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64
     return spmm(indptr, indices, data, (int)n, eta, X, (int)B, Y, (cudaStream_t)stream);
 }
 
-int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, void* stream) {
+int gp_csr_permute(int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
+                   const double* data, const double* ddata, const int* new_indptr, int* new_indices, double* new_data,
+                   double* new_ddata, void* stream) {
+    if (!order || !inv_order || !indptr || !indices || !data || !new_indptr || !new_indices || !new_data || n <= 0 || n > INT32_MAX)
+        return -1;
+    csr_permute_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (int)n, order, inv_order, indptr, indices, data, ddata, new_indptr, new_indices, new_data, new_ddata);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map, void* stream) {
     if (!V || n <= 0 || B <= 0) return -1;
-    rademacher_kernel<<<(unsigned)((n * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, (int)B, seed, probe_offset, V);
+    rademacher_kernel<<<(unsigned)((n * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, (int)B, seed, probe_offset, row_map, V);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;

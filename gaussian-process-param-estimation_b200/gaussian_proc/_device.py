@@ -50,7 +50,9 @@ SIGNATURES = {
     'gp_matern_sparse_count': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
     'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gp_csr_spmm': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
-    'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp]),
+    'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp, _vp]),
+    'gp_csr_permute': (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_sparse_cell_order': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'gp_krylov_workspace_bytes': (_i64, [_i64, _i64]),
     'gp_col_dot': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'gp_lanczos': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=8, cg_tol=1e-6, cg_maxiter=2000)
+                lanczos_degree=20, seed=0, batch=8, cg_tol=1e-6, cg_maxiter=2000, locality=True)
 
 
 def _p(t):
@@ -52,10 +52,11 @@ class DeviceCSR(object):
     """Canonical CSR (int32 indptr / sorted int32 indices, float64 data) resident on the GPU; `ddata` optionally holds
     d/d(rho) of every stored entry on the same pattern."""
 
-    def __init__(self, n, indptr, indices, data, ddata=None, kernel_threshold=None):
+    def __init__(self, n, indptr, indices, data, ddata=None, kernel_threshold=None, order=None):
         self.n = int(n)
         self.indptr, self.indices, self.data, self.ddata = indptr, indices, data, ddata
         self.kernel_threshold = kernel_threshold
+        self.order = order      # optional spatially local ordering of the points (device int32), see SparseEngine
 
     @property
     def shape(self):
@@ -100,13 +101,15 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
                                     _p(indptr), ctypes.byref(nnz), s)
     check(rc, 'gp_matern_sparse_count')
+    order = torch.empty(n, dtype=torch.int32, device='cuda')
+    check(lib.gp_sparse_cell_order(_p(ws), n, d, _p(order), s), 'gp_sparse_cell_order')
     indices = torch.empty(nnz.value, dtype=torch.int32, device='cuda')
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
     rc = lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
                                    _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None, s)
     check(rc, 'gp_matern_sparse_fill')
-    K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau)
+    K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order)
     if verbose:
         print('Generated sparse correlation matrix using kernel threshold: %0.4f and sparse density: %0.2e.'
               % (tau, K.nnz / float(n) ** 2))
@@ -142,8 +145,32 @@ class SparseEngine(object):
         self._ws = {}
         self._slq_cache = {}
         self.last_info = {}
-        # multi-GPU: (rank, world) -> this engine evaluates the probes p with p % world == rank; see _distributed.py
+        # multi-GPU: (rank, world) -> this engine evaluates its slice of every round of probes; see _run_estimator
         self.probe_range = probe_range
+        # Internally the operator works on a symmetrically permuted copy P K P^T whose rows follow the generator's
+        # cell order: neighbouring rows then gather neighbouring entries of the probe block (cache hits instead of
+        # random L2 traffic). Results are independent of the permutation: probes are hashed with ORIGINAL row ids.
+        self.order = self.inv_order = None
+        self.op = K
+        if K.order is not None and self.opt.get('locality', True):
+            self._build_permuted(K)
+
+    def _build_permuted(self, K):
+        torch = dev.torch
+        order = K.order.to(torch.int64)
+        inv = torch.empty(self.n, dtype=torch.int32, device='cuda')
+        inv[order] = torch.arange(self.n, dtype=torch.int32, device='cuda')
+        lengths = (K.indptr[1:] - K.indptr[:-1])[order]
+        new_indptr = torch.zeros(self.n + 1, dtype=torch.int32, device='cuda')
+        new_indptr[1:] = torch.cumsum(lengths, 0).to(torch.int32)
+        new_indices = torch.empty_like(K.indices)
+        new_data = torch.empty_like(K.data)
+        new_ddata = torch.empty_like(K.ddata) if K.ddata is not None else None
+        check(lib.gp_csr_permute(self.n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(K.data),
+                                 _p(K.ddata) if K.ddata is not None else None, _p(new_indptr), _p(new_indices), _p(new_data),
+                                 _p(new_ddata) if new_ddata is not None else None, dev.stream_ptr()), 'gp_csr_permute')
+        self.op = DeviceCSR(self.n, new_indptr, new_indices, new_data, new_ddata)
+        self.order, self.inv_order = order, inv.to(torch.int64)
 
     # ---- plumbing ----------------------------------------------------------------------------------------------
     def _workspace(self, B):
@@ -154,17 +181,26 @@ class SparseEngine(object):
 
     def spmm(self, eta, X_dev, data=None):
         torch = dev.torch
+        """(K + eta I) X in OPERATOR space (rows in self.order when the operator is permuted)"""
         B = X_dev.shape[1]
         Y = torch.empty_like(X_dev)
-        K = self.K
+        K = self.op
         check(lib.gp_csr_spmm(_p(K.indptr), _p(K.indices), _p(K.data if data is None else data), self.n, float(eta),
                               _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_csr_spmm')
         return Y
 
+    def to_op(self, X_dev):
+        return X_dev if self.order is None else X_dev[self.order].contiguous()
+
+    def from_op(self, X_dev):
+        return X_dev if self.order is None else X_dev[self.inv_order].contiguous()
+
     def probes(self, first, B):
         torch = dev.torch
         V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
-        check(lib.gp_rademacher(_p(V), self.n, B, int(self.opt['seed']), int(first), dev.stream_ptr()), 'gp_rademacher')
+        rmap = self.K.order if self.order is not None else None
+        check(lib.gp_rademacher(_p(V), self.n, B, int(self.opt['seed']), int(first), _p(rmap) if rmap is not None else None,
+                                dev.stream_ptr()), 'gp_rademacher')
         return V
 
     # ---- SLQ -----------------------------------------------------------------------------------------------------
@@ -172,7 +208,7 @@ class SparseEngine(object):
         """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1."""
         torch = dev.torch
         m = int(self.opt['lanczos_degree'])
-        K = self.K
+        K = self.op
         V = self.probes(first, B)
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
@@ -285,7 +321,7 @@ class SparseEngine(object):
         def fn(first, width):
             V = self.probes(first, width)
             U = self.solve_dev(eta, V.clone())
-            Wd = self.spmm(0.0, V, data=self.K.ddata)
+            Wd = self.spmm(0.0, V, data=self.op.ddata)
             return self.col_dot(U, Wd).reshape(-1, 1)
         mean, half, N = self._run_estimator(fn, 1)
         self.last_info = {'num_samples': N, 'half_width': half}
@@ -304,7 +340,7 @@ class SparseEngine(object):
         torch = dev.torch
         B = R_dev.shape[1]
         X = torch.empty_like(R_dev)
-        K = self.K
+        K = self.op
         it = ctypes.c_int64()
         rc = lib.gp_cg_solve(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(R_dev), _p(X), B,
                              float(self.opt['cg_tol']), int(self.opt['cg_maxiter']), ctypes.byref(it),
@@ -334,7 +370,7 @@ class SparseEngine(object):
                 B *= 2
             R = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
             R[:, :blk.shape[1]].copy_(torch.from_numpy(numpy.ascontiguousarray(blk)))
-            X = self.solve_dev(eta, R)
+            X = self.from_op(self.solve_dev(eta, self.to_op(R)))
             out[:, c0:c0 + blk.shape[1]] = X[:, :blk.shape[1]].cpu().numpy()
         return out[:, 0] if vec else out
 
@@ -351,7 +387,7 @@ class SparseEngine(object):
             return numpy.hstack([self.matmul(X2[:, c:c + 32]) for c in range(0, k, 32)])
         Xd = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
         Xd[:, :k].copy_(torch.from_numpy(numpy.ascontiguousarray(X2)))
-        res = self.spmm(0.0, Xd)[:, :k].cpu().numpy()
+        res = self.from_op(self.spmm(0.0, self.to_op(Xd)))[:, :k].cpu().numpy()
         return res[:, 0] if vec else res
 
     def trace_K(self):

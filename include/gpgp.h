@@ -74,6 +74,8 @@ int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d);
 int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d,
                            const double* scale_host, double nu, double tau, void* ws, int* indptr_dev,
                            int64_t* nnz_host, void* stream);
+/* cell-sorted (spatially local) order of the points left in ws by gp_matern_sparse_count: order_dev (device int32, n) */
+int gp_sparse_cell_order(void* ws, int64_t n, int64_t d, int* order_dev, void* stream);
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d,
                           const double* scale_host, double nu, double tau, void* ws, const int* indptr_dev,
                           int* indices_dev, double* data_dev, double* ddata_dev, void* stream);
@@ -135,8 +137,15 @@ int gp_symm_skinny(const double* K, int64_t n, int64_t npad, const double* X, in
 /* Y = (K + eta I) X */
 int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* X,
                 int64_t B, double* Y, void* stream);
-/* V[i][c] = +-1 from a counter-based hash of (seed, probe_offset + c, i): identical for any batching / rank count */
-int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, void* stream);
+/* V[i][c] = +-1 from a counter-based hash of (seed, probe_offset + c, row): identical for any batching / rank count.
+ * row = row_map[i] when row_map (device int32, n) is given (internally permuted operators), else i. */
+int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map,
+                  void* stream);
+/* Symmetric permutation of a CSR matrix: new row r = old row order[r], new column = inv_order[old column]
+ * (columns stay in the old within-row order). new_indptr is the caller's prefix sum of the permuted row lengths. */
+int gp_csr_permute(int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
+                   const double* data, const double* ddata, const int* new_indptr, int* new_indices, double* new_data,
+                   double* new_ddata, void* stream);
 /* workspace for gp_col_dot / gp_lanczos / gp_cg_solve */
 int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B);
 /* out_dev[c] = sum_i X[i][c] Y[i][c] (deterministic two-stage reduction) */

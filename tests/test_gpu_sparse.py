@@ -198,3 +198,21 @@ def test_likelihood_through_sparse_operator(sparse_problem):
     pts, z, X, Kd = sparse_problem
     lk = Likelihood(X, Kd.to_scipy(), likelihood_method='profiled')
     assert lk.K_mixed.sparse and lk.K_mixed.imate_method == 'slq'
+
+
+def test_internal_permutation_does_not_change_results(sparse_problem):
+    """The operator works on a cell-ordered permuted copy of the CSR matrix; probes are hashed with original row ids,
+    so every output must agree with the unpermuted operator up to summation order."""
+    from gaussian_proc._sparse import SparseEngine
+    pts, z, X, Kd = sparse_problem
+    opts = {'seed': 3, 'lanczos_degree': 25, 'min_num_samples': 16, 'max_num_samples': 16}
+    a = SparseEngine(Kd, 'slq', dict(opts, locality=True))
+    b = SparseEngine(Kd, 'slq', dict(opts, locality=False))
+    assert a.order is not None and b.order is None
+    assert abs(a.logdet(2.0) - b.logdet(2.0)) <= 1e-10 * abs(b.logdet(2.0))
+    assert abs(a.traceinv(2.0) - b.traceinv(2.0)) <= 1e-10 * abs(b.traceinv(2.0))
+    assert abs(a.traceinv_dK(2.0) - b.traceinv_dK(2.0)) <= 1e-7 * abs(b.traceinv_dK(2.0))    # CG stops at rtol 1e-6
+    assert numpy.max(numpy.abs(a.solve(2.0, z) - b.solve(2.0, z))) <= 1e-6 * numpy.max(numpy.abs(b.solve(2.0, z)))
+    assert numpy.max(numpy.abs(a.matmul(X) - b.matmul(X))) <= 1e-12
+    Va = a.from_op(a.probes(0, 4)).cpu().numpy()
+    assert (Va == b.probes(0, 4).cpu().numpy()).all()
