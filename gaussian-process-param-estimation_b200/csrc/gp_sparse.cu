@@ -397,6 +397,27 @@ static void launch_rows_mode(int mode, int pass, bool with_dk, const SparseParam
     }
 }
 
+struct MortonParams {
+    double lo[3], mul[3];
+    int nd, d, bits;
+};
+
+__global__ void morton_keys_kernel(const double* __restrict__ points, int64_t n, MortonParams mp, int64_t* keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long qmax = (1ull << mp.bits) - 1ull;
+    unsigned long long q[3] = {0ull, 0ull, 0ull};
+    for (int k = 0; k < mp.nd; ++k) {
+        double t = (points[i * mp.d + k] - mp.lo[k]) * mp.mul[k];
+        unsigned long long v = (t > 0.0) ? (unsigned long long)t : 0ull;
+        q[k] = v > qmax ? qmax : v;
+    }
+    unsigned long long key = 0ull;
+    for (int b = mp.bits - 1; b >= 0; --b)
+        for (int k = 0; k < mp.nd; ++k) key = (key << 1) | ((q[k] >> b) & 1ull);
+    keys[i] = (int64_t)key;
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -504,12 +525,26 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     return 0;
 }
 
-// the cell-sorted order of the points computed by gp_matern_sparse_count (device int32, n): a spatially local
-// ordering that the sparse operator uses internally to make its SpMM gathers cache friendly
-int gp_sparse_cell_order(void* ws, int64_t n, int64_t d, int* order_dev, void* stream) {
-    if (!ws || !order_dev || n <= 0) return -1;
-    SparseWs w = carve_sparse(ws, n, d);
-    GP_CUDA_CHECK(cudaMemcpyAsync(order_dev, w.sorted_idx, sizeof(int) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+// Z-order (Morton) keys of the points over their bounding box (the first min(d, 3) coordinates, 63 / min(d, 3) bits
+// each): a stable sort by this key gives a deterministic, spatially local ordering of the points. The sparse operator
+// uses it internally (row-blocked form, gp_bcsr_*): consecutive rows then have nearly identical patterns.
+int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo_host, const double* hi_host,
+                    int64_t* keys_dev, void* stream) {
+    if (!points || !lo_host || !hi_host || !keys_dev || n <= 0 || d <= 0) return -1;
+    MortonParams mp;
+    mp.nd = (int)(d < 3 ? d : 3);
+    mp.d = (int)d;
+    mp.bits = 63 / mp.nd;
+    if (mp.bits > 31) mp.bits = 31;
+    for (int k = 0; k < 3; ++k) { mp.lo[k] = 0.0; mp.mul[k] = 0.0; }
+    for (int k = 0; k < mp.nd; ++k) {
+        double extent = hi_host[k] - lo_host[k];
+        mp.lo[k] = lo_host[k];
+        mp.mul[k] = (extent > 0.0) ? ldexp(1.0, mp.bits) / extent : 0.0;
+    }
+    morton_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, n, mp, keys_dev);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
     return 0;
 }
 

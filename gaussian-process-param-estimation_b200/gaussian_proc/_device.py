@@ -51,8 +51,12 @@ SIGNATURES = {
     'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gp_csr_spmm': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp, _vp]),
-    'gp_csr_permute': (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'gp_sparse_cell_order': (_int, [_vp, _i64, _i64, _vp, _vp]),
+    'gp_spatial_keys': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_count': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_fill': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_spmm': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
+    'gp_bcsr_lanczos': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_cg_solve': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_krylov_workspace_bytes': (_i64, [_i64, _i64]),
     'gp_col_dot': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'gp_lanczos': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=8, cg_tol=1e-6, cg_maxiter=2000, locality=True)
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=4)
 
 
 def _p(t):
@@ -56,7 +56,7 @@ class DeviceCSR(object):
         self.n = int(n)
         self.indptr, self.indices, self.data, self.ddata = indptr, indices, data, ddata
         self.kernel_threshold = kernel_threshold
-        self.order = order      # optional spatially local ordering of the points (device int32), see SparseEngine
+        self.order = order      # optional spatially local ordering of the rows (device int32), see SparseEngine
 
     @property
     def shape(self):
@@ -101,8 +101,12 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
                                     _p(indptr), ctypes.byref(nnz), s)
     check(rc, 'gp_matern_sparse_count')
-    order = torch.empty(n, dtype=torch.int32, device='cuda')
-    check(lib.gp_sparse_cell_order(_p(ws), n, d, _p(order), s), 'gp_sparse_cell_order')
+    # deterministic, spatially local order of the points (stable sort of Z-order keys) for the row-blocked operator
+    lo, hi = dev.host_f64(points.min(axis=0)), dev.host_f64(points.max(axis=0))
+    keys = torch.empty(n, dtype=torch.int64, device='cuda')
+    check(lib.gp_spatial_keys(_p(dpts), n, d, dev.host_ptr(lo), dev.host_ptr(hi), _p(keys), s), 'gp_spatial_keys')
+    order = torch.sort(keys, stable=True)[1].to(torch.int32)
+    del keys
     indices = torch.empty(nnz.value, dtype=torch.int32, device='cuda')
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
@@ -147,29 +151,41 @@ class SparseEngine(object):
         self.last_info = {}
         # multi-GPU: (rank, world) -> this engine evaluates its slice of every round of probes; see _run_estimator
         self.probe_range = probe_range
-        # Internally the operator works on a symmetrically permuted copy P K P^T whose rows follow the generator's
-        # cell order: neighbouring rows then gather neighbouring entries of the probe block (cache hits instead of
-        # random L2 traffic). Results are independent of the permutation: probes are hashed with ORIGINAL row ids.
+        # Internally the operator works on the ROW-BLOCKED form of the symmetrically permuted matrix P K P^T (rows in
+        # the generator's Z-order): block_rows consecutive rows share one column list, so one gathered row of the probe
+        # block serves block_rows rows of K. Results do not depend on the permutation: probes are hashed with ORIGINAL
+        # row ids. block_rows = 1 (or a K without an order, e.g. from SciPy) keeps plain CSR in the original order.
         self.order = self.inv_order = None
-        self.op = K
-        if K.order is not None and self.opt.get('locality', True):
-            self._build_permuted(K)
+        self.R = 1
+        self.blocked = None
+        R = int(self.opt.get('block_rows', 4))
+        if R not in (1, 2, 4, 8):
+            raise ValueError('block_rows should be 1, 2, 4 or 8.')
+        if K.order is not None and R > 1:
+            self._build_blocked(K, R)
 
-    def _build_permuted(self, K):
+    def _build_blocked(self, K, R):
         torch = dev.torch
+        n = self.n
         order = K.order.to(torch.int64)
-        inv = torch.empty(self.n, dtype=torch.int32, device='cuda')
-        inv[order] = torch.arange(self.n, dtype=torch.int32, device='cuda')
-        lengths = (K.indptr[1:] - K.indptr[:-1])[order]
-        new_indptr = torch.zeros(self.n + 1, dtype=torch.int32, device='cuda')
-        new_indptr[1:] = torch.cumsum(lengths, 0).to(torch.int32)
-        new_indices = torch.empty_like(K.indices)
-        new_data = torch.empty_like(K.data)
-        new_ddata = torch.empty_like(K.ddata) if K.ddata is not None else None
-        check(lib.gp_csr_permute(self.n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(K.data),
-                                 _p(K.ddata) if K.ddata is not None else None, _p(new_indptr), _p(new_indices), _p(new_data),
-                                 _p(new_ddata) if new_ddata is not None else None, dev.stream_ptr()), 'gp_csr_permute')
-        self.op = DeviceCSR(self.n, new_indptr, new_indices, new_data, new_ddata)
+        inv = torch.empty(n, dtype=torch.int32, device='cuda')
+        inv[order] = torch.arange(n, dtype=torch.int32, device='cuda')
+        nrb = (n + R - 1) // R
+        nblk = torch.empty(nrb, dtype=torch.int32, device='cuda')
+        s = dev.stream_ptr()
+        check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), s), 'gp_bcsr_count')
+        bptr = torch.zeros(nrb + 1, dtype=torch.int64, device='cuda')
+        bptr[1:] = torch.cumsum(nblk, 0, dtype=torch.int64)
+        total = int(bptr[-1].item())
+        bidx = torch.empty(total, dtype=torch.int32, device='cuda')
+        bvals = torch.empty(total * R, dtype=torch.float64, device='cuda')
+        bdvals = torch.empty(total * R, dtype=torch.float64, device='cuda') if K.ddata is not None else None
+        check(lib.gp_bcsr_fill(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(K.data),
+                               _p(K.ddata) if K.ddata is not None else None, _p(bptr), _p(bidx), _p(bvals),
+                               _p(bdvals) if bdvals is not None else None, s), 'gp_bcsr_fill')
+        self.R = R
+        self.blocked = (bptr, bidx, bvals, bdvals)
+        self.fill_ratio = total * R / float(max(K.nnz, 1))     # stored values per original nonzero (>= 1)
         self.order, self.inv_order = order, inv.to(torch.int64)
 
     # ---- plumbing ----------------------------------------------------------------------------------------------
@@ -179,14 +195,20 @@ class SparseEngine(object):
             self._ws[B] = torch.empty(lib.gp_krylov_workspace_bytes(self.n, B) // 8 + 8, dtype=torch.float64, device='cuda')
         return self._ws[B]
 
-    def spmm(self, eta, X_dev, data=None):
+    def spmm(self, eta, X_dev, derivative=False):
+        """(K + eta I) X, or (dK/drho + eta I) X with ``derivative``, in OPERATOR space (rows in self.order when the
+        operator is permuted)"""
         torch = dev.torch
-        """(K + eta I) X in OPERATOR space (rows in self.order when the operator is permuted)"""
         B = X_dev.shape[1]
         Y = torch.empty_like(X_dev)
-        K = self.op
-        check(lib.gp_csr_spmm(_p(K.indptr), _p(K.indices), _p(K.data if data is None else data), self.n, float(eta),
-                              _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_csr_spmm')
+        if self.blocked is not None:
+            bptr, bidx, bvals, bdvals = self.blocked
+            check(lib.gp_bcsr_spmm(self.R, _p(bptr), _p(bidx), _p(bdvals if derivative else bvals), self.n, float(eta),
+                                   _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_bcsr_spmm')
+        else:
+            K = self.K
+            check(lib.gp_csr_spmm(_p(K.indptr), _p(K.indices), _p(K.ddata if derivative else K.data), self.n, float(eta),
+                                  _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_csr_spmm')
         return Y
 
     def to_op(self, X_dev):
@@ -208,12 +230,17 @@ class SparseEngine(object):
         """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1."""
         torch = dev.torch
         m = int(self.opt['lanczos_degree'])
-        K = self.op
         V = self.probes(first, B)
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
-        check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha), _p(beta),
-                             _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
+        if self.blocked is not None:
+            bptr, bidx, bvals, _ = self.blocked
+            check(lib.gp_bcsr_lanczos(self.R, _p(bptr), _p(bidx), _p(bvals), self.n, float(eta), _p(V), B, m, _p(alpha),
+                                      _p(beta), _p(self._workspace(B)), dev.stream_ptr()), 'gp_bcsr_lanczos')
+        else:
+            K = self.K
+            check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha),
+                                 _p(beta), _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
         a, b = alpha.cpu().numpy(), beta.cpu().numpy()
         out = numpy.empty((B, 3))
         for c in range(B):
@@ -321,7 +348,7 @@ class SparseEngine(object):
         def fn(first, width):
             V = self.probes(first, width)
             U = self.solve_dev(eta, V.clone())
-            Wd = self.spmm(0.0, V, data=self.op.ddata)
+            Wd = self.spmm(0.0, V, derivative=True)
             return self.col_dot(U, Wd).reshape(-1, 1)
         mean, half, N = self._run_estimator(fn, 1)
         self.last_info = {'num_samples': N, 'half_width': half}
@@ -340,11 +367,17 @@ class SparseEngine(object):
         torch = dev.torch
         B = R_dev.shape[1]
         X = torch.empty_like(R_dev)
-        K = self.op
         it = ctypes.c_int64()
-        rc = lib.gp_cg_solve(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(R_dev), _p(X), B,
-                             float(self.opt['cg_tol']), int(self.opt['cg_maxiter']), ctypes.byref(it),
-                             _p(self._workspace(B)), dev.stream_ptr())
+        if self.blocked is not None:
+            bptr, bidx, bvals, _ = self.blocked
+            rc = lib.gp_bcsr_cg_solve(self.R, _p(bptr), _p(bidx), _p(bvals), self.n, float(eta), _p(R_dev), _p(X), B,
+                                      float(self.opt['cg_tol']), int(self.opt['cg_maxiter']), ctypes.byref(it),
+                                      _p(self._workspace(B)), dev.stream_ptr())
+        else:
+            K = self.K
+            rc = lib.gp_cg_solve(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(R_dev), _p(X), B,
+                                 float(self.opt['cg_tol']), int(self.opt['cg_maxiter']), ctypes.byref(it),
+                                 _p(self._workspace(B)), dev.stream_ptr())
         check(rc, 'gp_cg_solve')
         self.last_cg_iterations = it.value
         if rc == 2:

@@ -74,8 +74,10 @@ int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d);
 int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d,
                            const double* scale_host, double nu, double tau, void* ws, int* indptr_dev,
                            int64_t* nnz_host, void* stream);
-/* cell-sorted (spatially local) order of the points left in ws by gp_matern_sparse_count: order_dev (device int32, n) */
-int gp_sparse_cell_order(void* ws, int64_t n, int64_t d, int* order_dev, void* stream);
+/* Z-order (Morton) keys of the points over the bounding box [lo_host, hi_host] (first min(d,3) coordinates): a stable
+ * sort by key is the deterministic, spatially local row order the row-blocked sparse operator (gp_bcsr_*) uses. */
+int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo_host, const double* hi_host,
+                    int64_t* keys_dev, void* stream);
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d,
                           const double* scale_host, double nu, double tau, void* ws, const int* indptr_dev,
                           int* indices_dev, double* data_dev, double* ddata_dev, void* stream);
@@ -141,11 +143,21 @@ int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64
  * row = row_map[i] when row_map (device int32, n) is given (internally permuted operators), else i. */
 int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map,
                   void* stream);
-/* Symmetric permutation of a CSR matrix: new row r = old row order[r], new column = inv_order[old column]
- * (columns stay in the old within-row order). new_indptr is the caller's prefix sum of the permuted row lengths. */
-int gp_csr_permute(int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
-                   const double* data, const double* ddata, const int* new_indptr, int* new_indices, double* new_data,
-                   double* new_ddata, void* stream);
+/* Row-blocked form of a (symmetrically permuted) CSR matrix: R (2, 4 or 8) consecutive rows share one list of
+ * block-columns (R x 1 blocks, zero filled). New row r = old row order[r], new column = inv_order[old column] (both
+ * NULL: no permutation); the source rows must be sorted. With a spatially local order (gp_spatial_keys) neighbouring
+ * rows have nearly the same pattern: one gathered row of X then serves R rows of K and the index is amortised.
+ *   gp_bcsr_count: nblk[rb] = number of block-columns of row block rb (ceil(n/R) entries); the caller's exclusive
+ *                  prefix sum gives bptr (int64, ceil(n/R)+1).
+ *   gp_bcsr_fill : bidx (int32, bptr[last]), bvals / bdvals (f64, R * bptr[last], block-column major). */
+int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
+                  int* nblk, void* stream);
+int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
+                 const double* data, const double* ddata, const int64_t* bptr, int* bidx, double* bvals, double* bdvals,
+                 void* stream);
+/* Y = (K + eta I) X on the row-blocked operator */
+int gp_bcsr_spmm(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
+                 const double* X, int64_t B, double* Y, void* stream);
 /* workspace for gp_col_dot / gp_lanczos / gp_cg_solve */
 int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B);
 /* out_dev[c] = sum_i X[i][c] Y[i][c] (deterministic two-stage reduction) */
@@ -159,6 +171,12 @@ int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_
  * definite: the hard-thresholded Matern matrix is indefinite, _generate_sparse_correlation.pyx:516-523). */
 int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64_t n, double eta, double* R0, double* X,
                 int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream);
+/* the same two Krylov drivers on the row-blocked operator */
+int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
+                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);
+int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
+                     double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused log-likelihood (+ gradient ingredients) evaluation at one (rho, eta)

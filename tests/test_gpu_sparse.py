@@ -200,15 +200,49 @@ def test_likelihood_through_sparse_operator(sparse_problem):
     assert lk.K_mixed.sparse and lk.K_mixed.imate_method == 'slq'
 
 
+@pytest.mark.parametrize('R', [2, 4, 8])
+def test_row_blocked_operator_equals_csr(gp, R):
+    """The row-blocked operator (R x 1 blocks of the Z-order permuted matrix, zero filled) is the same linear map as the
+    canonical CSR: products against the SciPy matrix to rounding, for K and for dK/drho, n not a multiple of R."""
+    import torch
+    from gaussian_proc._sparse import SparseEngine, generate_sparse_correlation
+    numpy.random.seed(5)
+    n = 3001
+    pts = numpy.random.rand(n, 2)
+    Kd = generate_sparse_correlation(pts, numpy.array([0.03, 0.03]), 1.5, 0.01, device=True, with_derivative=True)
+    order = Kd.order.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(n))
+    eng = SparseEngine(Kd, 'slq', {'block_rows': R})
+    assert eng.R == R and eng.blocked is not None and 1.0 <= eng.fill_ratio <= R
+    Ks = Kd.to_scipy()
+    dKs = scipy.sparse.csr_matrix((Kd.ddata.cpu().numpy(), Ks.indices, Ks.indptr), shape=Ks.shape)
+    for B in (1, 2, 4, 8, 16, 32):
+        Xh = numpy.random.randn(n, B)
+        Xd = torch.from_numpy(Xh).cuda()
+        Y = eng.from_op(eng.spmm(0.75, eng.to_op(Xd))).cpu().numpy()
+        ref = Ks @ Xh + 0.75 * Xh
+        assert numpy.max(numpy.abs(Y - ref)) <= 1e-12 * numpy.max(numpy.abs(ref))
+        Yd = eng.from_op(eng.spmm(0.0, eng.to_op(Xd), derivative=True)).cpu().numpy()
+        refd = dKs @ Xh
+        assert numpy.max(numpy.abs(Yd - refd)) <= 1e-12 * numpy.max(numpy.abs(refd))
+    # the stored block-columns are exactly the union of the rows' patterns: value count = R * (number of block-columns)
+    bptr, bidx, bvals, _ = eng.blocked
+    assert int(bptr[-1]) == bidx.numel() and bvals.numel() == R * bidx.numel()
+    assert int((bvals != 0).sum()) == Ks.nnz
+
+
 def test_internal_permutation_does_not_change_results(sparse_problem):
-    """The operator works on a cell-ordered permuted copy of the CSR matrix; probes are hashed with original row ids,
-    so every output must agree with the unpermuted operator up to summation order."""
+    """The operator works on a Z-order permuted, row-blocked copy of the CSR matrix; probes are hashed with original row
+    ids, so every output must agree with the unpermuted plain-CSR operator up to summation order. The order is a
+    stable sort, so two builds give bit-identical results."""
     from gaussian_proc._sparse import SparseEngine
     pts, z, X, Kd = sparse_problem
     opts = {'seed': 3, 'lanczos_degree': 25, 'min_num_samples': 16, 'max_num_samples': 16}
-    a = SparseEngine(Kd, 'slq', dict(opts, locality=True))
-    b = SparseEngine(Kd, 'slq', dict(opts, locality=False))
+    a = SparseEngine(Kd, 'slq', dict(opts, block_rows=4))
+    b = SparseEngine(Kd, 'slq', dict(opts, block_rows=1))
+    a2 = SparseEngine(Kd, 'slq', dict(opts, block_rows=4))
     assert a.order is not None and b.order is None
+    assert a.logdet(2.0) == a2.logdet(2.0)
     assert abs(a.logdet(2.0) - b.logdet(2.0)) <= 1e-10 * abs(b.logdet(2.0))
     assert abs(a.traceinv(2.0) - b.traceinv(2.0)) <= 1e-10 * abs(b.traceinv(2.0))
     assert abs(a.traceinv_dK(2.0) - b.traceinv_dK(2.0)) <= 1e-7 * abs(b.traceinv_dK(2.0))    # CG stops at rtol 1e-6

@@ -21,13 +21,19 @@ gen()
 out['t_generate_s'], K = timed(gen)
 out['nnz'] = K.nnz
 out['generate_GBs'] = (20.0 * K.nnz + 4.0 * (n + 1)) / out['t_generate_s'] * 1e-9
+for R in (1, 2, 4, 8):
+    SparseEngine(K, 'slq', {'block_rows': R})
+    t, e = timed(lambda: SparseEngine(K, 'slq', {'block_rows': R}))
+    out['R%d' % R] = {'build_s': t, 'fill_ratio': getattr(e, 'fill_ratio', 1.0)}
+    for B in (1, 8, 16, 32):
+        V = e.probes(0, B)
+        e.spmm(1.0, V)
+        t, _ = timed(lambda: e.spmm(1.0, V), 10)
+        out['R%d' % R]['spmm_B%d_ms' % B] = t * 1e3
+        out['R%d' % R]['spmm_B%d_algGBs' % B] = (12.0 * K.nnz + 4.0 * (n + 1) + 16.0 * n * B) / t * 1e-9
+    del e
+    torch.cuda.empty_cache()
 eng = SparseEngine(K, 'slq', {'seed': 0, 'lanczos_degree': 30})
-for B in (1, 8, 16, 32):
-    V = eng.probes(0, B)
-    eng.spmm(1.0, V)
-    t, _ = timed(lambda: eng.spmm(1.0, V), 10)
-    out['spmm_B%d_ms' % B] = t * 1e3
-    out['spmm_B%d_GBs' % B] = (12.0 * K.nnz + 4.0 * (n + 1) + 16.0 * n * B) / t * 1e-9
 # extreme Ritz values of K itself (eta = 0) from one 60-step Lanczos run: tells which eta keep K + eta I positive
 from gaussian_proc._sparse import lanczos_quadrature
 import torch as _t
