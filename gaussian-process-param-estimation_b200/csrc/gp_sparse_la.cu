@@ -125,7 +125,7 @@ __global__ void rademacher_kernel(int64_t n, int B, uint64_t seed, int64_t probe
     V[idx] = (z & 1ull) ? 1.0 : -1.0;
 }
 
-// ---- row-blocked operator: R consecutive rows share one column list (R x 1 blocks, zero filled) -----------------
+// ---- row-blocked operator: R = 8 consecutive rows share one column list (8 x 1 blocks, zero filled) -------------
 // Rows that are neighbours in a spatially sorted order have almost the same pattern, so one gathered row of X serves
 // R rows of K: gather traffic (the L1/L2-bound part of a multi-column SpMM) drops ~R-fold and the column index is
 // amortised over R values. Block-columns of a row block: [all columns of row 0][columns of row 1 not in row 0]...
@@ -139,7 +139,8 @@ __device__ __forceinline__ int find_col(const int* __restrict__ row, int len, in
     return (lo < len && row[lo] == c) ? lo : -1;
 }
 
-// one warp per row block. PASS 0: nblk[rb] = number of distinct columns; PASS 1: fill (bidx, bvals[, bdvals]).
+// one warp per row block. PASS 0: nblk[rb] = number of distinct columns rounded up to a multiple of 4 (the k extent of
+// one DMMA); PASS 1: fill (bidx, bvals[, bdvals]); padding block-columns repeat the block's first column with zeros.
 // new row r = old row order[r]; new column = inv_order[old column]; the source CSR must have sorted rows.
 template <int R, int PASS>
 __global__ void __launch_bounds__(256)
@@ -201,105 +202,99 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
             running += __popc(m);
         }
     }
-    if (PASS == 0 && lane == 0) nblk[rb] = running;
+    const int padded = (running + 3) & ~3;
+    if (PASS == 0 && lane == 0) nblk[rb] = padded;
+    if (PASS == 1 && lane < padded - running) {
+        const int64_t slot = base + running + lane;
+        const int c0 = (len[0] > 0) ? indices[s[0]] : (order ? order[rb * R] : rb * R);
+        bidx[slot] = inv_order ? inv_order[c0] : c0;
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) {
+            bvals[slot * R + kk] = 0.0;
+            if (ddata) bdvals[slot * R + kk] = 0.0;
+        }
+    }
 }
 
-// Y = (K + eta I) X on the row-blocked operator. One warp per row block. The (index, values) stream of the row block
-// is moved global -> shared with cp.async in chunks of 32 block-columns (one per lane, fully coalesced, double
-// buffered: the next chunk is in flight while the current one is consumed), which keeps enough bytes in flight for
-// HBM whatever B is. In the consume loop a lane owns CPL (= 2, or 1 for B = 1) columns of X and every NQ-th
-// block-column of the chunk: it reads index + R values from shared memory (broadcast within the lane group) and
-// gathers ONE row of X (16-byte loads, served by L1/L2: rows are in Z-order) for R rows of K.
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
-}
-
-template <int B, int R>
+// Y = (K + eta I) X on the row-blocked operator (R = 8) with FP64 tensor-core MMAs. One warp per row block. Four
+// block-columns form one DMMA.8x8x4: A (8 rows x 4 block-columns) is exactly 256 contiguous bytes of the value stream
+// (one 8-byte load per lane, no broadcast), B (4 x 8) holds the four gathered rows of X restricted to 8 columns, and the
+// 8 x 8 accumulator stays in two registers per lane for the whole row block - no cross-lane reduction. For B = 16 / 32
+// the 2 / 4 MMAs of a step share A; their column sets are interleaved (tile j owns columns j, j + NT, ...) so that a
+// lane's B operands are NT consecutive doubles of one X row (one 16-byte load for B = 16) and its results are 2 NT
+// consecutive columns of one Y row. Index and values are streamed past L1 (ld.global.cs): L1 is kept for X.
+template <int B>
 __global__ void __launch_bounds__(256)
-bcsr_spmm_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
-                 double eta, const double* __restrict__ X, double* __restrict__ Y) {
-    constexpr int CPL = (B >= 2) ? 2 : 1;
-    constexpr int LPB = B / CPL;       // lanes per block-column
-    constexpr int NQ = 32 / LPB;       // block-columns per warp step
-    constexpr int NST = 2;             // cp.async stages
-    __shared__ int s_idx[8][NST][32];
-    __shared__ __align__(16) double s_val[8][NST][32 * R];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int rb = blockIdx.x * 8 + w;
-    if (rb * R >= n) return;           // whole warps leave; only __syncwarp below
-    const int q = lane / LPB, c = (lane % LPB) * CPL;
-    const int64_t p0 = bptr[rb], p1 = bptr[rb + 1];
-    const int nch = (int)((p1 - p0 + 31) >> 5);
-    double acc[R][CPL];
+bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
+                       double eta, const double* __restrict__ X, double* __restrict__ Y) {
+    constexpr int NT = (B >= 8) ? B / 8 : 1;   // 8-column MMA tiles per step
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;     // DMMA.8x8x4 fragments: A[g][t], B[t][g], D[g][2t .. 2t+1]
+    const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rb * 8 >= n) return;
+    const int64_t p0 = bptr[rb], p1 = bptr[rb + 1];   // p1 - p0 is a multiple of 4
+    double acc[NT][2];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
+    const bool colok = (B >= 8) || (g < B);
+    const int coff = (B >= 8) ? g * NT : (colok ? g : 0);
+    const double* aptr = bvals + g + t * 8;
+    auto load_x = [&](int col, double* x) {
+        const double* xr = X + (int64_t)col * B + coff;
+        if (NT == 1) {
+            x[0] = colok ? *xr : 0.0;
+        } else {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) acc[r][k] = 0.0;
-
-    auto issue = [&](int ch) {
-        const int st = ch % NST;
-        const int64_t p = p0 + (int64_t)ch * 32 + lane;
-        if (ch < nch && p < p1) {
-            cp_async4(&s_idx[w][st][lane], bidx + p);
-#pragma unroll
-            for (int r = 0; r < R; r += 2) cp_async16(&s_val[w][st][lane * R + r], bvals + p * R + r);
+            for (int j = 0; j < NT; j += 2) {
+                double2 v = *reinterpret_cast<const double2*>(xr + j);
+                x[j] = v.x;
+                x[j + (NT > 1 ? 1 : 0)] = v.y;
+            }
         }
-        cp_async_commit();
     };
-    issue(0);
-    for (int ch = 0; ch < nch; ++ch) {
-        issue(ch + 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        const int st = ch % NST;
-        const int cnt = (int)min((int64_t)32, p1 - (p0 + (int64_t)ch * 32));
+    constexpr int U = (NT <= 2) ? 4 : 2;       // steps in flight per warp: all loads of U steps are issued before their MMAs
+    int64_t p = p0;
+    for (; p + 4 * U <= p1; p += 4 * U) {
+        int col[U];
+        double a[U], x[U][NT];
 #pragma unroll
-        for (int j = 0; j < 32 / NQ; ++j) {
-            const int e = j * NQ + q;
-            const bool ok = e < cnt;
-            const int col = ok ? s_idx[w][st][e] : 0;
-            double v[R], x[CPL];
+        for (int u = 0; u < U; ++u) col[u] = __ldcs(bidx + p + 4 * u + t);
 #pragma unroll
-            for (int r = 0; r < R; r += 2) {
-                double2 t = *reinterpret_cast<const double2*>(&s_val[w][st][e * R + r]);
-                v[r] = ok ? t.x : 0.0;
-                v[r + 1] = ok ? t.y : 0.0;
-            }
-            if (CPL == 2) {
-                double2 t = *reinterpret_cast<const double2*>(X + (int64_t)col * B + c);
-                x[0] = t.x;
-                x[CPL - 1] = t.y;
-            } else {
-                x[0] = X[(int64_t)col * B + c];
-            }
+        for (int u = 0; u < U; ++u) a[u] = __ldcs(aptr + (p + 4 * u) * 8);
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+        for (int u = 0; u < U; ++u) load_x(col[u], x[u]);
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) acc[r][k] += v[r] * x[k];
-        }
-        __syncwarp();
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a[u], x[u][j]);
     }
+    for (; p < p1; p += 4) {
+        const int col = __ldcs(bidx + p + t);
+        const double a = __ldcs(aptr + p * 8);
+        double x[NT];
+        load_x(col, x);
 #pragma unroll
-    for (int o = LPB; o < 32; o <<= 1)
+        for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, x[j]);
+    }
+    const int row = rb * 8 + g;
+    if (row >= n) return;
+    if (B >= 8) {
+        // tile j, fragment column cc in {2t, 2t+1} is the true column cc * NT + j: 2 NT consecutive columns from 2t NT
+        const int64_t o = (int64_t)row * B + 2 * t * NT;
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) acc[r][k] += __shfl_xor_sync(0xffffffffu, acc[r][k], o);
-    if (q == 0) {
+            for (int j = 0; j < NT; ++j) Y[o + i * NT + j] = acc[j][i] + eta * X[o + i * NT + j];
+    } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int row = rb * R + r;
-            if (row < n) {
-#pragma unroll
-                for (int k = 0; k < CPL; ++k)
-                    Y[(int64_t)row * B + c + k] = acc[r][k] + eta * X[(int64_t)row * B + c + k];
-            }
+        for (int i = 0; i < 2; ++i) {
+            const int cc = 2 * t + i;
+            if (cc < B) Y[(int64_t)row * B + cc] = acc[0][i] + eta * X[(int64_t)row * B + cc];
         }
     }
 }
 
-// the operator a Krylov routine works on: plain CSR (R = 1) or the row-blocked form (R = 2, 4, 8)
+// the operator a Krylov routine works on: plain CSR (R = 1) or the row-blocked form (R = 8)
 struct SparseOp {
     int R;                 // 1: CSR (ptr32, idx, val); > 1: row-blocked (ptr64, idx, val)
     const int* ptr32;
@@ -309,17 +304,16 @@ struct SparseOp {
     int n;
 };
 
-template <int R>
-static int bcsr_spmm_launch(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s) {
-    const int nrb = (A.n + R - 1) / R;
-    const int blocks = (nrb + 7) / 8;
+static int bcsr8_spmm_launch(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s) {
+    const int nrb = (A.n + 7) / 8;
+    const int blocks = (int)(((int64_t)nrb * 32 + 255) / 256);
     switch (B) {
-        case 1: bcsr_spmm_kernel<1, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 2: bcsr_spmm_kernel<2, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 4: bcsr_spmm_kernel<4, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 8: bcsr_spmm_kernel<8, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 16: bcsr_spmm_kernel<16, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 32: bcsr_spmm_kernel<32, R><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 1: bcsr8_spmm_dmma_kernel<1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 2: bcsr8_spmm_dmma_kernel<2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 4: bcsr8_spmm_dmma_kernel<4><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 8: bcsr8_spmm_dmma_kernel<8><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 16: bcsr8_spmm_dmma_kernel<16><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
+        case 32: bcsr8_spmm_dmma_kernel<32><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
         default: return -2;
     }
     return 0;
@@ -339,12 +333,8 @@ static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y
             case 32: csr_spmm_kernel<32><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
             default: return -2;
         }
-    } else if (A.R == 2) {
-        rc = bcsr_spmm_launch<2>(A, eta, X, B, Y, s);
-    } else if (A.R == 4) {
-        rc = bcsr_spmm_launch<4>(A, eta, X, B, Y, s);
     } else if (A.R == 8) {
-        rc = bcsr_spmm_launch<8>(A, eta, X, B, Y, s);
+        rc = bcsr8_spmm_launch(A, eta, X, B, Y, s);
     } else {
         return -3;
     }
@@ -406,8 +396,6 @@ static int bcsr_build_any(int64_t R, int pass, int64_t n, const int* order, cons
     cudaStream_t s = (cudaStream_t)stream;
     if (!indptr || !indices || n <= 0 || n > INT32_MAX || ((order == nullptr) != (inv_order == nullptr))) return -1;
     switch (R) {
-        case 2: return bcsr_build<2>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, s);
-        case 4: return bcsr_build<4>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, s);
         case 8: return bcsr_build<8>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, s);
         default: return -3;
     }
@@ -572,7 +560,7 @@ int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_
 
 int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                     const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream) {
-    if (!bptr || n <= 0 || n > INT32_MAX || (R != 2 && R != 4 && R != 8)) return -1;
+    if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
     return lanczos_run(bcsr_op(R, bptr, bidx, bvals, n), eta, V, B, m, alpha_dev, beta_dev, ws, stream);
 }
 
@@ -584,7 +572,7 @@ int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64
 
 int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta, double* R0,
                      double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream) {
-    if (!bptr || n <= 0 || n > INT32_MAX || (R != 2 && R != 4 && R != 8)) return -1;
+    if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
     return cg_run(bcsr_op(R, bptr, bidx, bvals, n), eta, R0, X, B, tol, maxiter, iters_host, ws, stream);
 }
 

@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=4)
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8)
 
 
 def _p(t):
@@ -152,15 +152,15 @@ class SparseEngine(object):
         # multi-GPU: (rank, world) -> this engine evaluates its slice of every round of probes; see _run_estimator
         self.probe_range = probe_range
         # Internally the operator works on the ROW-BLOCKED form of the symmetrically permuted matrix P K P^T (rows in
-        # the generator's Z-order): block_rows consecutive rows share one column list, so one gathered row of the probe
-        # block serves block_rows rows of K. Results do not depend on the permutation: probes are hashed with ORIGINAL
+        # the generator's Z-order): 8 consecutive rows share one column list, so one gathered row of the probe block
+        # serves 8 rows of K and four such block-columns are one DMMA.8x8x4 (csrc/gp_sparse_la.cu). Results do not depend on the permutation: probes are hashed with ORIGINAL
         # row ids. block_rows = 1 (or a K without an order, e.g. from SciPy) keeps plain CSR in the original order.
         self.order = self.inv_order = None
         self.R = 1
         self.blocked = None
-        R = int(self.opt.get('block_rows', 4))
-        if R not in (1, 2, 4, 8):
-            raise ValueError('block_rows should be 1, 2, 4 or 8.')
+        R = int(self.opt.get('block_rows', 8))
+        if R not in (1, 8):
+            raise ValueError('block_rows should be 8 (row-blocked, FP64 tensor-core SpMM) or 1 (plain CSR).')
         if K.order is not None and R > 1:
             self._build_blocked(K, R)
 

@@ -143,8 +143,8 @@ int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64
  * row = row_map[i] when row_map (device int32, n) is given (internally permuted operators), else i. */
 int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map,
                   void* stream);
-/* Row-blocked form of a (symmetrically permuted) CSR matrix: R (2, 4 or 8) consecutive rows share one list of
- * block-columns (R x 1 blocks, zero filled). New row r = old row order[r], new column = inv_order[old column] (both
+/* Row-blocked form of a (symmetrically permuted) CSR matrix: R = 8 consecutive rows share one list of block-columns
+ * (8 x 1 blocks, zero filled; the list is padded with zero blocks to a multiple of 4 = one DMMA.8x8x4 k-step). New row r = old row order[r], new column = inv_order[old column] (both
  * NULL: no permutation); the source rows must be sorted. With a spatially local order (gp_spatial_keys) neighbouring
  * rows have nearly the same pattern: one gathered row of X then serves R rows of K and the index is amortised.
  *   gp_bcsr_count: nblk[rb] = number of block-columns of row block rb (ceil(n/R) entries); the caller's exclusive
@@ -155,7 +155,7 @@ int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, 
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                  const double* data, const double* ddata, const int64_t* bptr, int* bidx, double* bvals, double* bdvals,
                  void* stream);
-/* Y = (K + eta I) X on the row-blocked operator */
+/* Y = (K + eta I) X on the row-blocked operator (FP64 tensor-core MMAs: 4 block-columns x 8 rows x 8 columns) */
 int gp_bcsr_spmm(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                  const double* X, int64_t B, double* Y, void* stream);
 /* workspace for gp_col_dot / gp_lanczos / gp_cg_solve */
