@@ -247,6 +247,59 @@ __global__ void place_extras_kernel(int nextra, const int* __restrict__ ei, cons
     if (ddata) ddata[o] = edv[t];
 }
 
+// One WARP per row (rows of <= WSORT_CAP entries, i.e. practically all of them): bitonic sort of packed (col, position)
+// words in shared memory with warp-level barriers only, then the values are permuted through their staged copies.
+// Longer rows are flagged and left to the CTA-wide kernel below.
+constexpr int WSORT_CAP = 512;
+__global__ void __launch_bounds__(128)
+sort_rows_warp_kernel(int n, const int* __restrict__ indptr, int* indices, double* data, double* ddata, int* has_long) {
+    __shared__ unsigned long long sk[4][WSORT_CAP];
+    __shared__ double sv[4][WSORT_CAP];
+    __shared__ double sd[4][WSORT_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long* k = sk[w];
+    double* v = sv[w];
+    double* dv = sd[w];
+    for (int row = blockIdx.x * 4 + w; row < n; row += gridDim.x * 4) {
+        const int s0 = indptr[row], len = indptr[row + 1] - s0;
+        if (len <= 1) continue;
+        if (len > WSORT_CAP) { if (lane == 0) atomicExch(has_long, 1); continue; }
+        int m = 32;
+        while (m < len) m <<= 1;
+        bool sorted = true;
+        for (int t = lane; t < m; t += 32) {
+            const int key = (t < len) ? indices[s0 + t] : 0x7fffffff;
+            if (t + 1 < len && indices[s0 + t + 1] < key) sorted = false;
+            k[t] = ((unsigned long long)(unsigned)key << 32) | (unsigned)t;
+            if (t < len) {
+                v[t] = data[s0 + t];
+                if (ddata) dv[t] = ddata[s0 + t];
+            }
+        }
+        if (__all_sync(0xffffffffu, sorted)) { __syncwarp(); continue; }
+        __syncwarp();
+        for (int kk = 2; kk <= m; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < (m >> 1); i += 32) {
+                    const int t = 2 * i - (i & (j - 1));      // lower index of the pair (bit j clear)
+                    const int p = t + j;
+                    const bool up = ((t & kk) == 0);
+                    const unsigned long long a = k[t], b = k[p];
+                    if ((a > b) == up) { k[t] = b; k[p] = a; }
+                }
+                __syncwarp();
+            }
+        for (int t = lane; t < len; t += 32) {
+            const unsigned long long e = k[t];
+            const int pos = (int)(e & 0xffffffffu);
+            indices[s0 + t] = (int)(e >> 32);
+            data[s0 + t] = v[pos];
+            if (ddata) ddata[s0 + t] = dv[pos];
+        }
+        __syncwarp();
+    }
+}
+
 // one CTA per row (grid-stride): bitonic sort of (col, value[, dvalue]) by col in shared memory
 __global__ void __launch_bounds__(256)
 sort_rows_kernel(int n, const int* __restrict__ indptr, int* indices, double* data, double* ddata, int* overflow) {
@@ -255,7 +308,7 @@ sort_rows_kernel(int n, const int* __restrict__ indptr, int* indices, double* da
     __shared__ double dvals[SORT_CAP];
     for (int row = blockIdx.x; row < n; row += gridDim.x) {
         const int s0 = indptr[row], len = indptr[row + 1] - s0;
-        if (len <= 1) continue;
+        if (len <= WSORT_CAP) continue;      // sorted by sort_rows_warp_kernel
         if (len > SORT_CAP) { if (threadIdx.x == 0) atomicExch(overflow, row + 1); continue; }
         int m = 1;
         while (m < len) m <<= 1;
@@ -599,13 +652,20 @@ int gp_matern_sparse_fill(const double* points, const double* points_host, int64
                                                              indices_dev, data_dev, ddata_dev);
         GP_COUNT(1);
     }
-    sort_rows_kernel<<<148 * 8, 256, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow);
+    sort_rows_warp_kernel<<<148 * 4, 128, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow + 1);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
-    int ovf = 0;
-    GP_CUDA_CHECK(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int ovf[2] = {0, 0};
+    GP_CUDA_CHECK(cudaMemcpyAsync(ovf, w.overflow, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (ovf) return -23;  // a row longer than SORT_CAP
+    if (ovf[1]) {   // rows longer than WSORT_CAP exist: CTA-wide sort for those
+        sort_rows_kernel<<<148 * 8, 256, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow);
+        GP_COUNT(1);
+        GP_LAUNCH_CHECK();
+        GP_CUDA_CHECK(cudaMemcpyAsync(ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    if (ovf[0]) return -23;  // a row longer than SORT_CAP
     return 0;
 }
 

@@ -14,7 +14,7 @@ constexpr int RED_PARTS = 592;  // CTAs of the column reductions (4 per SM)
 template <int B>
 __global__ void __launch_bounds__(256)
 csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ data, int n,
-                double eta, const double* __restrict__ X, double* __restrict__ Y) {
+                double eta, const double* __restrict__ X, const double* __restrict__ scale, double* __restrict__ Y) {
     constexpr int NQ = 32 / B;
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -25,11 +25,12 @@ csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
     for (int p = s0 + q; p < s1; p += NQ) acc += data[p] * X[(int64_t)indices[p] * B + c];
 #pragma unroll
     for (int o = B; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (q == 0) Y[(int64_t)row * B + c] = acc + eta * X[(int64_t)row * B + c];
+    if (q == 0) Y[(int64_t)row * B + c] = (acc + eta * X[(int64_t)row * B + c]) * (scale ? scale[c] : 1.0);
 }
 
 // ---- column reductions: partial[cta][c] = sum over the CTA's elements of column c --------------------------------
-// mode 0: x*y   mode 1: (lanczos) w -= a q + b qprev, accumulate w*w   mode 2: (cg) x += a p, r -= a ap, accumulate r*r
+// mode 0: x*y   mode 1: (lanczos) u_next = w - a u - b u_prev written over u_prev, accumulate u_next^2
+// mode 2: (cg) x += a p, r -= a ap, accumulate r*r
 template <int MODE>
 __global__ void __launch_bounds__(256)
 col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const double* __restrict__ Y, double* W,
@@ -43,8 +44,8 @@ col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const doubl
         if (MODE == 0) {
             acc += X[idx] * Y[idx];
         } else if (MODE == 1) {
-            double w = W[idx] - ac * X[idx] - bc * Y[idx];   // X = q_j, Y = q_{j-1}
-            W[idx] = w;
+            double w = W[idx] - ac * X[idx] - bc * Z[idx];   // X = u_j, Z = u_{j-1} (overwritten by u_{j+1})
+            Z[idx] = w;
             acc += w * w;
         } else {
             Z[idx] += ac * X[idx];                            // Z = solution, X = p
@@ -63,28 +64,58 @@ col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const doubl
     }
 }
 
-// final stage + the scalar recurrences, one thread per column (fixed order -> reproducible)
+// first stage for long partial lists (the SpMM epilogue leaves one row per CTA): CTA b sums rows [256 b, 256 b + 256)
+__global__ void __launch_bounds__(256)
+col_partial_reduce_kernel(const double* __restrict__ partial, int nparts, int B, double* __restrict__ out) {
+    __shared__ double red[256];
+    const int c = threadIdx.x % B, sl = threadIdx.x / B, nsl = 256 / B;
+    const int i0 = blockIdx.x * 256, i1 = min(nparts, i0 + 256);
+    double s = 0.0;
+#pragma unroll 4
+    for (int i = i0 + sl; i < i1; i += nsl) s += partial[(int64_t)i * B + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x >= B) return;
+    s = 0.0;
+    for (int k = 0; k < nsl; ++k) s += red[k * B + c];
+    out[(int64_t)blockIdx.x * B + c] = s;
+}
+
+// final stage + the scalar recurrences: 256 threads sum the partials in a fixed order (reproducible), then one thread
+// per column applies the recurrence.
 // op 0: out = sum
-// op 1 (lanczos alpha): alpha[c] = sum; store into coef row
-// op 2 (lanczos beta):  beta[c] = sqrt(sum); store; inv[c] = beta > tiny ? 1/beta : 0
+// op 1 (lanczos alpha): alpha = s_cur * sum -> out; s2 = a1 = alpha * s_cur; s3 = b1 = beta_prev * s_prev
+//                       (sc layout, 32 doubles each: s1 = {s_cur, s_prev, beta_prev} at s1, s1+32, s1+64)
+// op 2 (lanczos beta):  beta = sqrt(sum) -> out; beta_prev = beta; s_prev = s_cur; s_cur = beta > tiny ? 1/beta : 0
 // op 3 (cg pAp):        alpha[c] = active ? rr/sum : 0
 // op 4 (cg rr_new):     beta[c] = active ? sum/rr : 0; rr = sum; active &= rr > tol2*bb
-__global__ void col_final_kernel(const double* partial, int nparts, int B, int op, double* out, double* s1, double* s2,
-                                 double* s3, double tol2) {
-    int c = threadIdx.x;
-    if (c >= B) return;
+__global__ void __launch_bounds__(256)
+col_final_kernel(const double* __restrict__ partial, int nparts, int B, int op, double* out, double* s1, double* s2,
+                 double* s3, double tol2) {
+    __shared__ double red[256];
+    const int c = threadIdx.x % B, sl = threadIdx.x / B, nsl = 256 / B;
     double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += partial[(int64_t)i * B + c];
+    for (int i = sl; i < nparts; i += nsl) s += partial[(int64_t)i * B + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x >= B) return;
+    s = 0.0;
+    for (int k = 0; k < nsl; ++k) s += red[k * B + c];
     if (op == 0) {
         out[c] = s;
     } else if (op == 1) {
-        out[c] = s;
-        s1[c] = s;
+        double* s_cur = s1; double* s_prev = s1 + 32; double* beta_prev = s1 + 64;
+        const double al = s_cur[c] * s;
+        out[c] = al;
+        s2[c] = al * s_cur[c];
+        s3[c] = beta_prev[c] * s_prev[c];
     } else if (op == 2) {
-        double bt = sqrt(s);
+        double* s_cur = s1; double* s_prev = s1 + 32; double* beta_prev = s1 + 64;
+        const double bt = sqrt(s);
         out[c] = bt;
-        s1[c] = bt;
-        s2[c] = (bt > 1e-300) ? 1.0 / bt : 0.0;
+        beta_prev[c] = bt;
+        s_prev[c] = s_cur[c];
+        s_cur[c] = (bt > 1e-300) ? 1.0 / bt : 0.0;
     } else if (op == 3) {
         // s1 = rr, s2 = active flag (1/0), s3 = breakdown flag, out = alpha
         if (s2[c] != 0.0 && !(s > 0.0)) { s3[0] = 1.0; s2[c] = 0.0; }   // p^T A p <= 0: A is not positive definite
@@ -96,13 +127,6 @@ __global__ void col_final_kernel(const double* partial, int nparts, int B, int o
         s1[c] = s;
         if (!(s > tol2 * s3[c])) s2[c] = 0.0;
     }
-}
-
-// q_next = w * inv_beta (per column); also used for the initial normalisation
-__global__ void col_scale_kernel(int64_t total, int B, const double* __restrict__ W, const double* __restrict__ inv, double* Q) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    Q[idx] = W[idx] * inv[idx % B];
 }
 
 // p = r + beta p
@@ -223,16 +247,20 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
 // the 2 / 4 MMAs of a step share A; their column sets are interleaved (tile j owns columns j, j + NT, ...) so that a
 // lane's B operands are NT consecutive doubles of one X row (one 16-byte load for B = 16) and its results are 2 NT
 // consecutive columns of one Y row. Index and values are streamed past L1 (ld.global.cs): L1 is kept for X.
-template <int B>
+// Epilogue: Y = scale[c] (A X + eta X) (scale optional) and, with DOT, partial[cta][c] = sum over the CTA's 64 rows
+// of X[i][c] Y[i][c] (fixed order) - the Lanczos alpha / CG p^T A p reduction without another pass over the vectors.
+template <int B, bool DOT>
 __global__ void __launch_bounds__(256)
 bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
-                       double eta, const double* __restrict__ X, double* __restrict__ Y) {
+                       double eta, const double* __restrict__ X, const double* __restrict__ scale, double* __restrict__ Y,
+                       double* __restrict__ partial) {
     constexpr int NT = (B >= 8) ? B / 8 : 1;   // 8-column MMA tiles per step
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;     // DMMA.8x8x4 fragments: A[g][t], B[t][g], D[g][2t .. 2t+1]
     const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (rb * 8 >= n) return;
-    const int64_t p0 = bptr[rb], p1 = bptr[rb + 1];   // p1 - p0 is a multiple of 4
+    const bool live = rb * 8 < n;
+    if (!DOT && !live) return;
+    const int64_t p0 = live ? bptr[rb] : 0, p1 = live ? bptr[rb + 1] : 0;   // p1 - p0 is a multiple of 4
     double acc[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -277,19 +305,42 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
         for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, x[j]);
     }
     const int row = rb * 8 + g;
-    if (row >= n) return;
-    if (B >= 8) {
-        // tile j, fragment column cc in {2t, 2t+1} is the true column cc * NT + j: 2 NT consecutive columns from 2t NT
-        const int64_t o = (int64_t)row * B + 2 * t * NT;
+    constexpr int NC = (B >= 8) ? 2 * NT : 2;               // result columns of this lane, from column c0
+    const int c0 = (B >= 8) ? 2 * t * NT : 2 * t;
+    double dsum[NC];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < NC; ++k) dsum[k] = 0.0;
+    if (live && row < n) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) Y[o + i * NT + j] = acc[j][i] + eta * X[o + i * NT + j];
-    } else {
+        for (int k = 0; k < NC; ++k) {
+            // tile j, fragment column cc in {2t, 2t+1} is the true column cc * NT + j: k = i * NT + j
+            const int i = (B >= 8) ? k / NT : k, j = (B >= 8) ? k % NT : 0;
+            if (B >= 8 || c0 + k < B) {
+                const int64_t o = (int64_t)row * B + c0 + k;
+                const double xv = X[o];
+                double y = acc[j][i] + eta * xv;
+                if (scale) y *= scale[c0 + k];
+                Y[o] = y;
+                if (DOT) dsum[k] = xv * y;
+            }
+        }
+    }
+    if (DOT) {
+        __shared__ double red[8][32];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int cc = 2 * t + i;
-            if (cc < B) Y[(int64_t)row * B + cc] = acc[0][i] + eta * X[(int64_t)row * B + cc];
+        for (int k = 0; k < NC; ++k) {
+            double v = dsum[k];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0 && (B >= 8 || c0 + k < B)) red[threadIdx.x >> 5][c0 + k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < B) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+            partial[(int64_t)blockIdx.x * B + threadIdx.x] = v;
         }
     }
 }
@@ -304,44 +355,70 @@ struct SparseOp {
     int n;
 };
 
-static int bcsr8_spmm_launch(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s) {
-    const int nrb = (A.n + 7) / 8;
-    const int blocks = (int)(((int64_t)nrb * 32 + 255) / 256);
-    switch (B) {
-        case 1: bcsr8_spmm_dmma_kernel<1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 2: bcsr8_spmm_dmma_kernel<2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 4: bcsr8_spmm_dmma_kernel<4><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 8: bcsr8_spmm_dmma_kernel<8><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 16: bcsr8_spmm_dmma_kernel<16><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        case 32: bcsr8_spmm_dmma_kernel<32><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, Y); break;
-        default: return -2;
-    }
-    return 0;
+static int bcsr8_parts(int n) { return (((n + 7) / 8) + 7) / 8; }   // CTAs of the row-blocked SpMM = dot partials
+
+template <int B>
+static void bcsr8_spmm_launch_b(const SparseOp& A, double eta, const double* X, const double* scale, double* Y,
+                                double* partial, cudaStream_t s) {
+    const int blocks = bcsr8_parts(A.n);
+    if (partial)
+        bcsr8_spmm_dmma_kernel<B, true><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
+    else
+        bcsr8_spmm_dmma_kernel<B, false><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
 }
 
-static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s) {
+// Y = scale (.) ((A + eta I) X); with `partial` also the per-column partial sums of X (.) Y: *nparts rows of B doubles
+static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s,
+                const double* scale = nullptr, double* partial = nullptr, int* nparts = nullptr) {
     const int n = A.n;
-    int rc = 0;
     if (A.R == 1) {
         int blocks = (int)(((int64_t)n * 32 + 255) / 256);
         switch (B) {
-            case 1: csr_spmm_kernel<1><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
-            case 2: csr_spmm_kernel<2><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
-            case 4: csr_spmm_kernel<4><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
-            case 8: csr_spmm_kernel<8><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
-            case 16: csr_spmm_kernel<16><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
-            case 32: csr_spmm_kernel<32><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, Y); break;
+            case 1: csr_spmm_kernel<1><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
+            case 2: csr_spmm_kernel<2><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
+            case 4: csr_spmm_kernel<4><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
+            case 8: csr_spmm_kernel<8><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
+            case 16: csr_spmm_kernel<16><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
+            case 32: csr_spmm_kernel<32><<<blocks, 256, 0, s>>>(A.ptr32, A.idx, A.val, n, eta, X, scale, Y); break;
             default: return -2;
         }
+        GP_COUNT(1);
+        if (partial) {   // plain CSR keeps the separate reduction pass
+            col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>((int64_t)n * B, B, X, Y, nullptr, nullptr, nullptr, nullptr, partial);
+            *nparts = RED_PARTS;
+            GP_COUNT(1);
+        }
     } else if (A.R == 8) {
-        rc = bcsr8_spmm_launch(A, eta, X, B, Y, s);
+        switch (B) {
+            case 1: bcsr8_spmm_launch_b<1>(A, eta, X, scale, Y, partial, s); break;
+            case 2: bcsr8_spmm_launch_b<2>(A, eta, X, scale, Y, partial, s); break;
+            case 4: bcsr8_spmm_launch_b<4>(A, eta, X, scale, Y, partial, s); break;
+            case 8: bcsr8_spmm_launch_b<8>(A, eta, X, scale, Y, partial, s); break;
+            case 16: bcsr8_spmm_launch_b<16>(A, eta, X, scale, Y, partial, s); break;
+            case 32: bcsr8_spmm_launch_b<32>(A, eta, X, scale, Y, partial, s); break;
+            default: return -2;
+        }
+        if (partial) *nparts = bcsr8_parts(n);
+        GP_COUNT(1);
     } else {
         return -3;
     }
-    if (rc) return rc;
-    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
+}
+
+// partial (nparts x B) -> scalar recurrence `op`; long lists go through col_partial_reduce_kernel into `scratch`
+static void col_final(const double* partial, int nparts, int B, int op, double* out, double* s1, double* s2, double* s3,
+                      double tol2, double* scratch, cudaStream_t s) {
+    if (nparts > 1024) {
+        const int nb = (nparts + 255) / 256;
+        col_partial_reduce_kernel<<<nb, 256, 0, s>>>(partial, nparts, B, scratch);
+        col_final_kernel<<<1, 256, 0, s>>>(scratch, nb, B, op, out, s1, s2, s3, tol2);
+        GP_COUNT(2);
+    } else {
+        col_final_kernel<<<1, 256, 0, s>>>(partial, nparts, B, op, out, s1, s2, s3, tol2);
+        GP_COUNT(1);
+    }
 }
 
 static SparseOp csr_op(const int* indptr, const int* indices, const double* data, int64_t n) {
@@ -425,17 +502,27 @@ int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_
     return 0;
 }
 
-// out[c] = sum_i X[i][c] * Y[i][c]
-int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B) {
-    return (int64_t)(4 * al256(sizeof(double) * n * B) + al256(sizeof(double) * RED_PARTS * 32) + 16 * al256(sizeof(double) * 32));
+static size_t partial_rows(int64_t n) {
+    int64_t parts = bcsr8_parts((int)n);
+    return (size_t)(parts < RED_PARTS ? RED_PARTS : parts);
+}
+// reduction partials: the main list followed by the first-stage scratch (1/256 of it)
+static size_t partial_bytes(int64_t n) {
+    return al256(sizeof(double) * partial_rows(n) * 32) + al256(sizeof(double) * (partial_rows(n) / 256 + 1) * 32);
 }
 
+// workspace: 4 vectors of n x B, the reduction partials, 16 x 32 scalars
+int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B) {
+    return (int64_t)(4 * al256(sizeof(double) * n * B) + partial_bytes(n) + 16 * al256(sizeof(double) * 32));
+}
+
+// out[c] = sum_i X[i][c] * Y[i][c]
 int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream) {
     if (!X || !Y || !out_dev || !ws || B <= 0 || B > 32 || (32 % B)) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     double* partial = (double*)ws;
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(n * B, (int)B, X, Y, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, (int)B, 0, out_dev, nullptr, nullptr, nullptr, 0.0);
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, (int)B, 0, out_dev, nullptr, nullptr, nullptr, 0.0);
     GP_COUNT(2);
     GP_LAUNCH_CHECK();
     return 0;
@@ -443,8 +530,12 @@ int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* o
 
 }  // extern "C"
 
-// m Lanczos steps of A = K + eta I started from the columns of V (normalised internally).
+// m Lanczos steps of A = K + eta I started from the columns of V.
 // alpha_dev, beta_dev: (m x B) row-major; beta[j] is the norm of the (j+1)-th unnormalised vector.
+// The Lanczos vectors are kept UNNORMALISED (u_j = beta_{j-1} q_j) with their scales s_j = 1 / ||u_j|| on the device:
+//   W = s_j (A u_j) (scale applied in the SpMM epilogue, which also reduces u_j . W), alpha_j = s_j (u_j . W),
+//   u_{j+1} = W - (alpha_j s_j) u_j - (beta_{j-1} s_{j-1}) u_{j-1}  (written over u_{j-1}),  beta_j = ||u_{j+1}||
+// so a step is two passes over the vectors (the SpMM and one fused update) and four launches.
 static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B, int64_t m, double* alpha_dev,
                        double* beta_dev, void* ws, void* stream) {
     const int64_t n = A.n;
@@ -455,35 +546,35 @@ static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B
     const int64_t total = n * B;
     char* base = (char*)ws;
     size_t vb = al256(sizeof(double) * total);
-    double* Q0 = (double*)base;
-    double* Q1 = (double*)(base + vb);
+    double* U0 = (double*)base;
+    double* U1 = (double*)(base + vb);
     double* W = (double*)(base + 2 * vb);
     double* partial = (double*)(base + 4 * vb);
-    double* sc = (double*)(base + 4 * vb + al256(sizeof(double) * RED_PARTS * 32));
-    double* a = sc;            // current alpha
-    double* bprev = sc + 32;   // beta_{j-1}
-    double* inv = sc + 64;     // 1 / beta
-    double* tmp = sc + 96;
-    const unsigned eb = (unsigned)((total + 255) / 256);
-    // q_0 = v / ||v||
+    double* scratch = partial + partial_rows(n) * 32;
+    double* sc = (double*)(base + 4 * vb + partial_bytes(n));
+    double* st = sc;           // s_cur, s_prev (+32), beta_prev (+64)
+    double* a1 = sc + 96;      // alpha_j s_j
+    double* b1 = sc + 128;     // beta_{j-1} s_{j-1}
+    double* tmp = sc + 160;
+    // u_0 = v, s_0 = 1 / ||v||, u_{-1} = 0
+    GP_CUDA_CHECK(cudaMemcpyAsync(U0, V, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
+    GP_CUDA_CHECK(cudaMemsetAsync(U1, 0, sizeof(double) * total, s));
+    GP_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(double) * 96, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, V, V, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 2, tmp, tmp, inv, nullptr, 0.0);
-    col_scale_kernel<<<eb, 256, 0, s>>>(total, Bc, V, inv, Q0);
-    GP_CUDA_CHECK(cudaMemsetAsync(Q1, 0, sizeof(double) * total, s));
-    GP_CUDA_CHECK(cudaMemsetAsync(bprev, 0, sizeof(double) * 32, s));
-    GP_COUNT(3);
-    double* q = Q0;
-    double* qprev = Q1;
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, tmp, st, nullptr, nullptr, 0.0);
+    GP_CUDA_CHECK(cudaMemsetAsync(st + 32, 0, sizeof(double) * 64, s));    // s_prev = beta_prev = 0 for the first step
+    GP_COUNT(2);
+    double* u = U0;
+    double* uprev = U1;
     for (int64_t j = 0; j < m; ++j) {
-        int rc = spmm(A, eta, q, Bc, W, s);
+        int nparts = 0;
+        int rc = spmm(A, eta, u, Bc, W, s, st, partial, &nparts);
         if (rc) return rc;
-        col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, q, W, nullptr, nullptr, nullptr, nullptr, partial);
-        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 1, alpha_dev + j * B, a, nullptr, nullptr, 0.0);
-        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, q, qprev, W, nullptr, a, bprev, partial);
-        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 2, beta_dev + j * B, bprev, inv, nullptr, 0.0);
-        col_scale_kernel<<<eb, 256, 0, s>>>(total, Bc, W, inv, qprev);  // q_{j+1} overwrites q_{j-1}
-        GP_COUNT(5);
-        double* t = q; q = qprev; qprev = t;
+        col_final(partial, nparts, Bc, 1, alpha_dev + j * B, st, a1, b1, 0.0, scratch, s);
+        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, u, nullptr, W, uprev, a1, b1, partial);
+        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, beta_dev + j * B, st, nullptr, nullptr, 0.0);
+        GP_COUNT(2);
+        double* t = u; u = uprev; uprev = t;
     }
     GP_LAUNCH_CHECK();
     return 0;
@@ -505,7 +596,8 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     double* Pd = (double*)base;
     double* AP = (double*)(base + vb);
     double* partial = (double*)(base + 4 * vb);
-    double* sc = (double*)(base + 4 * vb + al256(sizeof(double) * RED_PARTS * 32));
+    double* scratch = partial + partial_rows(n) * 32;
+    double* sc = (double*)(base + 4 * vb + partial_bytes(n));
     double *rr = sc, *active = sc + 32, *bb = sc + 64, *alpha = sc + 96, *beta = sc + 128, *flag = sc + 160;
     const unsigned eb = (unsigned)((total + 255) / 256);
     const double tol2 = tol * tol;
@@ -513,7 +605,7 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     GP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(double) * 32, s));
     GP_CUDA_CHECK(cudaMemcpyAsync(Pd, R0, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, R0, R0, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 0, rr, nullptr, nullptr, nullptr, 0.0);
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 0, rr, nullptr, nullptr, nullptr, 0.0);
     GP_CUDA_CHECK(cudaMemcpyAsync(bb, rr, sizeof(double) * 32, cudaMemcpyDeviceToDevice, s));
     double ones[32], act[32];
     GP_CUDA_CHECK(cudaMemcpyAsync(ones, rr, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
@@ -525,14 +617,14 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     bool converged = false;
     const int check_every = 8;
     while (it < maxiter) {
-        int rc = spmm(A, eta, Pd, Bc, AP, s);
+        int nparts = 0;
+        int rc = spmm(A, eta, Pd, Bc, AP, s, nullptr, partial, &nparts);
         if (rc) return rc;
-        col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, Pd, AP, nullptr, nullptr, nullptr, nullptr, partial);
-        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 3, alpha, rr, active, flag, 0.0);
+        col_final(partial, nparts, Bc, 3, alpha, rr, active, flag, 0.0, scratch, s);
         col_fused_kernel<2><<<RED_PARTS, 256, 0, s>>>(total, Bc, Pd, AP, R0, X, alpha, nullptr, partial);
-        col_final_kernel<<<1, 32, 0, s>>>(partial, RED_PARTS, Bc, 4, beta, rr, active, bb, tol2);
+        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 4, beta, rr, active, bb, tol2);
         cg_direction_kernel<<<eb, 256, 0, s>>>(total, Bc, R0, beta, Pd);
-        GP_COUNT(5);
+        GP_COUNT(3);
         ++it;
         if (it % check_every == 0 || it == maxiter) {
             double brk = 0.0;

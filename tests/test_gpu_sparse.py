@@ -51,7 +51,8 @@ def test_sparse_edge_cases(gp):
     from oracle import matern
     # 1-D and 3-D points, anisotropic scale, tiny n (single cell), explicit threshold
     for (n, d, scale, nu, dens) in [(300, 1, [0.02], 0.5, 0.05), (500, 3, [0.2, 0.3, 0.25], 1.5, 0.02),
-                                    (64, 2, [0.5, 0.5], 2.5, 0.3), (700, 2, [0.02, 0.05], 1.5, 0.02)]:
+                                    (64, 2, [0.5, 0.5], 2.5, 0.3), (700, 2, [0.02, 0.05], 1.5, 0.02),
+                                    (2400, 2, [0.3, 0.3], 0.5, 0.9)]:     # rows of > 512 entries: CTA-wide sort path
         numpy.random.seed(n)
         pts = numpy.random.rand(n, d)
         S = gp.generate_correlation(pts, numpy.array(scale), nu, sparse=True, density=dens)
