@@ -163,31 +163,21 @@ __device__ __forceinline__ int find_col(const int* __restrict__ row, int len, in
     return (lo < len && row[lo] == c) ? lo : -1;
 }
 
-// one warp per row block. PASS 0: nblk[rb] = number of distinct columns rounded up to a multiple of 4 (the k extent of
-// one DMMA); PASS 1: fill (bidx, bvals[, bdvals]); padding block-columns repeat the block's first column with zeros.
-// new row r = old row order[r]; new column = inv_order[old column]; the source CSR must have sorted rows.
+// One warp per row block. PASS 0: nblk[rb] = number of distinct columns rounded up to a multiple of 4 (the k extent of
+// one DMMA); PASS 1: fill (bidx, bvals[, bdvals]; the value arrays are zeroed by the caller); padding block-columns
+// repeat the block's first column with zeros. New row r = old row order[r]; new column = inv_order[old column]; the
+// source CSR must have sorted rows.
+// Columns get their block-column slot in order of first appearance (row 0's entries, then the new ones of row 1, ...).
+// Fast path: a per-warp open-addressing hash table (column -> slot) in shared memory, one probe sequence per entry.
+// If a block has more than HMAX distinct columns the warp redoes it with binary searches in the (sorted) source rows:
+// the same layout, so both paths write identical output.
+constexpr int HCAP = 2048, HMAX = 1536;
+
 template <int R, int PASS>
-__global__ void __launch_bounds__(256)
-bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
-                  const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
-                  int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals) {
-    const int lane = threadIdx.x & 31;
-    const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (rb * R >= n) return;
-    int s[R], len[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        int r = rb * R + k;
-        if (r < n) {
-            int o = order ? order[r] : r;
-            s[k] = indptr[o];
-            len[k] = indptr[o + 1] - s[k];
-        } else {
-            s[k] = 0;
-            len[k] = 0;
-        }
-    }
-    const int64_t base = (PASS == 1) ? bptr[rb] : 0;
+__device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s, const int* len, const int* __restrict__ inv_order,
+                                                 const int* __restrict__ indices, const double* __restrict__ data,
+                                                 const double* __restrict__ ddata, int64_t base, int* bidx, double* bvals,
+                                                 double* bdvals) {
     int running = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -225,6 +215,87 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
             }
             running += __popc(m);
         }
+    }
+    return running;
+}
+
+template <int R, int PASS>
+__global__ void __launch_bounds__(128)
+bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
+                  const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
+                  int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals) {
+    __shared__ int hkey[4][HCAP];
+    __shared__ unsigned short hslot[4][HCAP];      // slots < HMAX + 32
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rb * R >= n) return;
+    int* hk = hkey[w];
+    unsigned short* hs = hslot[w];
+    for (int i = lane; i < HCAP; i += 32) hk[i] = -1;
+    int s[R], len[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        int r = rb * R + k;
+        if (r < n) {
+            int o = order ? order[r] : r;
+            s[k] = indptr[o];
+            len[k] = indptr[o + 1] - s[k];
+        } else {
+            s[k] = 0;
+            len[k] = 0;
+        }
+    }
+    const int64_t base = (PASS == 1) ? bptr[rb] : 0;
+    __syncwarp();
+    int running = 0;
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        for (int t0 = 0; t0 < len[k] && !overflow; t0 += 32) {
+            const int t = t0 + lane;
+            const bool valid = t < len[k];
+            const int c = valid ? indices[s[k] + t] : -1;
+            int slot = -1;
+            bool isnew = false;
+            unsigned h = ((unsigned)c * 2654435761u) >> 21;      // 11 bits = HCAP
+            if (valid) {
+                while (true) {
+                    const int kk = hk[h];
+                    if (kk == c) { slot = hs[h]; break; }
+                    if (kk == -1) { isnew = true; break; }
+                    h = (h + 1) & (HCAP - 1);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, isnew);
+            if (isnew) {
+                slot = running + __popc(m & ((1u << lane) - 1u));
+                while (true) {      // claim the first free cell from h on (other lanes insert other columns concurrently)
+                    const int old = atomicCAS(&hk[h], -1, c);
+                    if (old == -1) { hs[h] = (unsigned short)slot; break; }
+                    h = (h + 1) & (HCAP - 1);
+                }
+            }
+            running += __popc(m);
+            __syncwarp();
+            if (running > HMAX) overflow = true;
+            if (PASS == 1 && valid && !overflow) {
+                const int64_t o = (base + slot) * R + k;
+                bvals[o] = data[s[k] + t];
+                if (ddata) bdvals[o] = ddata[s[k] + t];
+                if (isnew) bidx[base + slot] = inv_order ? inv_order[c] : c;
+            }
+        }
+    }
+    if (overflow) {
+        if (PASS == 1) {      // clear what the hash path wrote, then redo the block by searching
+            const int64_t cnt = (bptr[rb + 1] - base) * R;
+            for (int64_t i = lane; i < cnt; i += 32) {
+                bvals[base * R + i] = 0.0;
+                if (ddata) bdvals[base * R + i] = 0.0;
+            }
+            __syncwarp();
+        }
+        running = bcsr_block_search<R, PASS>(lane, rb, s, len, inv_order, indices, data, ddata, base, bidx, bvals, bdvals);
     }
     const int padded = (running + 3) & ~3;
     if (PASS == 0 && lane == 0) nblk[rb] = padded;
@@ -457,11 +528,11 @@ static int bcsr_build(int pass, int n, const int* order, const int* inv_order, c
                       const double* data, const double* ddata, int* nblk, const int64_t* bptr, int* bidx, double* bvals,
                       double* bdvals, cudaStream_t s) {
     const int nrb = (n + R - 1) / R;
-    const unsigned blocks = (unsigned)(((int64_t)nrb * 32 + 255) / 256);
+    const unsigned blocks = (unsigned)(((int64_t)nrb * 32 + 127) / 128);
     if (pass == 0)
-        bcsr_build_kernel<R, 0><<<blocks, 256, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
+        bcsr_build_kernel<R, 0><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
     else
-        bcsr_build_kernel<R, 1><<<blocks, 256, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
+        bcsr_build_kernel<R, 1><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
@@ -488,9 +559,11 @@ int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, 
 }
 
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
-                 const double* data, const double* ddata, const int64_t* bptr, int* bidx, double* bvals, double* bdvals,
-                 void* stream) {
-    if (!data || !bptr || !bidx || !bvals || (ddata && !bdvals)) return -1;
+                 const double* data, const double* ddata, const int64_t* bptr, int64_t nblocks, int* bidx, double* bvals,
+                 double* bdvals, void* stream) {
+    if (!data || !bptr || !bidx || !bvals || (ddata && !bdvals) || nblocks < 0) return -1;
+    GP_CUDA_CHECK(cudaMemsetAsync(bvals, 0, sizeof(double) * nblocks * R, (cudaStream_t)stream));
+    if (ddata) GP_CUDA_CHECK(cudaMemsetAsync(bdvals, 0, sizeof(double) * nblocks * R, (cudaStream_t)stream));
     return bcsr_build_any(R, 1, n, order, inv_order, indptr, indices, data, ddata, nullptr, bptr, bidx, bvals, bdvals, stream);
 }
 

@@ -181,7 +181,7 @@ class SparseEngine(object):
         bvals = torch.empty(total * R, dtype=torch.float64, device='cuda')
         bdvals = torch.empty(total * R, dtype=torch.float64, device='cuda') if K.ddata is not None else None
         check(lib.gp_bcsr_fill(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(K.data),
-                               _p(K.ddata) if K.ddata is not None else None, _p(bptr), _p(bidx), _p(bvals),
+                               _p(K.ddata) if K.ddata is not None else None, _p(bptr), total, _p(bidx), _p(bvals),
                                _p(bdvals) if bdvals is not None else None, s), 'gp_bcsr_fill')
         self.R = R
         self.blocked = (bptr, bidx, bvals, bdvals)

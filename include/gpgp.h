@@ -149,12 +149,12 @@ int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_
  * rows have nearly the same pattern: one gathered row of X then serves R rows of K and the index is amortised.
  *   gp_bcsr_count: nblk[rb] = number of block-columns of row block rb (ceil(n/R) entries); the caller's exclusive
  *                  prefix sum gives bptr (int64, ceil(n/R)+1).
- *   gp_bcsr_fill : bidx (int32, bptr[last]), bvals / bdvals (f64, R * bptr[last], block-column major). */
+ *   gp_bcsr_fill : nblocks = bptr[last]; bidx (int32, nblocks), bvals / bdvals (f64, R * nblocks, block-column major). */
 int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                   int* nblk, void* stream);
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
-                 const double* data, const double* ddata, const int64_t* bptr, int* bidx, double* bvals, double* bdvals,
-                 void* stream);
+                 const double* data, const double* ddata, const int64_t* bptr, int64_t nblocks, int* bidx, double* bvals,
+                 double* bdvals, void* stream);
 /* Y = (K + eta I) X on the row-blocked operator (FP64 tensor-core MMAs: 4 block-columns x 8 rows x 8 columns) */
 int gp_bcsr_spmm(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                  const double* X, int64_t B, double* Y, void* stream);

@@ -232,6 +232,27 @@ def test_row_blocked_operator_equals_csr(gp, R=8):
     assert int((bvals != 0).sum()) == Ks.nnz
 
 
+def test_row_blocked_build_search_fallback():
+    """Row blocks with more distinct columns than the shared-memory hash table holds are built by the binary-search
+    path: an unstructured random symmetric matrix (8 rows share almost nothing) with the identity as row order."""
+    import torch
+    from gaussian_proc._sparse import SparseEngine, DeviceCSR
+    rng = numpy.random.RandomState(7)
+    n = 3003
+    A = scipy.sparse.random(n, n, density=0.08, random_state=rng, format='csr')
+    A = (A + A.T + scipy.sparse.identity(n)).tocsr()
+    A.sort_indices()
+    Kd = DeviceCSR.from_scipy(A)
+    Kd.order = torch.arange(n, dtype=torch.int32, device='cuda')
+    eng = SparseEngine(Kd, 'slq', {})
+    assert eng.R == 8 and eng.fill_ratio > 4.0          # ~ 8 x 480 distinct columns per block: above the hash capacity
+    Xh = rng.randn(n, 16)
+    Y = eng.from_op(eng.spmm(0.0, eng.to_op(torch.from_numpy(Xh).cuda()))).cpu().numpy()
+    ref = A @ Xh
+    assert numpy.max(numpy.abs(Y - ref)) <= 1e-12 * numpy.max(numpy.abs(ref))
+    assert int((eng.blocked[2] != 0).sum()) == A.nnz
+
+
 def test_internal_permutation_does_not_change_results(sparse_problem):
     """The operator works on a Z-order permuted, row-blocked copy of the CSR matrix; probes are hashed with original row
     ids, so every output must agree with the unpermuted plain-CSR operator up to summation order. The order is a
