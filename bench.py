@@ -185,15 +185,15 @@ def secondary_measurements():
     out = {}
     # configs[2]: one rho group (K generated once) x 8 eta values at n = 8000
     pts, z, X = make_inputs(8000)
-    etas = numpy.logspace(-2, 2, 8)
-    likelihood_grid(pts, z, X, NU, [0.1], etas[:2])
+    etas = numpy.logspace(-2, 2, 16)
+    likelihood_grid(pts, z, X, NU, [0.1, 0.2], etas[:4])      # same shapes: allocator and kernel attributes warm
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    G = likelihood_grid(pts, z, X, NU, [0.1, 0.2], etas)
+    G = likelihood_grid(pts, z, X, NU, [0.1, 0.15, 0.2], etas)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out['sweep_n8k'] = {'cells': int(G.shape[0] * G.shape[1]), 'cells_per_s': G.shape[0] * G.shape[1] / dt,
-                        'workload': 'configs[2] slice: n=8000, 2 rho x 8 eta, l^ + d/d eta + d/d rho per cell',
+                        'workload': 'configs[2] slice: n=8000, 3 rho x 16 eta, l^ + d/d eta + d/d rho per cell',
                         'tflops': G.shape[0] * G.shape[1] * 8000.0 ** 3 / dt * 1e-12}
     # configs[3]: sparse n = 2^20, nu = 0.5, rho = 0.005, density 1e-3
     n = 2 ** 20
@@ -202,9 +202,19 @@ def secondary_measurements():
     scale = numpy.array([0.005, 0.005])
     opts = {'seed': 0, 'lanczos_degree': 30}
 
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    _, zs, Xs = make_inputs(n)      # same seed 0 points as sp
+
     def build():
         Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
         return Kc, SparseEngine(Kc, 'slq', opts)
+
+    def loglik_grad():
+        """the public call: generate_correlation(sparse) -> MixedCorrelation -> ProfileLikelihood (l^, d/d eta, d/d rho)"""
+        Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
+        Km = MixedCorrelation(Kc, imate_method='slq', imate_options=opts)
+        return ProfileLikelihood.log_likelihood_and_gradient(zs, Xs, Km, 10.0)
 
     build()
     torch.cuda.synchronize()
@@ -245,19 +255,32 @@ def secondary_measurements():
     ld, info, ti, tr = evaluate(eng)
     torch.cuda.synchronize()
     te = time.perf_counter() - t0
-    # the same evaluation at a NEW rho: canonical CSR generation + row-blocked build + estimators
+    # the same evaluation at a NEW rho: canonical CSR generation + row-blocked build + estimators (the previous
+    # operator is released first, as an optimiser loop would: its buffers go back to the caching allocator)
+    nnz, fill = K.nnz, eng.fill_ratio
+    del K, eng, V
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     K2, eng2 = build()
     evaluate(eng2)
     torch.cuda.synchronize()
     tn = time.perf_counter() - t0
+    del K2, eng2
+    loglik_grad()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lgr = loglik_grad()
+    torch.cuda.synchronize()
+    tl = time.perf_counter() - t0
     out['sparse_n1M'] = {'workload': 'configs[3]: n=2^20 random 2-D points, nu=0.5, rho=0.005, density=1e-3, eta=10',
-                         'nnz': K.nnz, 'generate_s': tg, 'generate_GBs': (20.0 * K.nnz + 4.0 * (n + 1)) / tg * 1e-9,
-                         'row_blocked_build_s': tb, 'row_blocked_fill_ratio': eng.fill_ratio,
+                         'nnz': nnz, 'generate_s': tg, 'generate_GBs': (20.0 * nnz + 4.0 * (n + 1)) / tg * 1e-9,
+                         'row_blocked_build_s': tb, 'row_blocked_fill_ratio': fill,
                          'spmm': spm, 'spmm_kernel': 'gp::bcsr8_spmm_dmma_kernel (8x1 row blocks, DMMA.8x8x4)',
                          'evals_per_s': 1.0 / te, 'evals_per_s_new_rho': 1.0 / tn,
+                         'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],
                          'eval': 'SLQ logdet + traceinv (degree 30, <= 50 Rademacher probes, batch 16, rtol 1e-2 @ 95 %) + '
-                                 'Hutchinson/CG tr(Kn^-1 dK/drho); new_rho adds CSR generation and the row-blocked build',
+                                 'Hutchinson/CG tr(Kn^-1 dK/drho); new_rho adds CSR generation and the row-blocked build; loglik_grad = the '
+                                 'whole profile likelihood + gradient through the public API (adds the CG solves for [X z], m = 6)',
                          'logdet': ld, 'logdet_half_width': float(info['half_width'][0]), 'num_samples': info['num_samples'],
                          'traceinv': ti, 'trace_Kninv_dK': tr}
     return out

@@ -501,6 +501,39 @@ static SparseOp bcsr_op(int64_t R, const int64_t* bptr, const int* bidx, const d
     return A;
 }
 
+// ---- skinny Gram matrix: out[a][b] = sum_i X[i][a] Y[i][b] for two n x B blocks (B <= 16) ----------------------
+// thread (a, b) of each CTA walks the CTA's contiguous slice of rows; partial[cta][a][b], then a fixed-order final sum.
+constexpr int GRAM_PARTS = 296;
+__global__ void __launch_bounds__(256)
+gram_skinny_partial_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n, int B, double* partial) {
+    const int a = threadIdx.x / B, b = threadIdx.x % B;
+    if (a >= B) return;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    double acc0 = 0.0, acc1 = 0.0;
+    int64_t i = i0;
+    for (; i + 1 < i1; i += 2) {
+        acc0 += X[i * B + a] * Y[i * B + b];
+        acc1 += X[(i + 1) * B + a] * Y[(i + 1) * B + b];
+    }
+    if (i < i1) acc0 += X[i * B + a] * Y[i * B + b];
+    partial[(int64_t)blockIdx.x * B * B + threadIdx.x] = acc0 + acc1;
+}
+__global__ void gram_skinny_final_kernel(const double* __restrict__ partial, int nparts, int BB, double* out) {
+    const int t = threadIdx.x;
+    if (t >= BB) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = 0;
+    for (; i + 3 < nparts; i += 4) {
+        s0 += partial[(int64_t)i * BB + t];
+        s1 += partial[(int64_t)(i + 1) * BB + t];
+        s2 += partial[(int64_t)(i + 2) * BB + t];
+        s3 += partial[(int64_t)(i + 3) * BB + t];
+    }
+    for (; i < nparts; ++i) s0 += partial[(int64_t)i * BB + t];
+    out[t] = (s0 + s1) + (s2 + s3);
+}
+
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace gp
@@ -739,6 +772,22 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream) {
     if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
     return cg_run(bcsr_op(R, bptr, bidx, bvals, n), eta, R0, X, B, tol, maxiter, iters_host, ws, stream);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int64_t gp_gram_workspace_bytes(int64_t B) { return (int64_t)(sizeof(double) * GRAM_PARTS * B * B); }
+
+int gp_gram_skinny(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream) {
+    if (!X || !Y || !out_dev || !ws || n <= 0 || B <= 0 || B > 16) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    gram_skinny_partial_kernel<<<GRAM_PARTS, 256, 0, s>>>(X, Y, n, (int)B, (double*)ws);
+    gram_skinny_final_kernel<<<1, 256, 0, s>>>((const double*)ws, GRAM_PARTS, (int)(B * B), out_dev);
+    GP_COUNT(2);
+    GP_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 """
-Host-side (m+1)x(m+1) algebra on top of the fused device evaluator (csrc/gp_loglik.cu, `gp_loglik_dense`).
+Host-side (m+1)x(m+1) algebra on top of the fused device evaluator (dense: csrc/gp_loglik.cu, `gp_loglik_dense`;
+sparse: `SparseEngine.fused`, batched CG + skinny Gram matrices + stochastic traces, same out[] layout).
 
 With R = [X z], S = Kn^-1 R and the device outputs G = R^T S, H = S^T S, Q = S^T dK S the quantities of the reference
 formulas follow without touching n-sized data again (M = Kn^-1 - Kn^-1 X (X^T Kn^-1 X)^-1 X^T Kn^-1, c = [-beta; 1]):
@@ -59,9 +60,11 @@ def _rhs_device(K_mixed, X, z):
 def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
     """Enqueues one fused evaluation on torch's current stream and returns a handle without synchronising; several
     evaluations on different streams / operators can be in flight (see sweep.py). Complete it with finish()."""
-    if K_mixed.sparse:
-        raise TypeError('the fused dense evaluator needs a dense MixedCorrelation')
     n, m = X.shape
+    if K_mixed.sparse:
+        # sparse K: batched CG solves + skinny Gram matrices + the engine's stochastic traces (synchronous)
+        out = K_mixed.engine.fused(float(eta), X, z, traceinv=traceinv or inverse, drho=drho)
+        return (out, n, m, float(eta), -1, None)
     flags = 0
     if traceinv:
         flags |= FLAG_TRACEINV
@@ -78,6 +81,8 @@ def finish(handle):
     """Waits for the evaluation's stream, reads out[] back (one small D2H) and does the host algebra; raises
     numpy.linalg.LinAlgError if K + eta I was not positive definite."""
     out, n, m, eta, flags, stream = handle
+    if stream is None:
+        return FusedQuantities(out, n, m, eta, flags)      # sparse engine: already complete, breakdowns raised there
     stream.synchronize()
     q = FusedQuantities(out.cpu().numpy(), n, m, eta, flags)
     if q.info != 0:

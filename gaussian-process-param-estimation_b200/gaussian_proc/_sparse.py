@@ -423,6 +423,63 @@ class SparseEngine(object):
         res = self.from_op(self.spmm(0.0, self.to_op(Xd)))[:, :k].cpu().numpy()
         return res[:, 0] if vec else res
 
+    # ---- fused likelihood ingredients -------------------------------------------------------------------------
+    def gram(self, X_dev, Y_dev):
+        """X^T Y (B x B, host) of two n x B device blocks."""
+        torch = dev.torch
+        B = X_dev.shape[1]
+        if '_gram' not in self._ws:
+            self._ws['_gram'] = torch.empty(lib.gp_gram_workspace_bytes(16) // 8, dtype=torch.float64, device='cuda')
+        out = torch.empty(B * B, dtype=torch.float64, device='cuda')
+        check(lib.gp_gram_skinny(_p(X_dev), _p(Y_dev), self.n, B, _p(out), _p(self._ws['_gram']), dev.stream_ptr()),
+              'gp_gram_skinny')
+        return out.cpu().numpy().reshape(B, B)
+
+    def _rhs_block(self, X, z):
+        """[X z] as an operator-space device block, zero padded to a power-of-two width; cached per (X, z)."""
+        torch = dev.torch
+        key = (id(X), id(z))
+        if getattr(self, '_rhs_cache', None) is not None and self._rhs_cache[0] == key:
+            return self._rhs_cache[1]
+        R = numpy.c_[numpy.asarray(X, dtype=float), numpy.asarray(z, dtype=float)]
+        p = R.shape[1]
+        B = 1
+        while B < p:
+            B *= 2
+        if B > 16:
+            raise ValueError('the sparse likelihood evaluation supports at most 15 basis functions.')
+        Rd = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
+        Rd[:, :p].copy_(torch.from_numpy(numpy.ascontiguousarray(R)))
+        Rd = self.to_op(Rd)
+        self._rhs_cache = (key, Rd, X, z)
+        return Rd
+
+    def fused(self, eta, X, z, traceinv=True, drho=True):
+        """Everything log-likelihood + gradient need at one eta, in the layout of the dense evaluator's out[]
+        (csrc/gp_loglik.cu): [logdet Kn, tr Kn^-1, tr Kn^-2, tr(Kn^-1 dK/drho), info, -, -, -, G, H, Q] with R = [X z],
+        S = Kn^-1 R (batched CG, the reference's tol 1e-6), G = R^T S, H = S^T S, Q = S^T dK S; the traces are the
+        stochastic estimates (SLQ / Hutchinson) of this engine. Reference formulas: _direct_likelihood.py:113-150,
+        _profile_likelihood.py:104-130."""
+        n, m = X.shape
+        p = m + 1
+        Rd = self._rhs_block(X, z)
+        S = self.solve_dev(eta, Rd.clone())
+        out = numpy.zeros(8 + 3 * p * p)
+        out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
+        out[8 + p * p:8 + 2 * p * p] = self.gram(S, S)[:p, :p].ravel()
+        if drho:
+            if self.K.ddata is None:
+                raise ValueError('d/d(correlation_scale) needs a DeviceCSR generated with with_derivative=True')
+            D = self.spmm(0.0, S, derivative=True)
+            out[8 + 2 * p * p:8 + 3 * p * p] = self.gram(S, D)[:p, :p].ravel()
+        out[0] = self.logdet(eta)
+        if traceinv or drho:
+            out[1] = self.traceinv(eta)
+            out[2] = self.traceinv(eta, exponent=2)
+        if drho:
+            out[3] = self.traceinv_dK(eta)
+        return out
+
     def trace_K(self):
         """(tr K, tr K^2 = sum of squared entries) of the stored symmetric matrix (rare path: host reduction)."""
         Kh = self.K.to_scipy()

@@ -171,6 +171,10 @@ int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_
  * definite: the hard-thresholded Matern matrix is indefinite, _generate_sparse_correlation.pyx:516-523). */
 int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64_t n, double eta, double* R0, double* X,
                 int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream);
+/* Skinny Gram matrix out_dev[a*B + b] = sum_i X[i][a] Y[i][b] of two n x B row-major blocks (B <= 16); fixed summation
+ * order. Used for G = R^T S, H = S^T S, Q = S^T dK S of the sparse likelihood evaluation (_direct_likelihood.py:113-150). */
+int64_t gp_gram_workspace_bytes(int64_t B);
+int gp_gram_skinny(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream);
 /* the same two Krylov drivers on the row-blocked operator */
 int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                     const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);

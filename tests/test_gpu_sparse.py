@@ -201,6 +201,54 @@ def test_likelihood_through_sparse_operator(sparse_problem):
     assert lk.K_mixed.sparse and lk.K_mixed.imate_method == 'slq'
 
 
+def test_sparse_loglik_and_gradient(sparse_problem):
+    """The full profile log-likelihood + gradient through a sparse K (batched CG solves, skinny Gram matrices,
+    SLQ / Hutchinson traces) against the oracle on the densified matrix: the deterministic ingredients G, H, Q to the
+    CG tolerance, the final numbers within the estimators' confidence bands (fixed seed)."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood, _fused
+    from oracle import likelihood as L
+    pts, z, X, Kd = sparse_problem
+    n, m = X.shape
+    eta = 2.0
+    Km = MixedCorrelation(Kd, imate_method='slq',
+                          imate_options={'seed': 0, 'lanczos_degree': 40, 'min_num_samples': 128, 'max_num_samples': 128,
+                                         'cg_tol': 1e-11})
+    q = _fused.evaluate(z, X, Km, eta, traceinv=True, drho=True)
+    Ks = Kd.to_scipy()
+    Kh = Ks.toarray()
+    dKh = scipy.sparse.csr_matrix((Kd.ddata.cpu().numpy(), Ks.indices, Ks.indptr), shape=Ks.shape).toarray()
+    Kn = Kh + eta * numpy.eye(n)
+    R = numpy.c_[X, z]
+    S = numpy.linalg.solve(Kn, R)
+    for got, ref in ((q.G, R.T @ S), (q.H, S.T @ S), (q.Q, S.T @ dKh @ S)):
+        assert numpy.max(numpy.abs(got - ref)) <= 1e-8 * numpy.max(numpy.abs(ref))
+    Kninv = numpy.linalg.inv(Kn)
+    exact = {'logdet': numpy.linalg.slogdet(Kn)[1], 'ti': numpy.trace(Kninv), 'ti2': numpy.sum(Kninv * Kninv),
+             'tdk': numpy.sum(Kninv * dKh)}
+    # 128 probes: every estimate within 4 standard errors of the exact value (stated band: 1.96 standard errors)
+    eng = Km.engine
+    eng._slq_cache = {}
+    eng.logdet(eta)
+    hw = eng.last_info['half_width'] * 4.0 / 1.96
+    assert abs(q.logdet_Kn - exact['logdet']) <= hw[0]
+    assert abs(q.trace_Kninv - exact['ti']) <= hw[1]
+    assert abs(q.trace_Kninv2 - exact['ti2']) <= hw[2]
+    eng.traceinv_dK(eta)
+    hwd = float(eng.last_info['half_width'][0]) * 4.0 / 1.96
+    assert abs(q.trace_Kninv_dK - exact['tdk']) <= hwd
+    # final numbers: the oracle's formulas on the dense matrices; error budget = half the trace errors
+    Ko = L.MixedCorrelation(Kh, 'cholesky')
+    sig = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, eta)
+    ref = (L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [sig, eta]),
+           L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(eta)),
+           L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dKh, eta))
+    lp, deta, drho = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
+    assert abs(lp - ref[0]) <= 0.5 * hw[0] + 1e-7 * abs(ref[0])
+    assert abs(deta - ref[1]) <= 0.5 * hw[1] + 1e-7 * abs(ref[1])
+    assert abs(drho - ref[2]) <= 0.5 * hwd + 1e-7 * abs(ref[2])
+
+
 def test_row_blocked_operator_equals_csr(gp, R=8):
     """The row-blocked operator (8 x 1 blocks of the Z-order permuted matrix, zero filled, DMMA SpMM) is the same linear map as the
     canonical CSR: products against the SciPy matrix to rounding, for K and for dK/drho, n not a multiple of R."""
