@@ -29,11 +29,11 @@ csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 }
 
 // ---- column reductions: partial[cta][c] = sum over the CTA's elements of column c --------------------------------
-// mode 0: x*y   mode 1: (lanczos) u_next = w - a u - b u_prev written over u_prev, accumulate u_next^2
+// mode 0: x*y   mode 1: (lanczos) u_next = w - a u - b u_prev (Z; may be u_prev's buffer), accumulate u_next^2
 // mode 2: (cg) x += a p, r -= a ap, accumulate r*r
 template <int MODE>
 __global__ void __launch_bounds__(256)
-col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const double* __restrict__ Y, double* W,
+col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const double* Y, double* W,
                  double* Z, const double* __restrict__ a, const double* __restrict__ b, double* partial) {
     __shared__ double red[256];
     const int64_t stride = (int64_t)gridDim.x * 256;  // multiple of 32 >= B: a thread stays in one column
@@ -44,7 +44,7 @@ col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const doubl
         if (MODE == 0) {
             acc += X[idx] * Y[idx];
         } else if (MODE == 1) {
-            double w = W[idx] - ac * X[idx] - bc * Z[idx];   // X = u_j, Z = u_{j-1} (overwritten by u_{j+1})
+            double w = W[idx] - ac * X[idx] - bc * Y[idx];   // X = u_j, Y = u_{j-1}, Z = u_{j+1} (may alias Y)
             Z[idx] = w;
             acc += w * w;
         } else {
@@ -501,23 +501,69 @@ static SparseOp bcsr_op(int64_t R, const int64_t* bptr, const int* bidx, const d
     return A;
 }
 
+// X = sum_j coef[j][c] U_j (elementwise per column): one pass over the m kept Lanczos vectors
+__global__ void __launch_bounds__(256)
+block_combine_kernel(const double* __restrict__ basis, int64_t total, int B, int m, const double* __restrict__ coef,
+                     double* __restrict__ X) {
+    extern __shared__ double cf[];      // m x B
+    for (int i = threadIdx.x; i < m * B; i += blockDim.x) cf[i] = coef[i];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B == 1) {
+        if (idx >= total) return;
+        double acc = 0.0;
+        for (int j = 0; j < m; ++j) acc += cf[j] * basis[(int64_t)j * total + idx];
+        X[idx] = acc;
+        return;
+    }
+    const int64_t e = idx * 2;          // two adjacent columns of one row (B is even)
+    if (e >= total) return;
+    const int c = (int)(e % B);
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) {
+        const double2 u = *reinterpret_cast<const double2*>(basis + (int64_t)j * total + e);
+        a0 += cf[j * B + c] * u.x;
+        a1 += cf[j * B + c + 1] * u.y;
+    }
+    *reinterpret_cast<double2*>(X + e) = make_double2(a0, a1);
+}
+
 // ---- skinny Gram matrix: out[a][b] = sum_i X[i][a] Y[i][b] for two n x B blocks (B <= 16) ----------------------
-// thread (a, b) of each CTA walks the CTA's contiguous slice of rows; partial[cta][a][b], then a fixed-order final sum.
-constexpr int GRAM_PARTS = 296;
+// Each CTA walks a contiguous slice of rows in tiles of 64 rows staged in shared memory (coalesced loads); thread
+// (pair (a, b), slice) accumulates its pair over every (256 / B^2)-th row of the tile; partial[cta][a][b], then a
+// fixed-order final sum.
+constexpr int GRAM_PARTS = 1184;
+constexpr int GRAM_TILE = 64;
 __global__ void __launch_bounds__(256)
 gram_skinny_partial_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n, int B, double* partial) {
-    const int a = threadIdx.x / B, b = threadIdx.x % B;
-    if (a >= B) return;
+    __shared__ double sx[GRAM_TILE * 16], sy[GRAM_TILE * 16];
+    __shared__ double red[256];
+    const int BB = B * B;
+    const int nsl = 256 / BB;                 // row slices (>= 1 since B <= 16)
+    const int pair = threadIdx.x % BB, sl = threadIdx.x / BB;
+    const int a = pair / B, b = pair % B;
     const int64_t per = (n + gridDim.x - 1) / gridDim.x;
     const int64_t i0 = blockIdx.x * per, i1 = min(n, i0 + per);
-    double acc0 = 0.0, acc1 = 0.0;
-    int64_t i = i0;
-    for (; i + 1 < i1; i += 2) {
-        acc0 += X[i * B + a] * Y[i * B + b];
-        acc1 += X[(i + 1) * B + a] * Y[(i + 1) * B + b];
+    double acc = 0.0;
+    for (int64_t r0 = i0; r0 < i1; r0 += GRAM_TILE) {
+        const int rows = (int)min((int64_t)GRAM_TILE, i1 - r0);
+        for (int e = threadIdx.x; e < rows * B; e += 256) {
+            sx[e] = X[r0 * B + e];
+            sy[e] = Y[r0 * B + e];
+        }
+        __syncthreads();
+        if (sl < nsl)
+            for (int r = sl; r < rows; r += nsl) acc += sx[r * B + a] * sy[r * B + b];
+        __syncthreads();
     }
-    if (i < i1) acc0 += X[i * B + a] * Y[i * B + b];
-    partial[(int64_t)blockIdx.x * B * B + threadIdx.x] = acc0 + acc1;
+    red[threadIdx.x] = (sl < nsl) ? acc : 0.0;
+    __syncthreads();
+    if (threadIdx.x < BB) {
+        double s = 0.0;
+        for (int k = 0; k < nsl; ++k) s += red[k * BB + threadIdx.x];
+        partial[(int64_t)blockIdx.x * BB + threadIdx.x] = s;
+    }
 }
 __global__ void gram_skinny_final_kernel(const double* __restrict__ partial, int nparts, int BB, double* out) {
     const int t = threadIdx.x;
@@ -642,8 +688,10 @@ int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* o
 //   W = s_j (A u_j) (scale applied in the SpMM epilogue, which also reduces u_j . W), alpha_j = s_j (u_j . W),
 //   u_{j+1} = W - (alpha_j s_j) u_j - (beta_{j-1} s_{j-1}) u_{j-1}  (written over u_{j-1}),  beta_j = ||u_{j+1}||
 // so a step is two passes over the vectors (the SpMM and one fused update) and four launches.
+// With `basis` (m x n x B doubles) the vectors u_0 .. u_{m-1} are kept: q_j = u_j / beta_{j-1} (beta_{-1} = ||v||) is the
+// Krylov basis from which the caller forms (K + eta I)^-1 v = ||v|| Q T^-1 e_1 without a separate CG solve.
 static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B, int64_t m, double* alpha_dev,
-                       double* beta_dev, void* ws, void* stream) {
+                       double* beta_dev, double* basis, void* ws, void* stream) {
     const int64_t n = A.n;
     if (!A.idx || !A.val || !V || !alpha_dev || !beta_dev || !ws || n <= 0 || m <= 0) return -1;
     if (B <= 0 || B > 32 || (32 % B)) return -2;
@@ -663,24 +711,26 @@ static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B
     double* b1 = sc + 128;     // beta_{j-1} s_{j-1}
     double* tmp = sc + 160;
     // u_0 = v, s_0 = 1 / ||v||, u_{-1} = 0
-    GP_CUDA_CHECK(cudaMemcpyAsync(U0, V, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
+    auto vec = [&](int64_t j) -> double* {      // storage of u_j
+        if (basis) return (j >= 0 && j < m) ? basis + j * total : U1;
+        return (j & 1) ? U1 : U0;
+    };
+    GP_CUDA_CHECK(cudaMemcpyAsync(vec(0), V, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
     GP_CUDA_CHECK(cudaMemsetAsync(U1, 0, sizeof(double) * total, s));
     GP_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(double) * 96, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, V, V, nullptr, nullptr, nullptr, nullptr, partial);
     col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, tmp, st, nullptr, nullptr, 0.0);
     GP_CUDA_CHECK(cudaMemsetAsync(st + 32, 0, sizeof(double) * 64, s));    // s_prev = beta_prev = 0 for the first step
     GP_COUNT(2);
-    double* u = U0;
-    double* uprev = U1;
     for (int64_t j = 0; j < m; ++j) {
+        double* u = vec(j);
         int nparts = 0;
         int rc = spmm(A, eta, u, Bc, W, s, st, partial, &nparts);
         if (rc) return rc;
         col_final(partial, nparts, Bc, 1, alpha_dev + j * B, st, a1, b1, 0.0, scratch, s);
-        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, u, nullptr, W, uprev, a1, b1, partial);
+        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, u, vec(j - 1), W, vec(j + 1), a1, b1, partial);
         col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, beta_dev + j * B, st, nullptr, nullptr, 0.0);
         GP_COUNT(2);
-        double* t = u; u = uprev; uprev = t;
     }
     GP_LAUNCH_CHECK();
     return 0;
@@ -751,15 +801,28 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
 extern "C" {
 
 int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* V, int64_t B,
-               int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream) {
+               int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws, void* stream) {
     if (!indptr || n <= 0 || n > INT32_MAX) return -1;
-    return lanczos_run(csr_op(indptr, indices, data, n), eta, V, B, m, alpha_dev, beta_dev, ws, stream);
+    return lanczos_run(csr_op(indptr, indices, data, n), eta, V, B, m, alpha_dev, beta_dev, basis_dev, ws, stream);
 }
 
 int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
-                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream) {
+                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws,
+                    void* stream) {
     if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
-    return lanczos_run(bcsr_op(R, bptr, bidx, bvals, n), eta, V, B, m, alpha_dev, beta_dev, ws, stream);
+    return lanczos_run(bcsr_op(R, bptr, bidx, bvals, n), eta, V, B, m, alpha_dev, beta_dev, basis_dev, ws, stream);
+}
+
+// X[i][c] = sum_j coef[j][c] basis[j][i][c]: the Lanczos solution ||v|| Q T^-1 e_1 from the kept vectors
+int gp_block_combine(const double* basis, int64_t n, int64_t B, int64_t m, const double* coef_dev, double* X, void* stream) {
+    if (!basis || !coef_dev || !X || n <= 0 || B <= 0 || B > 32 || m <= 0 || m > 256) return -1;
+    const int64_t total = n * B;
+    const int64_t work = (B == 1) ? total : total / 2;
+    block_combine_kernel<<<(unsigned)((work + 255) / 256), 256, (size_t)(m * B * sizeof(double)), (cudaStream_t)stream>>>(
+        basis, total, (int)B, (int)m, coef_dev, X);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
 }
 
 int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64_t n, double eta, double* R0, double* X,

@@ -57,11 +57,12 @@ SIGNATURES = {
     'gp_bcsr_spmm': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_gram_workspace_bytes': (_i64, [_i64]),
     'gp_gram_skinny': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
-    'gp_bcsr_lanczos': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_lanczos': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'gp_bcsr_cg_solve': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_krylov_workspace_bytes': (_i64, [_i64, _i64]),
     'gp_col_dot': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
-    'gp_lanczos': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'gp_lanczos': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'gp_block_combine': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     'gp_cg_solve': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_dgemm_f64': (_int, [_int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _int, _int,
                             _vp]),

@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8)
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True)
 
 
 def _p(t):
@@ -120,7 +120,7 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     return K if device else K.to_scipy()
 
 
-def lanczos_quadrature(alpha, beta, funcs):
+def lanczos_quadrature(alpha, beta, funcs, return_size=False):
     """Gauss quadrature of v^T f(A) v / ||v||^2 from the Lanczos tridiagonal: sum_k tau_k^2 f(theta_k) with theta the
     Ritz values and tau the first components of the Ritz vectors. A beta ~ 0 truncates the recurrence (invariant
     subspace reached)."""
@@ -131,7 +131,8 @@ def lanczos_quadrature(alpha, beta, funcs):
             break
     theta, Y = scipy.linalg.eigh_tridiagonal(alpha[:m], beta[:m - 1]) if m > 1 else (alpha[:1], numpy.ones((1, 1)))
     w = Y[0, :] ** 2
-    return [float(numpy.sum(w * f(theta))) for f in funcs], float(theta.min())
+    res = [float(numpy.sum(w * f(theta))) for f in funcs], float(theta.min())
+    return res + (m,) if return_size else res
 
 
 class SparseEngine(object):
@@ -226,31 +227,75 @@ class SparseEngine(object):
         return V
 
     # ---- SLQ -----------------------------------------------------------------------------------------------------
-    def _slq_samples(self, eta, first, B):
-        """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1."""
+    def _lanczos(self, eta, V, m, basis=None):
         torch = dev.torch
-        m = int(self.opt['lanczos_degree'])
-        V = self.probes(first, B)
+        B = V.shape[1]
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        bp = _p(basis) if basis is not None else None
         if self.blocked is not None:
             bptr, bidx, bvals, _ = self.blocked
             check(lib.gp_bcsr_lanczos(self.R, _p(bptr), _p(bidx), _p(bvals), self.n, float(eta), _p(V), B, m, _p(alpha),
-                                      _p(beta), _p(self._workspace(B)), dev.stream_ptr()), 'gp_bcsr_lanczos')
+                                      _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_bcsr_lanczos')
         else:
             K = self.K
             check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha),
-                                 _p(beta), _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
-        a, b = alpha.cpu().numpy(), beta.cpu().numpy()
-        out = numpy.empty((B, 3))
+                                 _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
+        return alpha.cpu().numpy(), beta.cpu().numpy()
+
+    def _slq_samples(self, eta, first, B, with_dk=False):
+        """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1. With ``with_dk`` a fourth column:
+        the Hutchinson sample v^T Kn^-1 dK v with Kn^-1 v taken from the SAME Lanczos run (x = ||v|| Q T^-1 e_1, the
+        Lanczos form of CG) when its residual beta_k |y_k| meets the CG tolerance, else from a batched CG solve."""
+        torch = dev.torch
+        m = int(self.opt['lanczos_degree'])
+        V = self.probes(first, B)
+        basis = None
+        if with_dk:
+            key = ('basis', m, B)
+            if key not in self._ws:
+                self._ws[key] = torch.empty((m, self.n, B), dtype=torch.float64, device='cuda')
+            basis = self._ws[key]
+        a, b = self._lanczos(eta, V, m, basis)
+        out = numpy.empty((B, 4 if with_dk else 3))
+        coef = numpy.zeros((m, B))
+        vnorm = numpy.sqrt(float(self.n))          # Rademacher probes
+        resid = 0.0
         for c in range(B):
-            vals, tmin = lanczos_quadrature(a[:, c], b[:, c], [numpy.log, lambda t: 1.0 / t, lambda t: 1.0 / t ** 2])
+            vals, tmin, k = lanczos_quadrature(a[:, c], b[:, c], [numpy.log, lambda t: 1.0 / t, lambda t: 1.0 / t ** 2],
+                                               return_size=True)
             if not (tmin > 0):
                 raise numpy.linalg.LinAlgError(
                     'K + eta*I (eta=%g) is not positive definite: Lanczos found a Ritz value %.3e. The thresholded '
                     'Matern matrix is indefinite; use a larger eta (reference: _generate_sparse_correlation.pyx:516-523).'
                     % (eta, tmin))
-            out[c] = numpy.array(vals) * self.n
+            out[c, :3] = numpy.array(vals) * self.n
+            if with_dk:
+                e1 = numpy.zeros(k)
+                e1[0] = 1.0
+                if k > 1:
+                    ab = numpy.zeros((2, k))
+                    ab[0, 1:] = b[:k - 1, c]
+                    ab[1, :] = a[:k, c]
+                    y = scipy.linalg.solveh_banded(ab, e1)
+                else:
+                    y = e1 / a[0, c]
+                scale = numpy.empty(k)                  # 1 / ||u_j||: u_0 = v, u_j = beta_{j-1} q_j
+                scale[0] = 1.0 / vnorm
+                scale[1:] = 1.0 / b[:k - 1, c]
+                coef[:k, c] = vnorm * y * scale
+                resid = max(resid, abs(b[k - 1, c] * y[k - 1]))
+        if with_dk:
+            if resid <= float(self.opt['cg_tol']):
+                U = torch.empty_like(V)
+                cd = torch.from_numpy(coef).cuda()
+                check(lib.gp_block_combine(_p(basis), self.n, B, m, _p(cd), _p(U), dev.stream_ptr()), 'gp_block_combine')
+                self.last_dk_solver = 'lanczos'
+            else:
+                U = self.solve_dev(eta, V.clone())
+                self.last_dk_solver = 'cg'
+            Wd = self.spmm(0.0, V, derivative=True)
+            out[:, 3] = self.col_dot(U, Wd)
         return out
 
     @staticmethod
@@ -266,20 +311,32 @@ class SparseEngine(object):
             count -= w
         return out
 
-    def _run_estimator(self, sample_fn, ncols):
-        """imate-style sampling loop: rounds of probes until every estimated quantity satisfies
-        z * s / sqrt(N) <= max(atol, rtol |mean|) (after min_num_samples) or max_num_samples is reached.
+    def _run_estimator(self, sample_fn, ncols, check_cols=None, state=None):
+        """imate-style sampling loop: rounds of probes until every estimated quantity (the first ``check_cols`` columns)
+        satisfies z * s / sqrt(N) <= max(atol, rtol |mean|) (after min_num_samples) or max_num_samples is reached.
+        ``state`` = (samples, first) continues an earlier run (its convergence is tested before sampling more).
         Multi-GPU: each round's probe ids are cut into `world` contiguous slices, one per rank; the running
         (count, sum, sum of squares) are all-reduced, so every rank takes the same stopping decision. Probe ids, not
-        ranks, seed the random signs: the union of the samples is the same set for any number of GPUs."""
+        ranks, seed the random signs: the union of the samples is the same set for any number of GPUs.
+        Returns mean, half_width, N, (samples, first)."""
         o = self.opt
         B = int(o['batch'])
         zc = float(numpy.sqrt(2.0) * scipy.special.erfinv(float(o['confidence_level'])))
         lo, hi = int(o['min_num_samples']), int(o['max_num_samples'])
         rank, world = self.probe_range if self.probe_range is not None else (0, 1)
-        samples = numpy.empty((0, ncols))
-        first = 0
-        while first < hi:
+        cc = ncols if check_cols is None else check_cols
+        samples, first = (numpy.empty((0, ncols)), 0) if state is None else state
+        atol = o['error_atol'] if o['error_atol'] is not None else 0.0
+
+        def converged():
+            N, mean, sd = self._reduce(samples)
+            if N < lo:
+                return False
+            half = zc * sd / numpy.sqrt(N)
+            return bool(numpy.all(half[:cc] <= numpy.maximum(atol, o['error_rtol'] * numpy.abs(mean[:cc]))))
+
+        done = (first > 0) and converged()
+        while first < hi and not done:
             nb = min(B * world, hi - first)
             per = (nb + world - 1) // world
             my0 = first + rank * per
@@ -287,15 +344,10 @@ class SparseEngine(object):
             for (f, w) in self._chunks(my0, max(0, my1 - my0), B):
                 samples = numpy.vstack([samples, sample_fn(f, w)])
             first += nb
-            N, mean, sd = self._reduce(samples)
-            if N >= lo:
-                half = zc * sd / numpy.sqrt(N)
-                atol = o['error_atol'] if o['error_atol'] is not None else 0.0
-                if numpy.all(half <= numpy.maximum(atol, o['error_rtol'] * numpy.abs(mean))):
-                    break
+            done = converged()
         N, mean, sd = self._reduce(samples)
         half = zc * sd / numpy.sqrt(max(N, 1))
-        return mean, half, int(N)
+        return mean, half, int(N), (samples, first)
 
     def _reduce(self, samples):
         """(N, mean, unbiased std) over all ranks: all-reduce of (count, sum, sum of squares) per quantity."""
@@ -313,10 +365,16 @@ class SparseEngine(object):
         return N, mean, numpy.sqrt(var)
 
     def _slq(self, eta):
+        """SLQ estimates [logdet, tr Kn^-1, tr Kn^-2] at eta (cached). When the matrix carries dK/drho the same Lanczos
+        runs also yield the Hutchinson samples of tr(Kn^-1 dK) (kept for traceinv_dK; they do not influence the
+        stopping decision here)."""
         key = float(eta)
         if key not in self._slq_cache:
-            mean, half, N = self._run_estimator(lambda first, width: self._slq_samples(eta, first, width), 3)
-            self._slq_cache = {key: (mean, half, N)}
+            with_dk = self.K.ddata is not None and bool(self.opt.get('reuse_lanczos', True))
+            mean, half, N, state = self._run_estimator(
+                lambda first, width: self._slq_samples(eta, first, width, with_dk), 4 if with_dk else 3, check_cols=3)
+            self._slq_cache = {key: (mean[:3], half[:3], N)}
+            self._dk_state = {key: (state[0][:, 3:4].copy(), state[1])} if with_dk else {}
         mean, half, N = self._slq_cache[key]
         self.last_info = {'num_samples': N, 'half_width': half, 'confidence_level': self.opt['confidence_level'],
                           'lanczos_degree': self.opt['lanczos_degree']}
@@ -336,12 +394,14 @@ class SparseEngine(object):
             V = self.probes(first, width)
             U = self.solve_dev(eta, V.clone())
             return self.col_dot(U, V).reshape(-1, 1)
-        mean, half, N = self._run_estimator(fn, 1)
+        mean, half, N, _ = self._run_estimator(fn, 1)
         self.last_info = {'num_samples': N, 'half_width': half}
         return float(mean[0])
 
     def traceinv_dK(self, eta):
-        """Hutchinson estimate of tr((K + eta I)^-1 dK/d rho): mean over probes of (Kn^-1 v)^T (dK v)."""
+        """Hutchinson estimate of tr((K + eta I)^-1 dK/d rho): mean over probes of (Kn^-1 v)^T (dK v). Samples that the
+        SLQ run at this eta already produced (same probe ids, Kn^-1 v from its Lanczos basis) are used first; further
+        rounds, if its own stopping rule asks for them, use batched CG."""
         if self.K.ddata is None:
             raise ValueError('needs a DeviceCSR generated with with_derivative=True')
 
@@ -350,7 +410,8 @@ class SparseEngine(object):
             U = self.solve_dev(eta, V.clone())
             Wd = self.spmm(0.0, V, derivative=True)
             return self.col_dot(U, Wd).reshape(-1, 1)
-        mean, half, N = self._run_estimator(fn, 1)
+        state = getattr(self, '_dk_state', {}).get(float(eta))
+        mean, half, N, _ = self._run_estimator(fn, 1, state=state)
         self.last_info = {'num_samples': N, 'half_width': half}
         return float(mean[0])
 

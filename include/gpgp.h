@@ -163,9 +163,10 @@ int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B);
 /* out_dev[c] = sum_i X[i][c] Y[i][c] (deterministic two-stage reduction) */
 int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream);
 /* m Lanczos steps per column started from V (normalised internally); alpha_dev, beta_dev: (m x B) device arrays of
- * the tridiagonal coefficients (beta[j] couples steps j and j+1). The quadrature itself is host-side. */
+ * the tridiagonal coefficients (beta[j] couples steps j and j+1). The quadrature itself is host-side.
+ * basis_dev: NULL, or m x n x B doubles that receive the unnormalised Lanczos vectors u_j = beta_{j-1} q_j. */
 int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_t n, double eta, const double* V,
-               int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);
+               int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws, void* stream);
 /* Batched CG from a zero start: X = (K + eta I)^-1 R0 column by column, stop at ||r|| <= tol ||b||. R0 is
  * overwritten. Returns 0; 1 when maxiter was reached first; 2 when p^T A p <= 0 was met (K + eta I not positive
  * definite: the hard-thresholded Matern matrix is indefinite, _generate_sparse_correlation.pyx:516-523). */
@@ -177,7 +178,12 @@ int64_t gp_gram_workspace_bytes(int64_t B);
 int gp_gram_skinny(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream);
 /* the same two Krylov drivers on the row-blocked operator */
 int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
-                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, void* ws, void* stream);
+                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws,
+                    void* stream);
+/* X[i][c] = sum_j coef_dev[j][c] basis[j][i][c] (coef: m x B). With coef[j][c] = ||v_c|| y_jc / beta_{j-1,c} and
+ * y = T^-1 e_1 this is the Lanczos solution of (K + eta I) x = v from the vectors kept by gp_*_lanczos: the Hutchinson
+ * tr(Kn^-1 dK) estimator reuses the SLQ run instead of a second Krylov solve. */
+int gp_block_combine(const double* basis, int64_t n, int64_t B, int64_t m, const double* coef_dev, double* X, void* stream);
 int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                      double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
                      void* stream);

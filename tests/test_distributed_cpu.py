@@ -46,7 +46,7 @@ def _worker(rank, world, port, out):
     eng = object.__new__(SparseEngine)
     eng.opt = dict(DEFAULTS, min_num_samples=10, max_num_samples=24, batch=4, error_rtol=1e-9)
     eng.probe_range = (rank, world)
-    res['est'] = eng._run_estimator(_fake_samples, 2)
+    res['est'] = eng._run_estimator(_fake_samples, 2)[:3]
     dist.barrier()
     dist.destroy_process_group()
     out[rank] = res
@@ -71,7 +71,10 @@ def test_two_rank_gloo_matches_single_process():
     eng = object.__new__(SparseEngine)
     eng.opt = dict(DEFAULTS, min_num_samples=10, max_num_samples=24, batch=4, error_rtol=1e-9)
     eng.probe_range = None
-    mean1, half1, n1 = eng._run_estimator(_fake_samples, 2)
+    mean1, half1, n1, state = eng._run_estimator(_fake_samples, 2)
+    # continuing a finished run changes nothing (max_num_samples reached)
+    mean2, half2, n2, _ = eng._run_estimator(_fake_samples, 2, state=state)
+    assert n2 == n1 and numpy.array_equal(mean2, mean1)
     for r in range(world):
         mean, half, n = out[r]['est']
         assert n == n1 == 24

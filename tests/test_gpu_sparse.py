@@ -249,6 +249,27 @@ def test_sparse_loglik_and_gradient(sparse_problem):
     assert abs(drho - ref[2]) <= 0.5 * hwd + 1e-7 * abs(ref[2])
 
 
+def test_hutchinson_dk_reuses_the_lanczos_basis(sparse_problem):
+    """tr(Kn^-1 dK): Kn^-1 v from the SLQ run's Lanczos vectors (x = ||v|| Q T^-1 e_1, residual checked against the CG
+    tolerance) gives the same per-probe samples as separate batched CG solves."""
+    from gaussian_proc._sparse import SparseEngine
+    pts, z, X, Kd = sparse_problem
+    opts = {'seed': 2, 'lanczos_degree': 40, 'min_num_samples': 32, 'max_num_samples': 32, 'cg_tol': 1e-8}
+    a = SparseEngine(Kd, 'slq', dict(opts, reuse_lanczos=True))
+    b = SparseEngine(Kd, 'slq', dict(opts, reuse_lanczos=False))
+    a.logdet(2.0)
+    assert a.last_dk_solver == 'lanczos' and a._dk_state[2.0][0].shape == (32, 1)
+    ta, tb = a.traceinv_dK(2.0), b.traceinv_dK(2.0)
+    assert a.last_info['num_samples'] == b.last_info['num_samples'] == 32
+    assert abs(ta - tb) <= 1e-6 * abs(tb)
+    # 6 Lanczos steps cannot reach the tolerance at a small shift (lambda_min(K) ~ -0.5) -> fall back to CG
+    c = SparseEngine(Kd, 'slq', dict(opts, lanczos_degree=6, reuse_lanczos=True))
+    c.logdet(0.8)
+    assert c.last_dk_solver == 'cg'
+    assert abs(c.traceinv_dK(0.8) - SparseEngine(Kd, 'slq', dict(opts, reuse_lanczos=False)).traceinv_dK(0.8)) \
+        <= 1e-6 * abs(c.traceinv_dK(0.8))
+
+
 def test_row_blocked_operator_equals_csr(gp, R=8):
     """The row-blocked operator (8 x 1 blocks of the Z-order permuted matrix, zero filled, DMMA SpMM) is the same linear map as the
     canonical CSR: products against the SciPy matrix to rounding, for K and for dK/drho, n not a multiple of R."""

@@ -40,7 +40,7 @@ import torch as _t
 Vp = eng.probes(0, 1)
 al = _t.empty((60, 1), dtype=_t.float64, device='cuda'); be = _t.empty((60, 1), dtype=_t.float64, device='cuda')
 P = lambda t: ctypes.c_void_p(t.data_ptr())
-dev.lib.gp_lanczos(P(K.indptr), P(K.indices), P(K.data), n, 0.0, P(Vp), 1, 60, P(al), P(be), P(eng._workspace(1)), dev.stream_ptr())
+dev.lib.gp_lanczos(P(K.indptr), P(K.indices), P(K.data), n, 0.0, P(Vp), 1, 60, P(al), P(be), None, P(eng._workspace(1)), dev.stream_ptr())
 import scipy.linalg
 th = scipy.linalg.eigh_tridiagonal(al.cpu().numpy()[:, 0], be.cpu().numpy()[:59, 0], eigvals_only=True)
 out['ritz_min_max_of_K'] = [float(th.min()), float(th.max())]
@@ -61,7 +61,7 @@ bptr, bidx, bvals, _ = eng.blocked
 al = torch.empty((30, 16), dtype=torch.float64, device='cuda'); be = torch.empty((30, 16), dtype=torch.float64, device='cuda')
 ws = eng._workspace(16)
 def lz():
-    dev.lib.gp_bcsr_lanczos(8, P(bptr), P(bidx), P(bvals), n, 10.0, P(V), 16, 30, P(al), P(be), P(ws), dev.stream_ptr())
+    dev.lib.gp_bcsr_lanczos(8, P(bptr), P(bidx), P(bvals), n, 10.0, P(V), 16, 30, P(al), P(be), None, P(ws), dev.stream_ptr())
 lz()
 t, _ = timed(lz, 3)
 out['lanczos30_B16_ms'] = t * 1e3
