@@ -150,6 +150,8 @@ __global__ void cell_scatter_kernel(const double* __restrict__ pts, int n, int d
 
 struct SparseParams {
     double tau, band;         // keep rule K > tau; |K - tau| <= band -> host decides
+    double r2_lo, r2_hi;      // squared scaled distance certainly inside / outside the support (quick classification)
+    int quick;                // 0: no quick classification (tau <= 0 or tau >= 1)
     double scale[8];
     MaternParams mp;
     int d, n;
@@ -166,13 +168,20 @@ __device__ __forceinline__ double scaled_distance(const double* a, const double*
 }
 
 // One warp per (cell-sorted) point. PASS 0 counts kept entries and lists borderline pairs; PASS 1 writes (col, value
-// [, dvalue]) in candidate order into the row's segment.
+// [, dvalue]) into the row's segment (any order: the rows are sorted afterwards).
+// Candidates are first classified by their squared scaled distance (multiply-by-reciprocal, no sqrt / exp): further than
+// the support radius by a 1e-7 margin -> dropped; closer by the same margin -> kept (PASS 0 just counts them). Only the
+// others are evaluated in the reference's arithmetic (IEEE divide, sqrt, exp) - in PASS 0 a vanishing fraction, in
+// PASS 1 the kept third of the candidates, which are compacted through a per-warp queue so that the expensive
+// evaluation always runs on full warps.
 template <int MODE, int PASS, bool WITH_DK>
 __global__ void __launch_bounds__(256)
 sparse_rows_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_start, const int* __restrict__ sorted_idx,
                    const double* __restrict__ sorted_pts, int* devcount, int* border_cnt, int2* border,
                    const int* __restrict__ indptr, int* indices, double* data, double* ddata) {
+    __shared__ int queue_s[8][64];
     const int lane = threadIdx.x & 31;
+    int* queue = queue_s[threadIdx.x >> 5];
     const int wpos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wpos >= sp.n) return;
     const int i = sorted_idx[wpos];
@@ -184,7 +193,38 @@ sparse_rows_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_sta
         for (int k = g.d - 1; k >= 0; --k) { cc[k] = id % g.nc[k]; id /= g.nc[k]; }
     }
     int count = 0;
+    int qn = 0;                                   // queued candidates (warp-uniform)
     const int64_t base = (PASS == 1) ? (int64_t)indptr[i] : 0;
+
+    // exact evaluation of candidate q (sorted position) by the lanes with act = true
+    auto evaluate = [&](int q, bool act) {
+        bool keep = false;
+        double val = 0.0, dval = 0.0;
+        int j = -1;
+        if (act) {
+            j = sorted_idx[q];
+            double pj[8];
+            for (int k = 0; k < sp.d; ++k) pj[k] = sorted_pts[(int64_t)q * sp.d + k];
+            double x = (i <= j) ? scaled_distance(pi, pj, sp) : scaled_distance(pj, pi, sp);
+            if (WITH_DK && PASS == 1) matern_value_drho<MODE>(x, sp.mp, &val, &dval);
+            else val = matern_value<MODE>(x, sp.mp);
+            bool borderline = (i != j) && fabs(val - sp.tau) <= sp.band;
+            keep = !borderline && (val > sp.tau);
+            if (PASS == 0 && borderline) {
+                int slot = atomicAdd(border_cnt, 1);
+                if (slot < BORDER_CAP) border[slot] = make_int2(i, j);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (PASS == 1 && keep) {
+            int64_t o = base + count + __popc(m & ((1u << lane) - 1u));
+            indices[o] = j;
+            data[o] = val;
+            if (WITH_DK) ddata[o] = dval;
+        }
+        count += __popc(m);
+    };
+
     const int span = (g.ncells > 1) ? 3 : 1;
     const int nnb = (g.ncells > 1) ? (g.d == 1 ? 3 : (g.d == 2 ? 9 : 27)) : 1;
     for (int nb = 0; nb < nnb; ++nb) {
@@ -203,34 +243,35 @@ sparse_rows_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_sta
         if (!ok) continue;
         const int s0 = cell_start[id], s1 = cell_start[id + 1];
         for (int q0 = s0; q0 < s1; q0 += 32) {
-            int q = q0 + lane;
-            bool keep = false;
-            double val = 0.0, dval = 0.0;
-            int j = -1;
+            const int q = q0 + lane;
+            if (!sp.quick) { evaluate(q, q < s1); continue; }
+            bool need = false, sure = false;
             if (q < s1) {
-                j = sorted_idx[q];
-                double pj[8];
-                for (int k = 0; k < sp.d; ++k) pj[k] = sorted_pts[(int64_t)q * sp.d + k];
-                double x = (i <= j) ? scaled_distance(pi, pj, sp) : scaled_distance(pj, pi, sp);
-                if (WITH_DK && PASS == 1) matern_value_drho<MODE>(x, sp.mp, &val, &dval);
-                else val = matern_value<MODE>(x, sp.mp);
-                bool borderline = (i != j) && fabs(val - sp.tau) <= sp.band;
-                keep = !borderline && (val > sp.tau);
-                if (PASS == 0 && borderline) {
-                    int slot = atomicAdd(border_cnt, 1);
-                    if (slot < BORDER_CAP) border[slot] = make_int2(i, j);
+                double s2 = 0.0;
+                for (int k = 0; k < sp.d; ++k) {
+                    double t = (pi[k] - sorted_pts[(int64_t)q * sp.d + k]) * sp.mp.inv_scale[k];
+                    s2 += t * t;
                 }
+                if (PASS == 0 && s2 < sp.r2_lo) sure = true;          // certainly K > tau
+                else if (!(s2 > sp.r2_hi)) need = true;               // kept entry (PASS 1) or inside the margin
             }
-            unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (PASS == 1 && keep) {
-                int64_t o = base + count + __popc(m & ((1u << lane) - 1u));
-                indices[o] = j;
-                data[o] = val;
-                if (WITH_DK) ddata[o] = dval;
+            if (PASS == 0) count += __popc(__ballot_sync(0xffffffffu, sure));
+            const unsigned mn = __ballot_sync(0xffffffffu, need);
+            if (need) queue[qn + __popc(mn & ((1u << lane) - 1u))] = q;
+            qn += __popc(mn);
+            __syncwarp();
+            if (qn >= 32) {
+                const int qq = queue[lane];
+                const int rest = (lane < qn - 32) ? queue[32 + lane] : 0;
+                __syncwarp();
+                if (lane < qn - 32) queue[lane] = rest;
+                qn -= 32;
+                __syncwarp();
+                evaluate(qq, true);
             }
-            count += __popc(m);
         }
     }
+    if (qn > 0) evaluate(lane < qn ? queue[lane] : 0, lane < qn);
     if (PASS == 0 && lane == 0) devcount[i] = count;
 }
 
@@ -392,6 +433,9 @@ static int make_params(int64_t n, int64_t d, const double* scale_host, double nu
         sp->mp.sq2nu = sqrt(2.0 * nu);
     }
     double xr = support_radius(tau, nu);
+    sp->quick = (tau > 0.0 && tau < 1.0 && xr > 0.0 && xr < 1e100) ? 1 : 0;
+    sp->r2_lo = xr * xr * (1.0 - 4e-7);
+    sp->r2_hi = xr * xr * (1.0 + 4e-7);
     g->d = (int)d;
     g->ncells = 1;
     for (int k = 0; k < SMAXD; ++k) { g->nc[k] = 1; g->lo[k] = 0.0; g->inv_size[k] = 0.0; }
@@ -601,9 +645,37 @@ int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo
     return 0;
 }
 
+static int sort_rows_run(int64_t n, const int* indptr_dev, int* indices_dev, double* data_dev, double* ddata_dev, int* flags,
+                         cudaStream_t s) {
+    GP_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 2, s));
+    sort_rows_warp_kernel<<<148 * 4, 128, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, flags + 1);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    int ovf[2] = {0, 0};
+    GP_CUDA_CHECK(cudaMemcpyAsync(ovf, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (ovf[1]) {   // rows longer than WSORT_CAP exist: CTA-wide sort for those
+        sort_rows_kernel<<<148 * 8, 256, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, flags);
+        GP_COUNT(1);
+        GP_LAUNCH_CHECK();
+        GP_CUDA_CHECK(cudaMemcpyAsync(ovf, flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    if (ovf[0]) return -23;  // a row longer than SORT_CAP
+    return 0;
+}
+
+// Sorts every row of a CSR matrix by column index (values and optional derivative values follow): the canonical form.
+// flags_dev: 2 device ints of scratch.
+int gp_csr_sort_rows(int64_t n, const int* indptr_dev, int* indices_dev, double* data_dev, double* ddata_dev, int* flags_dev,
+                     void* stream) {
+    if (!indptr_dev || !indices_dev || !data_dev || !flags_dev || n <= 0 || n > INT32_MAX) return -1;
+    return sort_rows_run(n, indptr_dev, indices_dev, data_dev, ddata_dev, flags_dev, (cudaStream_t)stream);
+}
+
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
                           double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
-                          double* ddata_dev, void* stream) {
+                          double* ddata_dev, int sort_rows, void* stream) {
     if (!points || !points_host || !scale_host || !ws || !indptr_dev || !indices_dev || !data_dev || n <= 0 || d <= 0 || d > 8)
         return -1;
     if (ddata_dev)
@@ -652,20 +724,9 @@ int gp_matern_sparse_fill(const double* points, const double* points_host, int64
                                                              indices_dev, data_dev, ddata_dev);
         GP_COUNT(1);
     }
-    sort_rows_warp_kernel<<<148 * 4, 128, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow + 1);
-    GP_COUNT(1);
     GP_LAUNCH_CHECK();
-    int ovf[2] = {0, 0};
-    GP_CUDA_CHECK(cudaMemcpyAsync(ovf, w.overflow, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    if (sort_rows) return sort_rows_run(n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow, s);
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (ovf[1]) {   // rows longer than WSORT_CAP exist: CTA-wide sort for those
-        sort_rows_kernel<<<148 * 8, 256, 0, s>>>((int)n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow);
-        GP_COUNT(1);
-        GP_LAUNCH_CHECK();
-        GP_CUDA_CHECK(cudaMemcpyAsync(ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
-        GP_CUDA_CHECK(cudaStreamSynchronize(s));
-    }
-    if (ovf[0]) return -23;  // a row longer than SORT_CAP
     return 0;
 }
 

@@ -223,7 +223,7 @@ template <int R, int PASS>
 __global__ void __launch_bounds__(128)
 bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
                   const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
-                  int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals) {
+                  int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals, int* searched) {
     __shared__ int hkey[4][HCAP];
     __shared__ unsigned short hslot[4][HCAP];      // slots < HMAX + 32
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -287,6 +287,7 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
         }
     }
     if (overflow) {
+        if (searched && lane == 0) atomicExch(searched, 1);
         if (PASS == 1) {      // clear what the hash path wrote, then redo the block by searching
             const int64_t cnt = (bptr[rb + 1] - base) * R;
             for (int64_t i = lane; i < cnt; i += 32) {
@@ -605,13 +606,13 @@ int gp_bcsr_spmm(int64_t R, const int64_t* bptr, const int* bidx, const double* 
 template <int R>
 static int bcsr_build(int pass, int n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                       const double* data, const double* ddata, int* nblk, const int64_t* bptr, int* bidx, double* bvals,
-                      double* bdvals, cudaStream_t s) {
+                      double* bdvals, int* searched, cudaStream_t s) {
     const int nrb = (n + R - 1) / R;
     const unsigned blocks = (unsigned)(((int64_t)nrb * 32 + 127) / 128);
     if (pass == 0)
-        bcsr_build_kernel<R, 0><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
+        bcsr_build_kernel<R, 0><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, searched);
     else
-        bcsr_build_kernel<R, 1><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals);
+        bcsr_build_kernel<R, 1><<<blocks, 128, 0, s>>>(n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, searched);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
@@ -619,11 +620,11 @@ static int bcsr_build(int pass, int n, const int* order, const int* inv_order, c
 
 static int bcsr_build_any(int64_t R, int pass, int64_t n, const int* order, const int* inv_order, const int* indptr,
                           const int* indices, const double* data, const double* ddata, int* nblk, const int64_t* bptr,
-                          int* bidx, double* bvals, double* bdvals, void* stream) {
+                          int* bidx, double* bvals, double* bdvals, int* searched, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!indptr || !indices || n <= 0 || n > INT32_MAX || ((order == nullptr) != (inv_order == nullptr))) return -1;
     switch (R) {
-        case 8: return bcsr_build<8>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, s);
+        case 8: return bcsr_build<8>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, searched, s);
         default: return -3;
     }
 }
@@ -631,10 +632,11 @@ static int bcsr_build_any(int64_t R, int pass, int64_t n, const int* order, cons
 extern "C" {
 
 int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
-                  int* nblk, void* stream) {
+                  int* nblk, int* needs_sorted_dev, void* stream) {
     if (!nblk) return -1;
+    if (needs_sorted_dev) GP_CUDA_CHECK(cudaMemsetAsync(needs_sorted_dev, 0, sizeof(int), (cudaStream_t)stream));
     return bcsr_build_any(R, 0, n, order, inv_order, indptr, indices, nullptr, nullptr, nblk, nullptr, nullptr, nullptr, nullptr,
-                          stream);
+                          needs_sorted_dev, stream);
 }
 
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
@@ -643,7 +645,8 @@ int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, c
     if (!data || !bptr || !bidx || !bvals || (ddata && !bdvals) || nblocks < 0) return -1;
     GP_CUDA_CHECK(cudaMemsetAsync(bvals, 0, sizeof(double) * nblocks * R, (cudaStream_t)stream));
     if (ddata) GP_CUDA_CHECK(cudaMemsetAsync(bdvals, 0, sizeof(double) * nblocks * R, (cudaStream_t)stream));
-    return bcsr_build_any(R, 1, n, order, inv_order, indptr, indices, data, ddata, nullptr, bptr, bidx, bvals, bdvals, stream);
+    return bcsr_build_any(R, 1, n, order, inv_order, indptr, indices, data, ddata, nullptr, bptr, bidx, bvals, bdvals, nullptr,
+                          stream);
 }
 
 int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map, void* stream) {

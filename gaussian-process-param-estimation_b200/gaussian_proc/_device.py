@@ -48,11 +48,12 @@ SIGNATURES = {
     'gp_kernel_threshold': (_int, [_i64, _i64, _f64, _vp, _f64, _vp]),
     'gp_sparse_workspace_bytes': (_i64, [_i64, _i64]),
     'gp_matern_sparse_count': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
-    'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    'gp_csr_sort_rows': (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gp_csr_spmm': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp, _vp]),
     'gp_spatial_keys': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
-    'gp_bcsr_count': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gp_bcsr_count': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gp_bcsr_fill': (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'gp_bcsr_spmm': (_int, [_i64, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_gram_workspace_bytes': (_i64, [_i64]),

@@ -49,14 +49,28 @@ def estimate_kernel_threshold(matrix_size, dimension, density, correlation_scale
 
 
 class DeviceCSR(object):
-    """Canonical CSR (int32 indptr / sorted int32 indices, float64 data) resident on the GPU; `ddata` optionally holds
-    d/d(rho) of every stored entry on the same pattern."""
+    """CSR (int32 indptr / int32 indices, float64 data) resident on the GPU; `ddata` optionally holds d/d(rho) of every
+    stored entry on the same pattern. The device generator leaves the rows in generation order (``sorted_rows`` False):
+    the device operators do not need more; ``canonicalize()`` sorts every row by column - the reference's canonical CSR,
+    bit-exact pattern - and is called by ``to_scipy()`` / whenever a consumer needs sorted rows."""
 
-    def __init__(self, n, indptr, indices, data, ddata=None, kernel_threshold=None, order=None):
+    def __init__(self, n, indptr, indices, data, ddata=None, kernel_threshold=None, order=None, sorted_rows=True):
         self.n = int(n)
         self.indptr, self.indices, self.data, self.ddata = indptr, indices, data, ddata
         self.kernel_threshold = kernel_threshold
         self.order = order      # optional spatially local ordering of the rows (device int32), see SparseEngine
+        self.sorted_rows = bool(sorted_rows)
+
+    def canonicalize(self):
+        """sort every row by column index, in place (no-op when already sorted)"""
+        if not self.sorted_rows:
+            torch = dev.torch
+            flags = torch.zeros(2, dtype=torch.int32, device='cuda')
+            rc = lib.gp_csr_sort_rows(self.n, _p(self.indptr), _p(self.indices), _p(self.data),
+                                      _p(self.ddata) if self.ddata is not None else None, _p(flags), dev.stream_ptr())
+            check(rc, 'gp_csr_sort_rows')
+            self.sorted_rows = True
+        return self
 
     @property
     def shape(self):
@@ -78,14 +92,17 @@ class DeviceCSR(object):
                    torch.from_numpy(K.data.astype(numpy.float64)).cuda())
 
     def to_scipy(self):
+        self.canonicalize()
         return scipy.sparse.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
                                        shape=(self.n, self.n))
 
 
 def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=False, device=False,
-                                with_derivative=False, kernel_threshold=None):
+                                with_derivative=False, kernel_threshold=None, sort_rows=None):
     """Device generator behind the reference's generate_sparse_correlation. Returns scipy.sparse.csr_matrix (or a
-    DeviceCSR when ``device``)."""
+    DeviceCSR when ``device``). ``sort_rows``: canonical (column-sorted) rows right away; default: yes for the SciPy
+    result, deferred (DeviceCSR.canonicalize) for a device handle."""
+    sort_rows = (not device) if sort_rows is None else bool(sort_rows)
     torch = dev.require_cuda()
     points = numpy.ascontiguousarray(points, dtype=numpy.float64)
     scale = dev.host_f64(correlation_scale)
@@ -111,9 +128,10 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
     rc = lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
-                                   _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None, s)
+                                   _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None,
+                                   1 if sort_rows else 0, s)
     check(rc, 'gp_matern_sparse_fill')
-    K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order)
+    K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order, sorted_rows=sort_rows)
     if verbose:
         print('Generated sparse correlation matrix using kernel threshold: %0.4f and sparse density: %0.2e.'
               % (tau, K.nnz / float(n) ** 2))
@@ -174,7 +192,14 @@ class SparseEngine(object):
         nrb = (n + R - 1) // R
         nblk = torch.empty(nrb, dtype=torch.int32, device='cuda')
         s = dev.stream_ptr()
-        check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), s), 'gp_bcsr_count')
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), _p(flag), s),
+              'gp_bcsr_count')
+        if not K.sorted_rows and int(flag.item()) != 0:
+            # some row block is too wide for the hash path: its binary-search fallback needs canonical rows
+            K.canonicalize()
+            check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), _p(flag), s),
+                  'gp_bcsr_count')
         bptr = torch.zeros(nrb + 1, dtype=torch.int64, device='cuda')
         bptr[1:] = torch.cumsum(nblk, 0, dtype=torch.int64)
         total = int(bptr[-1].item())

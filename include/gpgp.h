@@ -78,9 +78,14 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
  * sort by key is the deterministic, spatially local row order the row-blocked sparse operator (gp_bcsr_*) uses. */
 int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo_host, const double* hi_host,
                     int64_t* keys_dev, void* stream);
+/* sort_rows = 1: canonical CSR (rows sorted by column). sort_rows = 0: rows are left in generation order - enough for
+ * the device operators (gp_csr_spmm, the hash path of gp_bcsr_*); gp_csr_sort_rows canonicalises later, on demand. */
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d,
                           const double* scale_host, double nu, double tau, void* ws, const int* indptr_dev,
-                          int* indices_dev, double* data_dev, double* ddata_dev, void* stream);
+                          int* indices_dev, double* data_dev, double* ddata_dev, int sort_rows, void* stream);
+/* Sorts every row of a CSR matrix by column (data / ddata follow); flags_dev: 2 device ints of scratch. */
+int gp_csr_sort_rows(int64_t n, const int* indptr_dev, int* indices_dev, double* data_dev, double* ddata_dev,
+                     int* flags_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Dense FP64 linear algebra on K + eta*I  (reference: _mixed_correlation/mixed_correlation.py:155-335 and
@@ -148,10 +153,12 @@ int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_
  * NULL: no permutation); the source rows must be sorted. With a spatially local order (gp_spatial_keys) neighbouring
  * rows have nearly the same pattern: one gathered row of X then serves R rows of K and the index is amortised.
  *   gp_bcsr_count: nblk[rb] = number of block-columns of row block rb (ceil(n/R) entries); the caller's exclusive
- *                  prefix sum gives bptr (int64, ceil(n/R)+1).
+ *                  prefix sum gives bptr (int64, ceil(n/R)+1). needs_sorted_dev (device int, may be NULL) is set to 1
+ *                  when some row block exceeded the shared-memory hash table and used the binary-search path, which
+ *                  requires SORTED source rows (the hash path does not).
  *   gp_bcsr_fill : nblocks = bptr[last]; bidx (int32, nblocks), bvals / bdvals (f64, R * nblocks, block-column major). */
 int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
-                  int* nblk, void* stream);
+                  int* nblk, int* needs_sorted_dev, void* stream);
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                  const double* data, const double* ddata, const int64_t* bptr, int64_t nblocks, int* bidx, double* bvals,
                  double* bdvals, void* stream);

@@ -40,9 +40,9 @@ def run():
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     t = tick('alloc', t)
-    lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws), _p(indptr), _p(indices), _p(data), _p(ddata), s)
-    t = tick('fill+sort', t)
-    K = S.DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order)
+    lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws), _p(indptr), _p(indices), _p(data), _p(ddata), 0, s)
+    t = tick('fill', t)
+    K = S.DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order, sorted_rows=False)
     e = S.SparseEngine(K, 'slq', {})
     t = tick('blocked_build', t)
     return T
