@@ -44,6 +44,11 @@ class FusedQuantities(object):
         self.trace_M = self.trace_Kninv - float(numpy.trace(self.Binv @ H[:m, :m]))
         self.trace_MdK = self.trace_Kninv_dK - float(numpy.trace(self.Binv @ Q[:m, :m]))
 
+    def set_trace_Kninv(self, value):
+        """tr Kn^-1 supplied from outside (the interpolated trace of a MixedCorrelation(interpolate=True))"""
+        self.trace_Kninv = float(value)
+        self.trace_M = self.trace_Kninv - float(numpy.trace(self.Binv @ self.H[:self.m, :self.m]))
+
 
 def _rhs_device(K_mixed, X, z):
     """[X z] zero-padded on the device, cached on the operator while X and z are the same objects."""
@@ -92,5 +97,11 @@ def finish(handle):
 
 
 def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
-    """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite."""
+    """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite.
+    With MixedCorrelation(interpolate=True) the trace of the inverse is the interpolated one
+    (mixed_correlation.py:167-170) and the evaluation skips the inverse it would otherwise need for it."""
+    if traceinv and getattr(K_mixed, 'interpolate', False) and not (inverse or drho):
+        q = finish(evaluate_async(z, X, K_mixed, eta, traceinv=False))
+        q.set_trace_Kninv(K_mixed.traceinv(eta))
+        return q
     return finish(evaluate_async(z, X, K_mixed, eta, traceinv=traceinv, inverse=inverse, drho=drho))

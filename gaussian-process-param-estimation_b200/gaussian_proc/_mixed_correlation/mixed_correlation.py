@@ -25,18 +25,19 @@ class MixedCorrelation(object):
     in __init__ like mixed_correlation.py:76-79 -- here with the cuSOLVER symmetric eigensolver behind
     torch.linalg.eigvalsh, a LIBRARY call (own kernel: next) -- after which logdet / traceinv / trace are
     O(n) reductions over lambda + eta; solves still use the native Cholesky engine.
-    ``interpolate=True`` raises NotImplementedError (imate.InterpolateTraceInv).
+    ``interpolate=True``: tr (K + eta I)^-1 is interpolated in eta from evaluations at ``interpolant_points``
+    (_interpolate_traceinv.py, the role of imate.InterpolateTraceInv; rational polynomial scheme, parity unpinned).
     """
 
     def __init__(self, K, interpolate=False, interpolant_points=None, imate_method='cholesky', imate_options={}):
         if interpolate:
             if interpolant_points is None:
                 raise TypeError('When "interpolate" is set to "True", the "interpolant_points" cannot be None.')
-            raise NotImplementedError('trace interpolation (imate.InterpolateTraceInv) is not part of this build.')
         self.interpolate = interpolate
         self.interpolant_points = interpolant_points
         self.imate_method = imate_method
         self.imate_options = dict(imate_options)
+        self.interpolate_traceinv = None      # built on first use (evaluates traceinv at the interpolant points)
         self.sparse = False
 
         if scipy.sparse.issparse(K) or type(K).__name__ == 'DeviceCSR':
@@ -89,6 +90,16 @@ class MixedCorrelation(object):
 
     def traceinv(self, eta, exponent=1):
         """mixed_correlation.py:155-215"""
+        if self.interpolate and exponent == 1:                                          # :167-170
+            if self.interpolate_traceinv is None:
+                from ._interpolate_traceinv import InterpolateTraceInv
+                self.interpolate_traceinv = InterpolateTraceInv(
+                    lambda t: self._traceinv_direct(t, 1), self.K.shape[0], self.interpolant_points,
+                    self.imate_options.get('interpolation_method', 'RPF'))
+            return self.interpolate_traceinv.interpolate(eta)
+        return self._traceinv_direct(eta, exponent)
+
+    def _traceinv_direct(self, eta, exponent=1):
         if not self.sparse and self.imate_method == 'eigenvalue':
             return float(((self.K_eigenvalues + eta) ** (-exponent)).sum().item())     # :172-181
         return self.engine.traceinv(eta, exponent)

@@ -345,3 +345,27 @@ def test_eigenvalue_method_matches_reference_vectors(gp, golden_likelihood):
     lk = Likelihood(X, K, likelihood_method='direct', imate_method='eigenvalue')
     assert rel(lk.likelihood(z, h), g['c1_eigenvalue_direct_ll'][0]) <= RTOL
     assert rel(DirectLikelihood.log_likelihood_hessian(z, X, Km, False, h), g['c1_eigenvalue_direct_hess'][0]) <= 1e-8
+
+
+def test_trace_interpolation_through_mixed_correlation(gp, problem):
+    """MixedCorrelation(interpolate=True, interpolant_points=...) (mixed_correlation.py:52-66,167-170): traceinv is
+    interpolated from Cholesky evaluations at the interpolant points; d l^/d eta with the interpolated trace stays within
+    the interpolation error of the exact one, and its root is found by the unchanged driver."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    pts, z, X = problem[:3]
+    K = gp.generate_correlation(pts, 0.1, 0.5, device=True)
+    P = [1e-2, 1e-1, 1.0, 10.0, 100.0]
+    Ki = MixedCorrelation(K, interpolate=True, interpolant_points=P)
+    Ke = MixedCorrelation(K)
+    for eta in (0.03, 0.5, 4.0, 60.0):
+        a, b = Ki.traceinv(eta), Ke.traceinv(eta)
+        assert abs(a - b) <= 2e-2 * abs(b)
+    for eta in P:
+        assert abs(Ki.traceinv(eta) - Ke.traceinv(eta)) <= 1e-9 * abs(Ke.traceinv(eta))
+    with pytest.raises(TypeError):
+        MixedCorrelation(K, interpolate=True)
+    n, m = X.shape
+    d_i = ProfileLikelihood.log_likelihood_der1_eta(z, X, Ki, numpy.log10(0.5))
+    d_e = ProfileLikelihood.log_likelihood_der1_eta(z, X, Ke, numpy.log10(0.5))
+    assert abs(d_i - d_e) <= 0.5 * 2e-2 * abs(Ke.traceinv(0.5)) + 1e-9

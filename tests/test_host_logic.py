@@ -101,3 +101,41 @@ def test_bench_inputs_equal_reference_generators():
     p2 = numpy.random.rand(400, 2)
     assert (pts == p2).all() and (z == du.generate_data(p2, 0.2)).all()
     assert numpy.max(numpy.abs(X - du.generate_basis_functions(p2, 2))) == 0.0
+
+
+def test_trace_interpolation_rational_polynomial():
+    """MixedCorrelation(interpolate=True) (reference mixed_correlation.py:52-66,167-170 -> imate.InterpolateTraceInv):
+    the rational-polynomial interpolant reproduces tr (K + eta I)^-1 at the interpolant points exactly and to a few
+    1e-3 in between (legacy points of examples/CompareVariousNumberOfPoints.py:68); parity unpinned (imate absent)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        'itp', os.path.join(root, 'gaussian-process-param-estimation_b200', 'gaussian_proc', '_mixed_correlation',
+                            '_interpolate_traceinv.py'))
+    itp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(itp)
+    from oracle import matern
+    numpy.random.seed(0)
+    pts = numpy.random.rand(400, 2)
+    lam = numpy.linalg.eigvalsh(matern.generate_dense_correlation(pts, numpy.array([0.1, 0.1]), 0.5))
+    calls = []
+
+    def exact(eta):
+        calls.append(eta)
+        return float(numpy.sum(1.0 / (lam + eta)))
+
+    P = [1.0, 10.0, 40.0, 100.0, 1000.0]
+    it = itp.InterpolateTraceInv(exact, 400, P)
+    assert sorted(calls) == P                                   # one evaluation per interpolant point
+    for t in P:
+        assert it.interpolate(t) == exact(t)
+    etas = numpy.logspace(0, 3, 40)
+    err = numpy.abs(it.interpolate(etas) - numpy.array([exact(e) for e in etas])) / numpy.array([exact(e) for e in etas])
+    assert err.max() <= 5e-3
+    n_calls = len(calls)
+    assert abs(it.interpolate(0.5) - exact(0.5)) == 0.0 and len(calls) == n_calls + 2     # below the anchor: direct
+    six = itp.InterpolateTraceInv(exact, 400, [1.0, 5.0, 10.0, 40.0, 100.0, 1000.0])      # q = 5: least squares
+    assert abs(six.interpolate(20.0) - exact(20.0)) <= 1e-2 * exact(20.0)
+    with pytest.raises(ValueError):
+        itp.InterpolateTraceInv(exact, 400, [1.0, 2.0])
