@@ -173,6 +173,11 @@ __device__ __forceinline__ int find_col(const int* __restrict__ row, int len, in
 // the same layout, so both paths write identical output.
 constexpr int HCAP = 2048, HMAX = 1536;
 
+// Position of (block-column slot, row k) in the value stream: groups of four block-columns are stored in DMMA A-fragment
+// order [row][block-column in group] so that lane (g, t) of the SpMM warp reads 32 consecutive doubles (bptr entries are
+// multiples of 4, R = 8).
+__device__ __forceinline__ int64_t bval_pos(int64_t slot, int k) { return (slot >> 2) * 32 + k * 4 + (slot & 3); }
+
 template <int R, int PASS>
 __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s, const int* len, const int* __restrict__ inv_order,
                                                  const int* __restrict__ indices, const double* __restrict__ data,
@@ -207,10 +212,10 @@ __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s,
                     }
                 }
 #pragma unroll
-                for (int kk = 0; kk < R; ++kk) bvals[slot * R + kk] = v[kk];
+                for (int kk = 0; kk < R; ++kk) bvals[bval_pos(slot, kk)] = v[kk];
                 if (ddata) {
 #pragma unroll
-                    for (int kk = 0; kk < R; ++kk) bdvals[slot * R + kk] = dv[kk];
+                    for (int kk = 0; kk < R; ++kk) bdvals[bval_pos(slot, kk)] = dv[kk];
                 }
             }
             running += __popc(m);
@@ -221,7 +226,8 @@ __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s,
 
 template <int R, int PASS>
 __global__ void __launch_bounds__(128)
-bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
+bcsr_build_kernel(  // R == 8: bval_pos is the 8-row fragment layout
+    int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
                   const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
                   int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals, int* searched) {
     __shared__ int hkey[4][HCAP];
@@ -279,7 +285,7 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
             __syncwarp();
             if (running > HMAX) overflow = true;
             if (PASS == 1 && valid && !overflow) {
-                const int64_t o = (base + slot) * R + k;
+                const int64_t o = bval_pos(base + slot, k);
                 bvals[o] = data[s[k] + t];
                 if (ddata) bdvals[o] = ddata[s[k] + t];
                 if (isnew) bidx[base + slot] = inv_order ? inv_order[c] : c;
@@ -306,8 +312,8 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
         bidx[slot] = inv_order ? inv_order[c0] : c0;
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) {
-            bvals[slot * R + kk] = 0.0;
-            if (ddata) bdvals[slot * R + kk] = 0.0;
+            bvals[bval_pos(slot, kk)] = 0.0;
+            if (ddata) bdvals[bval_pos(slot, kk)] = 0.0;
         }
     }
 }
@@ -338,7 +344,7 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
     const bool colok = (B >= 8) || (g < B);
     const int coff = (B >= 8) ? g * NT : (colok ? g : 0);
-    const double* aptr = bvals + g + t * 8;
+    const double* aptr = bvals + lane;          // A fragment order: element (row g, block-column t) at 4 g + t = lane
     auto load_x = [&](int col, double* x) {
         const double* xr = X + (int64_t)col * B + coff;
         if (NT == 1) {

@@ -156,7 +156,8 @@ int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_
  *                  prefix sum gives bptr (int64, ceil(n/R)+1). needs_sorted_dev (device int, may be NULL) is set to 1
  *                  when some row block exceeded the shared-memory hash table and used the binary-search path, which
  *                  requires SORTED source rows (the hash path does not).
- *   gp_bcsr_fill : nblocks = bptr[last]; bidx (int32, nblocks), bvals / bdvals (f64, R * nblocks, block-column major). */
+ *   gp_bcsr_fill : nblocks = bptr[last]; bidx (int32, nblocks), bvals / bdvals (f64, R * nblocks): every group of four
+ *                  block-columns is stored in DMMA A-fragment order, value (slot s, row k) at 32 (s/4) + 4 k + s%4. */
 int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                   int* nblk, int* needs_sorted_dev, void* stream);
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,

@@ -52,7 +52,7 @@ for eta in etas:
         t, ld = timed(lambda: eng.logdet(eta))
         t2, tr = timed(lambda: eng.traceinv_dK(eta))
     out['slq_eta%g' % eta] = {'t_s': t, 'logdet': ld, 'info': {k: (v.tolist() if hasattr(v, 'tolist') else v) for k, v in eng.last_info.items()}}
-    out['hutch_dK_eta%g' % eta] = {'t_s': t2, 'value': tr, 'cg_iters': eng.last_cg_iterations, 'samples': eng.last_info['num_samples']}
+    out['hutch_dK_eta%g' % eta] = {'t_s': t2, 'value': tr, 'cg_iters': getattr(eng, 'last_cg_iterations', None), 'dk_solver': getattr(eng, 'last_dk_solver', None), 'samples': eng.last_info['num_samples']}
     out['evals_per_s_eta%g' % eta] = 1.0 / (t + t2)
 # raw driver timings (CUDA events): one 30-step Lanczos and one CG solve at B = 16
 V = eng.probes(0, 16)
