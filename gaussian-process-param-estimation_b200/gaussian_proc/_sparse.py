@@ -34,6 +34,9 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_RHS_DEVICE_CACHE = []      # [(key, device block, X, z)]: see SparseEngine._rhs_block
+
+
 def estimate_kernel_threshold(matrix_size, dimension, density, correlation_scale, nu):
     """tau for the requested density (_generate_sparse_correlation.pyx:294-413); ValueError when density*n < 1."""
     tau = ctypes.c_double()
@@ -522,23 +525,34 @@ class SparseEngine(object):
         return out.cpu().numpy().reshape(B, B)
 
     def _rhs_block(self, X, z):
-        """[X z] as an operator-space device block, zero padded to a power-of-two width; cached per (X, z)."""
+        """[X z] as an operator-space device block, zero padded to a power-of-two width. The device copy in the original
+        row order is cached per (X, z) objects across engines (an optimiser builds a new operator for every rho but
+        keeps X and z); the operator-space permutation of it is cached per engine."""
         torch = dev.torch
         key = (id(X), id(z))
         if getattr(self, '_rhs_cache', None) is not None and self._rhs_cache[0] == key:
             return self._rhs_cache[1]
-        R = numpy.c_[numpy.asarray(X, dtype=float), numpy.asarray(z, dtype=float)]
-        p = R.shape[1]
-        B = 1
-        while B < p:
-            B *= 2
-        if B > 16:
-            raise ValueError('the sparse likelihood evaluation supports at most 15 basis functions.')
-        Rd = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
-        Rd[:, :p].copy_(torch.from_numpy(numpy.ascontiguousarray(R)))
-        Rd = self.to_op(Rd)
-        self._rhs_cache = (key, Rd, X, z)
-        return Rd
+        Rd = None
+        for ent in _RHS_DEVICE_CACHE:
+            if ent[0] == key and ent[1].shape[0] == self.n:
+                Rd = ent[1]
+        if Rd is None:
+            X2 = numpy.asarray(X, dtype=float)
+            p = X2.shape[1] + 1
+            B = 1
+            while B < p:
+                B *= 2
+            if B > 16:
+                raise ValueError('the sparse likelihood evaluation supports at most 15 basis functions.')
+            R = numpy.zeros((self.n, B))
+            R[:, :p - 1] = X2
+            R[:, p - 1] = numpy.asarray(z, dtype=float)
+            Rd = torch.from_numpy(R).cuda()
+            _RHS_DEVICE_CACHE.append((key, Rd, X, z))       # X, z kept alive so the ids stay unique
+            del _RHS_DEVICE_CACHE[:-2]
+        Rop = self.to_op(Rd)
+        self._rhs_cache = (key, Rop, X, z)
+        return Rop
 
     def fused(self, eta, X, z, traceinv=True, drho=True):
         """Everything log-likelihood + gradient need at one eta, in the layout of the dense evaluator's out[]
