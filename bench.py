@@ -272,6 +272,46 @@ def secondary_measurements():
     lgr = loglik_grad()
     torch.cuda.synchronize()
     tl = time.perf_counter() - t0
+    # CPU comparator for the sparse leg, bounded (~15 s): the reference's compiled brute-force generator (O(n^2)) at
+    # n = 2^13 extrapolated with n^2, and the operation its SLQ / CG estimators are built on - SciPy's CSR x dense-block
+    # product with the same number of non-zeros per row - at n = 2^17 extrapolated linearly in nnz.
+    cpu = {}
+    try:
+        from oracle import matern as omat
+        ns = 2 ** 13
+        fac = float(n) / ns
+        psub = sp[:ns] * 1.0
+        args_s = (numpy.array([0.005, 0.005]) * numpy.sqrt(fac), 0.5, 1e-3 * fac)
+        kind = 'port (oracle/cmatern.c)'
+        gen = lambda: omat.generate_sparse_correlation(psub, *args_s)   # noqa: E731
+        try:
+            from oracle import ref_loader
+            cy = ref_loader.load_cython()
+            gen = lambda: cy.generate_sparse_correlation(psub, args_s[0], args_s[1], args_s[2], False)   # noqa: E731
+            kind = 'reference (compiled Cython generator)'
+        except Exception:  # noqa: BLE001
+            pass
+        t0 = time.perf_counter()
+        Ks = gen()
+        tgs = time.perf_counter() - t0
+        nm = 2 ** 17
+        fm = float(n) / nm
+        Km_host = generate_sparse_correlation(sp[:nm] * 1.0, numpy.array([0.005, 0.005]) * numpy.sqrt(fm), 0.5, 1e-3 * fm)
+        Vh = numpy.random.randn(nm, 16)
+        Km_host @ Vh
+        t0 = time.perf_counter()
+        for _ in range(3):
+            Km_host @ Vh
+        tsp = (time.perf_counter() - t0) / 3 * (nnz / float(Km_host.nnz))
+        n_spmm16, n_spmm8 = 31, 25
+        cpu = {'kind': kind, 'cores': os.cpu_count(),
+               'generate_s_extrapolated': tgs * fac ** 2, 'generate_sample': 'n=%d in %.2f s, x (n/ns)^2' % (ns, tgs),
+               'spmm_B16_s_extrapolated': tsp, 'spmm_sample': 'scipy CSR @ (n x 16) at n=%d, nnz=%d, x nnz ratio' % (nm, Km_host.nnz),
+               'loglik_grad_s_new_rho_extrapolated': tgs * fac ** 2 + (n_spmm16 + 0.5 * n_spmm8) * tsp,
+               'note': 'the reference has no working sparse likelihood path (SURVEY Q6, Q8, Q9); this is its generator '
+                       'plus %d B=16 and %d B=8 SciPy products, the SpMM count of one evaluation here' % (n_spmm16, n_spmm8)}
+    except Exception as exc:  # noqa: BLE001
+        cpu = {'unavailable': repr(exc)[:200]}
     out['sparse_n1M'] = {'workload': 'configs[3]: n=2^20 random 2-D points, nu=0.5, rho=0.005, density=1e-3, eta=10',
                          'nnz': nnz, 'generate_s': tg, 'generate_GBs': (20.0 * nnz + 4.0 * (n + 1)) / tg * 1e-9,
                          'row_blocked_build_s': tb, 'row_blocked_fill_ratio': fill,
@@ -282,7 +322,7 @@ def secondary_measurements():
                                  'Hutchinson/CG tr(Kn^-1 dK/drho); new_rho adds CSR generation and the row-blocked build; loglik_grad = the '
                                  'whole profile likelihood + gradient through the public API (adds the CG solves for [X z], m = 6)',
                          'logdet': ld, 'logdet_half_width': float(info['half_width'][0]), 'num_samples': info['num_samples'],
-                         'traceinv': ti, 'trace_Kninv_dK': tr}
+                         'traceinv': ti, 'trace_Kninv_dK': tr, 'cpu_comparator': cpu}
     return out
 
 
