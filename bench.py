@@ -5,7 +5,8 @@ bench.py -- headline benchmark of the GP log-likelihood hot path on B200.
 Metric (BASELINE.json): log-likelihood + gradient evaluations per second, dense Matern nu = 2.5, n = 20 000 random 2-D
 points (configs[1]), FP64. One STEP = one evaluation at a new (eta, rho): Matern correlation generation for that rho,
 one blocked Cholesky of K + eta I, the solves for [X z], the inverse for the traces, and every reduction needed for
-l^, d l^/d eta and d l^/d rho (n^3 flop).
+l^, d l^/d eta and d l^/d rho (n^3 flop). --cells-in-flight (default 2) independent evaluations are in
+flight per GPU, each with its own buffers and CUDA stream; exactly K steps complete inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (under torchrun for N > 1: one rank per
                                                                 GPU, independent (eta, rho) cells per rank, weak scaling,
@@ -355,21 +356,41 @@ def run_ours(args):
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
     # ---- resident inputs -------------------------------------------------------------------------------------
+    # `cells_in_flight` independent evaluations are kept in flight per GPU, each with its own K buffer / scratch and its
+    # own CUDA stream (the latency-bound phases of one evaluation - diagonal blocks, small recursion levels, the
+    # HBM-bound reductions - are filled by the GEMMs of another; the grid sweep does the same, gaussian_proc/sweep.py)
     dpts = torch.from_numpy(pts).cuda()
-    Kbuf = torch.empty((npad, npad), dtype=torch.float64, device='cuda')
-    Kdev = DeviceCorrelation(n, Kbuf, points=dpts, correlation_scale=numpy.array([0.1, 0.1]), nu=NU)
-    eng = DenseEngine(Kdev)
-    R, _ = eng.pad_rhs(numpy.c_[X, z])
+    C = max(1, int(args.cells_in_flight))
+    slots = []
+    for c in range(C):
+        Kbuf = torch.empty((npad, npad), dtype=torch.float64, device='cuda')
+        Kdev = DeviceCorrelation(n, Kbuf, points=dpts, correlation_scale=numpy.array([0.1, 0.1]), nu=NU)
+        slots.append({'Kbuf': Kbuf, 'Kdev': Kdev, 'eng': DenseEngine(Kdev), 'stream': torch.cuda.Stream()})
+    R, _ = slots[0]['eng'].pad_rhs(numpy.c_[X, z])
     flags = FLAG_TRACEINV | FLAG_INVERSE | FLAG_DRHO
     results = []
+    counter = [0]
 
     def step(idx):
         eta, rho = cell(idx)
         scale = numpy.array([rho, rho])
-        Kdev.correlation_scale = scale
-        dev.check(lib.gp_matern_dense(P(dpts), n, 2, dev.host_ptr(scale), NU, P(Kbuf), npad, None, dev.stream_ptr()),
-                  'gp_matern_dense')
-        results.append(eng.fused(eta, R, p, flags))
+        sl = slots[counter[0] % C]
+        counter[0] += 1
+        with torch.cuda.stream(sl['stream']):
+            sl['Kdev'].correlation_scale = scale
+            dev.check(lib.gp_matern_dense(P(dpts), n, 2, dev.host_ptr(scale), NU, P(sl['Kbuf']), npad, None,
+                                          dev.stream_ptr()), 'gp_matern_dense')
+            results.append(sl['eng'].fused(eta, R, p, flags))
+
+    def fork():
+        cur = torch.cuda.current_stream()
+        for sl in slots:
+            sl['stream'].wait_stream(cur)
+
+    def join():
+        cur = torch.cuda.current_stream()
+        for sl in slots:
+            cur.wait_stream(sl['stream'])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -377,8 +398,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for w in range(args.warmup):
+    fork()
+    for w in range(max(args.warmup, C)):
         step(w * world + rank)
+    join()
+    torch.cuda.synchronize()
     results.clear()
 
     sampler = ClockSampler(local)
@@ -389,8 +413,10 @@ def run_ours(args):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for s in range(args.steps):
         step((args.warmup + s) * world + rank)
+    join()
     stacked = torch.stack(results)
     if world > 1:
         gathered = [torch.empty_like(stacked) for _ in range(world)]
@@ -445,30 +471,41 @@ def run_ours(args):
                 'step_tflops': alg_flops / (ms / args.steps * 1e-3) * 1e-12}
 
     # ---- end-to-end through the public API with host (pinned) buffers ----------------------------------------------
-    del eng, Kdev, Kbuf, results, stacked
+    del slots, results, stacked, Kbuf, Kdev
     torch.cuda.empty_cache()
     pin = lambda a: torch.from_numpy(numpy.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     hp, hz, hX = pin(pts), pin(z), pin(X)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2 * C, min(args.steps, 6))
+    streams = [torch.cuda.Stream() for _ in range(C)]
 
-    def e2e_step(idx):
-        eta, rho = cell(idx)
-        K = generate_correlation(hp, rho, NU, device=True)                 # H2D: points
-        Km = MixedCorrelation(K)
-        return ProfileLikelihood.log_likelihood_and_gradient(hz, hX, Km, eta)   # H2D: [X z]; D2H: out[]
-    e2e_step(rank)
+    def e2e_run(first, count):
+        """`count` evaluations through the public API, C in flight (log_likelihood_and_gradient_async returns a
+        completion callable; its result is read back - D2H of out[] - when the slot is needed again)"""
+        pending, last = [], None
+        for k in range(count):
+            eta, rho = cell((first + k) * world + rank)
+            if len(pending) >= C:
+                last = pending.pop(0)()
+            with torch.cuda.stream(streams[k % C]):
+                K = generate_correlation(hp, rho, NU, device=True)                 # H2D: points
+                Km = MixedCorrelation(K)
+                pending.append(ProfileLikelihood.log_likelihood_and_gradient_async(hz, hX, Km, eta))   # H2D: [X z]
+        for fin in pending:
+            last = fin()                                                           # D2H: out[]
+        return last
+    e2e_run(0, C)
     sync_all()
     t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        r = e2e_step((1 + s) * world + rank)
+    r = e2e_run(C, e2e_steps)
     sync_all()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = {'value': e2e_steps * world / float(e2e_s.item()), 'unit': UNIT, 'steps': e2e_steps,
            'h2d_bytes_per_step': int(hp.nbytes + npad * p * 8), 'd2h_bytes_per_step': int((8 + 3 * p * p) * 8),
+           'cells_in_flight': C,
            'api': 'generate_correlation(points, rho, nu, device=True) -> MixedCorrelation(K) -> '
-                  'ProfileLikelihood.log_likelihood_and_gradient(z, X, K_mixed, eta)',
+                  'ProfileLikelihood.log_likelihood_and_gradient_async(z, X, K_mixed, eta)() ',
            'last_result': [float(v) for v in r]}
 
     if rank == 0:
@@ -478,7 +515,8 @@ def run_ours(args):
                 'config': {'workload': 'configs[1]: dense Matern nu=2.5, n=%d random 2-D points (seed 0), m=6 (Poly-2 basis), '
                                        'one (eta, rho) cell per step per GPU, eta in {1e-2,1e-1,1,10}, rho ~ 0.1' % n,
                            'l2': 'inputs larger than L2 (K = %.1f GB per evaluation)' % (npad * npad * 8e-9),
-                           'parallelism': 'independent cells per GPU (replicas), results all-gathered'},
+                           'parallelism': 'independent cells per GPU (replicas), results all-gathered',
+                           'cells_in_flight': C},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
         if world == 1 and not args.no_secondary:
             del hp, hz, hX
@@ -500,6 +538,8 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cells-in-flight', type=int, default=2,
+                    help='independent evaluations kept in flight per GPU (own buffers and stream each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-secondary', action='store_true', help='skip the sparse / sweep secondary measurements')
     args = ap.parse_args()

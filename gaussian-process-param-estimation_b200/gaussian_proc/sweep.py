@@ -63,7 +63,7 @@ class _GpuRowEvaluator(object):
         return out
 
 
-def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=2):
+def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
     on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
     `concurrency` cells in flight per GPU."""
