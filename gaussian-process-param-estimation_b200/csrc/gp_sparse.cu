@@ -10,6 +10,7 @@
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_matern.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 #include <vector>
 
@@ -138,13 +139,18 @@ __global__ void cell_histogram_kernel(const double* __restrict__ pts, int n, int
     atomicAdd(&cell_cnt[id], 1);
 }
 
-__global__ void cell_scatter_kernel(const double* __restrict__ pts, int n, int d, const int* cell_of, const int* cell_start,
-                                    int* cell_fill, int* sorted_idx, double* sorted_pts) {
+// The points of a cell are kept in ORIGINAL index order (stable radix sort of the cell ids): the generation order of
+// every row - and with it the row-blocked operator and every estimate - is the same in every run.
+__global__ void iota_kernel(int n, int* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int id = cell_of[i];
-    int pos = cell_start[id] + atomicAdd(&cell_fill[id], 1);
-    sorted_idx[pos] = i;
+    if (i < n) out[i] = i;
+}
+
+__global__ void gather_points_kernel(const double* __restrict__ pts, int n, int d, const int* __restrict__ sorted_idx,
+                                     double* sorted_pts) {
+    int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    int i = sorted_idx[pos];
     for (int k = 0; k < d; ++k) sorted_pts[(int64_t)pos * d + k] = pts[(int64_t)i * d + k];
 }
 
@@ -386,7 +392,9 @@ sort_rows_kernel(int n, const int* __restrict__ indptr, int* indices, double* da
 
 // workspace carving (all int32 / f64 device arrays)
 struct SparseWs {
-    int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow;
+    int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow, *cell_sorted, *iota;
+    void* sort_temp;
+    size_t sort_temp_bytes;
     int2* border;
     int *ei, *ej, *eslot;
     double *ev, *edv, *sorted_pts;
@@ -413,6 +421,10 @@ static SparseWs carve_sparse(void* ws, int64_t n, int64_t d) {
     w.ev = (double*)take(sizeof(double) * BORDER_CAP);
     w.edv = (double*)take(sizeof(double) * BORDER_CAP);
     w.sorted_pts = (double*)take(sizeof(double) * n * d);
+    w.cell_sorted = (int*)take(sizeof(int) * n);
+    w.iota = (int*)take(sizeof(int) * n);
+    w.sort_temp_bytes = (size_t)n * 16 + (8u << 20);      // radix sort scratch (alternate key/value buffers + histograms)
+    w.sort_temp = (void*)take(w.sort_temp_bytes);
     w.total = off;
     return w;
 }
@@ -571,9 +583,18 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
     for (int c = 0; c < g.ncells; ++c) cs[c + 1] += cs[c];
     GP_CUDA_CHECK(cudaMemcpyAsync(w.cell_start, cs.data(), sizeof(int) * (g.ncells + 1), cudaMemcpyHostToDevice, s));
-    cell_scatter_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, w.cell_of, w.cell_start, w.cell_fill, w.sorted_idx,
-                                                        w.sorted_pts);
-    GP_COUNT(1);
+    {
+        int bits = 1;
+        while ((1 << bits) < g.ncells && bits < 31) ++bits;
+        size_t need = 0;
+        GP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, w.cell_of, w.cell_sorted, w.iota, w.sorted_idx, N, 0, bits, s));
+        if (need > w.sort_temp_bytes) return -24;
+        iota_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, w.iota);
+        GP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_temp, need, w.cell_of, w.cell_sorted, w.iota, w.sorted_idx, N, 0, bits,
+                                                      s));
+        gather_points_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, w.sorted_idx, w.sorted_pts);
+        GP_COUNT(3);
+    }
     launch_rows_mode(matern_mode_of(nu), 0, false, sp, g, w, nullptr, nullptr, nullptr, nullptr, s);
     GP_LAUNCH_CHECK();
     std::vector<int> cnt(n);

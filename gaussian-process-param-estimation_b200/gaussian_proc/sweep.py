@@ -63,15 +63,43 @@ class _GpuRowEvaluator(object):
         return out
 
 
-def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4):
+class _GpuSparseRowEvaluator(object):
+    """All eta cells of one rho for the kernel-threshold sparse correlation: the CSR matrix and its row-blocked
+    operator are generated once per rho; every eta is one stochastic evaluation (batched SLQ + CG, _sparse.py)."""
+
+    def __init__(self, points, z, X, nu, density, imate_options):
+        from . import _device as dev
+        dev.require_cuda()
+        self.points = numpy.ascontiguousarray(points, dtype=float)
+        self.z, self.X, self.nu, self.density = z, X, float(nu), float(density)
+        self.options = dict(imate_options or {})
+
+    def row(self, rho, etas):
+        from ._sparse import generate_sparse_correlation
+        from ._mixed_correlation import MixedCorrelation
+        from ._likelihood import ProfileLikelihood
+        K = generate_sparse_correlation(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu, self.density,
+                                        device=True, with_derivative=True)
+        Km = MixedCorrelation(K, imate_method='slq', imate_options=self.options)
+        return numpy.array([ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta) for eta in etas])
+
+
+def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, sparse=False, density=1e-3,
+                    imate_options=None):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
     on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
-    `concurrency` cells in flight per GPU."""
+    `concurrency` cells in flight per GPU (dense), or, with ``sparse``, the stochastic evaluator on the kernel-threshold
+    correlation of the given ``density`` (``imate_options``: estimator settings, see _sparse.DEFAULTS)."""
     rhos = numpy.asarray(rhos, dtype=float)
     etas = numpy.asarray(etas, dtype=float)
     rank, world = gpd.rank_world()
     begin, end = gpd.partition_cells(len(rhos), world, rank)
-    rows = None if evaluate is not None else _GpuRowEvaluator(points, z, X, nu, concurrency)
+    if evaluate is not None:
+        rows = None
+    elif sparse:
+        rows = _GpuSparseRowEvaluator(points, z, X, nu, density, imate_options)
+    else:
+        rows = _GpuRowEvaluator(points, z, X, nu, concurrency)
     local = numpy.empty(((end - begin) * len(etas), 5))
     k = 0
     for i in range(begin, end):

@@ -341,3 +341,19 @@ def test_internal_permutation_does_not_change_results(sparse_problem):
     assert numpy.max(numpy.abs(a.matmul(X) - b.matmul(X))) <= 1e-12
     Va = a.from_op(a.probes(0, 4)).cpu().numpy()
     assert (Va == b.probes(0, 4).cpu().numpy()).all()
+
+
+def test_sparse_grid_sweep(sparse_problem):
+    """likelihood_grid(sparse=True): every cell equals the direct public-API evaluation at the same seed."""
+    from gaussian_proc.sweep import likelihood_grid
+    from gaussian_proc._sparse import generate_sparse_correlation
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    pts, z, X, _ = sparse_problem
+    opts = {'seed': 1, 'lanczos_degree': 25, 'min_num_samples': 16, 'max_num_samples': 16}
+    rhos, etas = [0.025, 0.03], [2.0, 20.0]
+    G = likelihood_grid(pts, z, X, 0.5, rhos, etas, sparse=True, density=0.01, imate_options=opts)
+    assert G.shape == (2, 2, 3) and numpy.isfinite(G).all()
+    K = generate_sparse_correlation(pts, numpy.array([0.03, 0.03]), 0.5, 0.01, device=True, with_derivative=True)
+    ref = ProfileLikelihood.log_likelihood_and_gradient(z, X, MixedCorrelation(K, imate_method='slq', imate_options=opts), 20.0)
+    assert numpy.allclose(G[1, 1], ref, rtol=1e-12, atol=0)

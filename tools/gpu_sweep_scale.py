@@ -19,15 +19,24 @@ from gaussian_proc.sweep import likelihood_grid
 n_rho = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n_eta = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 8000
+sparse = len(sys.argv) > 4 and sys.argv[4] == 'sparse'
 pts, z, X = make_inputs(n)
-rhos = numpy.linspace(0.05, 0.3, n_rho)
-etas = numpy.logspace(-2, 2, n_eta)
-likelihood_grid(pts, z, X, 2.5, rhos[:world], etas[:4])            # warm-up: one small row per rank
+kw = {}
+if sparse:      # configs[3] family: nu = 0.5, rho around 0.005, density 1e-3, eta >= 10 (hard-thresholded K is indefinite)
+    rhos = numpy.linspace(0.004, 0.006, n_rho) * numpy.sqrt(2 ** 20 / float(n))
+    etas = numpy.logspace(1, 3, n_eta)
+    nu = 0.5
+    kw = dict(sparse=True, density=1e-3 * 2 ** 20 / float(n), imate_options={'seed': 0, 'lanczos_degree': 30})
+else:
+    rhos = numpy.linspace(0.05, 0.3, n_rho)
+    etas = numpy.logspace(-2, 2, n_eta)
+    nu = 2.5
+likelihood_grid(pts, z, X, nu, rhos[:world], etas[:min(4, n_eta)], **kw)            # warm-up: one small row per rank
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-G = likelihood_grid(pts, z, X, 2.5, rhos, etas)
+G = likelihood_grid(pts, z, X, nu, rhos, etas, **kw)
 torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
 if world > 1:
@@ -35,8 +44,8 @@ if world > 1:
 dt = float(dt.item())
 if rank == 0:
     i, j = numpy.unravel_index(numpy.nanargmax(G[:, :, 0]), G[:, :, 0].shape)
-    print(json.dumps({'world': world, 'n': n, 'cells': n_rho * n_eta, 'seconds': dt, 'cells_per_s': n_rho * n_eta / dt,
-                      'tflops_total': n_rho * n_eta * float(n) ** 3 / dt * 1e-12, 'finite': bool(numpy.isfinite(G).all()),
+    print(json.dumps({'world': world, 'n': n, 'sparse': sparse, 'cells': n_rho * n_eta, 'seconds': dt, 'cells_per_s': n_rho * n_eta / dt,
+                      'tflops_total': None if sparse else n_rho * n_eta * float(n) ** 3 / dt * 1e-12, 'finite': bool(numpy.isfinite(G).all()),
                       'argmax': {'rho': float(rhos[i]), 'eta': float(etas[j]), 'lp': float(G[i, j, 0]),
                                  'dlp_deta': float(G[i, j, 1]), 'dlp_drho': float(G[i, j, 2])}}))
 if world > 1:
