@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True)
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True, overlap=True)
 
 
 def _p(t):
@@ -246,9 +246,9 @@ class SparseEngine(object):
     def from_op(self, X_dev):
         return X_dev if self.order is None else X_dev[self.inv_order].contiguous()
 
-    def probes(self, first, B):
+    def probes(self, first, B, out=None):
         torch = dev.torch
-        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
+        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda') if out is None else out
         rmap = self.K.order if self.order is not None else None
         check(lib.gp_rademacher(_p(V), self.n, B, int(self.opt['seed']), int(first), _p(rmap) if rmap is not None else None,
                                 dev.stream_ptr()), 'gp_rademacher')
@@ -256,10 +256,15 @@ class SparseEngine(object):
 
     # ---- SLQ -----------------------------------------------------------------------------------------------------
     def _lanczos(self, eta, V, m, basis=None):
+        alpha, beta = self._lanczos_launch(eta, V, m, basis)
+        return alpha.cpu().numpy(), beta.cpu().numpy()
+
+    def _lanczos_launch(self, eta, V, m, basis=None, alpha=None, beta=None):
+        """enqueues the batched Lanczos run on torch's current stream; returns the device (alpha, beta)"""
         torch = dev.torch
         B = V.shape[1]
-        alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
-        beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        alpha = torch.empty((m, B), dtype=torch.float64, device='cuda') if alpha is None else alpha
+        beta = torch.empty((m, B), dtype=torch.float64, device='cuda') if beta is None else beta
         bp = _p(basis) if basis is not None else None
         if self.blocked is not None:
             bptr, bidx, bvals, _ = self.blocked
@@ -269,7 +274,53 @@ class SparseEngine(object):
             K = self.K
             check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha),
                                  _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
-        return alpha.cpu().numpy(), beta.cpu().numpy()
+        return alpha, beta
+
+    def _basis(self, m, B):
+        torch = dev.torch
+        key = ('basis', m, B)
+        if key not in self._ws:
+            self._ws[key] = torch.empty((m, self.n, B), dtype=torch.float64, device='cuda')
+        return self._ws[key]
+
+    def _first_chunk(self):
+        """(first probe id, width) of the first block of probes this rank evaluates in an estimator run"""
+        o = self.opt
+        B, hi = int(o['batch']), int(o['max_num_samples'])
+        rank, world = self.probe_range if self.probe_range is not None else (0, 1)
+        nb = min(B * world, hi)
+        per = (nb + world - 1) // world
+        my0 = rank * per
+        chunks = self._chunks(my0, max(0, min(nb, my0 + per) - my0), B)
+        return chunks[0] if chunks else None
+
+    def prefetch_slq(self, eta):
+        """Enqueues the first SLQ block of probes at `eta` on a side stream and returns at once, so that the batched CG
+        for [X z] that follows on the main stream (HBM-bound, B = 8) overlaps the Lanczos run (L1-bound, B = 16).
+        _slq_samples picks the result up."""
+        torch = dev.torch
+        if float(eta) in self._slq_cache or getattr(self, '_prefetched', None) is not None:
+            return
+        chunk = self._first_chunk()
+        if chunk is None:
+            return
+        first, B = chunk
+        m = int(self.opt['lanczos_degree'])
+        with_dk = self.K.ddata is not None and bool(self.opt.get('reuse_lanczos', True))
+        if not hasattr(self, '_side_stream'):
+            self._side_stream = torch.cuda.Stream()
+        # every buffer is allocated on the main stream; the side stream only runs kernels on them
+        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
+        alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
+        basis = self._basis(m, B) if with_dk else None
+        self._workspace(B)
+        cur = torch.cuda.current_stream()
+        self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream):
+            self.probes(first, B, out=V)
+            self._lanczos_launch(eta, V, m, basis, alpha, beta)
+        self._prefetched = (float(eta), first, B, with_dk, V, alpha, beta)
 
     def _slq_samples(self, eta, first, B, with_dk=False):
         """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1. With ``with_dk`` a fourth column:
@@ -277,14 +328,19 @@ class SparseEngine(object):
         Lanczos form of CG) when its residual beta_k |y_k| meets the CG tolerance, else from a batched CG solve."""
         torch = dev.torch
         m = int(self.opt['lanczos_degree'])
-        V = self.probes(first, B)
-        basis = None
-        if with_dk:
-            key = ('basis', m, B)
-            if key not in self._ws:
-                self._ws[key] = torch.empty((m, self.n, B), dtype=torch.float64, device='cuda')
-            basis = self._ws[key]
-        a, b = self._lanczos(eta, V, m, basis)
+        pre = getattr(self, '_prefetched', None)
+        self._prefetched = None
+        if pre is not None and pre[:4] == (float(eta), first, B, with_dk):
+            V, alpha, beta = pre[4:]
+            basis = self._basis(m, B) if with_dk else None
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            a, b = alpha.cpu().numpy(), beta.cpu().numpy()
+        else:
+            if pre is not None:
+                self._side_stream.synchronize()        # an unused prefetch still owns the workspace
+            V = self.probes(first, B)
+            basis = self._basis(m, B) if with_dk else None
+            a, b = self._lanczos(eta, V, m, basis)
         out = numpy.empty((B, 4 if with_dk else 3))
         coef = numpy.zeros((m, B))
         vnorm = numpy.sqrt(float(self.n))          # Rademacher probes
@@ -563,6 +619,8 @@ class SparseEngine(object):
         n, m = X.shape
         p = m + 1
         Rd = self._rhs_block(X, z)
+        if bool(self.opt.get('overlap', True)) and (self.method == 'slq' or drho):
+            self.prefetch_slq(eta)
         S = self.solve_dev(eta, Rd.clone())
         out = numpy.zeros(8 + 3 * p * p)
         out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
