@@ -11,6 +11,7 @@
 #include "gp_common.cuh"
 #include "gp_matern.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <math.h>
 #include <vector>
 
@@ -137,6 +138,46 @@ __global__ void cell_histogram_kernel(const double* __restrict__ pts, int n, int
     int id = (g.ncells == 1) ? 0 : cell_of_point(p, g);
     cell_of[i] = id;
     atomicAdd(&cell_cnt[id], 1);
+}
+
+// bounding box of the points on the device: order-preserving 64-bit keys, atomicMin / atomicMax per coordinate
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static double dkey_decode(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double x;
+    memcpy(&x, &b, sizeof(double));
+    return x;
+}
+__global__ void bbox_kernel(const double* __restrict__ pts, int64_t n, int d, unsigned long long* keys /* [8] min, [8] max */) {
+    __shared__ unsigned long long smin[8], smax[8];
+    if (threadIdx.x < 8) { smin[threadIdx.x] = ~0ull; smax[threadIdx.x] = 0ull; }
+    __syncthreads();
+    // block-uniform trip count: every lane takes part in the shuffles, out-of-range lanes carry the identities
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        for (int k = 0; k < d; ++k) {
+            unsigned long long mn = ~0ull, mx = 0ull;
+            if (i < n) mn = mx = dkey(pts[i * d + k]);
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+                mn = a < mn ? a : mn;
+                mx = b > mx ? b : mx;
+            }
+            if ((threadIdx.x & 31) == 0) { atomicMin(&smin[k], mn); atomicMax(&smax[k], mx); }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < d) { atomicMin(&keys[threadIdx.x], smin[threadIdx.x]); atomicMax(&keys[8 + threadIdx.x], smax[threadIdx.x]); }
+}
+
+__global__ void sum64_kernel(const int* __restrict__ v, int n, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += (unsigned)v[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // The points of a cell are kept in ORIGINAL index order (stable radix sort of the cell ids): the generation order of
@@ -395,6 +436,8 @@ struct SparseWs {
     int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow, *cell_sorted, *iota;
     void* sort_temp;
     size_t sort_temp_bytes;
+    unsigned long long* bbox_keys;   // [8] min keys, [8] max keys, [16] total nnz
+    double* bbox;                    // lo[8], hi[8] (decoded, for the fill call)
     int2* border;
     int *ei, *ej, *eslot;
     double *ev, *edv, *sorted_pts;
@@ -425,6 +468,8 @@ static SparseWs carve_sparse(void* ws, int64_t n, int64_t d) {
     w.iota = (int*)take(sizeof(int) * n);
     w.sort_temp_bytes = (size_t)n * 16 + (8u << 20);      // radix sort scratch (alternate key/value buffers + histograms)
     w.sort_temp = (void*)take(w.sort_temp_bytes);
+    w.bbox_keys = (unsigned long long*)take(sizeof(unsigned long long) * 24);
+    w.bbox = (double*)take(sizeof(double) * 16);
     w.total = off;
     return w;
 }
@@ -559,18 +604,27 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
         return -1;
     cudaStream_t s = (cudaStream_t)stream;
     SparseWs w = carve_sparse(ws, n, d);
-    double lo[8], hi[8];
-    for (int k = 0; k < d; ++k) { lo[k] = 1e300; hi[k] = -1e300; }
-    for (int64_t i = 0; i < n; ++i)
-        for (int k = 0; k < d; ++k) {
-            double v = points_host[i * d + k];
-            if (v < lo[k]) lo[k] = v;
-            if (v > hi[k]) hi[k] = v;
+    const int N = (int)n, D = (int)d;
+    double lo[8], hi[8], bb[16];
+    {
+        unsigned long long init[24], got[16];
+        for (int k = 0; k < 8; ++k) { init[k] = ~0ull; init[8 + k] = 0ull; init[16 + k] = 0ull; }
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.bbox_keys, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        bbox_kernel<<<296, 256, 0, s>>>(points, n, D, w.bbox_keys);
+        GP_COUNT(1);
+        GP_CUDA_CHECK(cudaMemcpyAsync(got, w.bbox_keys, sizeof(got), cudaMemcpyDeviceToHost, s));
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (int k = 0; k < 8; ++k) {
+            lo[k] = (k < d) ? dkey_decode(got[k]) : 0.0;
+            hi[k] = (k < d) ? dkey_decode(got[8 + k]) : 0.0;
+            bb[k] = lo[k];
+            bb[8 + k] = hi[k];
         }
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
+    }
     SparseParams sp;
     CellGrid g;
     make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
-    const int N = (int)n, D = (int)d;
     GP_CUDA_CHECK(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * (g.ncells + 1), s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.cell_fill, 0, sizeof(int) * g.ncells, s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.border_cnt, 0, sizeof(int) * 4, s));
@@ -597,12 +651,31 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     }
     launch_rows_mode(matern_mode_of(nu), 0, false, sp, g, w, nullptr, nullptr, nullptr, nullptr, s);
     GP_LAUNCH_CHECK();
-    std::vector<int> cnt(n);
     int nb = 0;
-    GP_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), w.devcount, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    unsigned long long total = 0;
+    sum64_kernel<<<296, 256, 0, s>>>(w.devcount, N, w.bbox_keys + 16);
+    GP_COUNT(1);
     GP_CUDA_CHECK(cudaMemcpyAsync(&nb, w.border_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaMemcpyAsync(&total, w.bbox_keys + 16, sizeof(total), cudaMemcpyDeviceToHost, s));
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
     if (nb > BORDER_CAP) return -21;
+    if (nb == 0) {
+        // the common case: no borderline pair -> the row pointer is an exclusive scan on the device
+        if (total > (unsigned long long)INT32_MAX) return -22;
+        size_t need = 0;
+        GP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, w.devcount, indptr_dev, N + 1, s));
+        if (need > w.sort_temp_bytes) return -24;
+        GP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.sort_temp, need, w.devcount, indptr_dev, N + 1, s));
+        GP_COUNT(1);
+        int meta0[4] = {0, 0, 0, 0};
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.border_cnt, meta0, sizeof(int) * 4, cudaMemcpyHostToDevice, s));
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+        *nnz_host = (int64_t)total;
+        return 0;
+    }
+    std::vector<int> cnt(n);
+    GP_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), w.devcount, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
     // borderline pairs: decide with the reference's host arithmetic
     std::vector<int> ei, ej, eslot;
     std::vector<double> ev, edv;
@@ -704,20 +777,14 @@ int gp_matern_sparse_fill(const double* points, const double* points_host, int64
             if (scale_host[k] != scale_host[0]) return -4;
     cudaStream_t s = (cudaStream_t)stream;
     SparseWs w = carve_sparse(ws, n, d);
-    double lo[8], hi[8];
-    for (int k = 0; k < d; ++k) { lo[k] = 1e300; hi[k] = -1e300; }
-    for (int64_t i = 0; i < n; ++i)
-        for (int k = 0; k < d; ++k) {
-            double v = points_host[i * d + k];
-            if (v < lo[k]) lo[k] = v;
-            if (v > hi[k]) hi[k] = v;
-        }
-    SparseParams sp;
-    CellGrid g;
-    make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
+    double bb[16];
     int meta[4];
+    GP_CUDA_CHECK(cudaMemcpyAsync(bb, w.bbox, sizeof(bb), cudaMemcpyDeviceToHost, s));      // left by the count call
     GP_CUDA_CHECK(cudaMemcpyAsync(meta, w.border_cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    SparseParams sp;
+    CellGrid g;
+    make_params(n, d, scale_host, nu, tau, bb, bb + 8, &sp, &g);
     int ne = meta[0];
     launch_rows_mode(matern_mode_of(nu), 1, ddata_dev != nullptr, sp, g, w, indptr_dev, indices_dev, data_dev, ddata_dev, s);
     if (ne > 0) {
