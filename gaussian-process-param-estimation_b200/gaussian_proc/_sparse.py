@@ -27,7 +27,8 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True, overlap=True)
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True, overlap=True,
+                shift_reuse=True, solve_degree=None)
 
 
 def _p(t):
@@ -169,6 +170,8 @@ class SparseEngine(object):
         self.opt = dict(DEFAULTS)
         self.opt.update(imate_options or {})
         self._ws = {}
+        self._krylov = {}          # shift-invariant Lanczos runs, see _probe_krylov / solve_rhs_block
+        self._rhs_etas = set()
         self._slq_cache = {}
         self.last_info = {}
         # multi-GPU: (rank, world) -> this engine evaluates its slice of every round of probes; see _run_estimator
@@ -276,13 +279,6 @@ class SparseEngine(object):
                                  _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
         return alpha, beta
 
-    def _basis(self, m, B):
-        torch = dev.torch
-        key = ('basis', m, B)
-        if key not in self._ws:
-            self._ws[key] = torch.empty((m, self.n, B), dtype=torch.float64, device='cuda')
-        return self._ws[key]
-
     def _first_chunk(self):
         """(first probe id, width) of the first block of probes this rank evaluates in an estimator run"""
         o = self.opt
@@ -305,6 +301,8 @@ class SparseEngine(object):
         if chunk is None:
             return
         first, B = chunk
+        if ('probes', first, B) in self._krylov and bool(self.opt.get('shift_reuse', True)):
+            return                                 # already served by a kept Lanczos run
         m = int(self.opt['lanczos_degree'])
         with_dk = self.K.ddata is not None and bool(self.opt.get('reuse_lanczos', True))
         if not hasattr(self, '_side_stream'):
@@ -313,14 +311,77 @@ class SparseEngine(object):
         V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
-        basis = self._basis(m, B) if with_dk else None
+        basis = self._new_basis(m, B) if with_dk else None
         self._workspace(B)
         cur = torch.cuda.current_stream()
         self._side_stream.wait_stream(cur)
         with torch.cuda.stream(self._side_stream):
             self.probes(first, B, out=V)
             self._lanczos_launch(eta, V, m, basis, alpha, beta)
-        self._prefetched = (float(eta), first, B, with_dk, V, alpha, beta)
+        self._prefetched = (float(eta), first, B, with_dk, V, alpha, beta, basis)
+
+    # The Krylov space of K + eta I does not depend on eta and the Lanczos tridiagonal only shifts: T(eta) = T(eta_ref) +
+    # (eta - eta_ref) I (the reference builds imate.AffineMatrixFunction(K) for this, mixed_correlation.py:44,141,207,266).
+    # One batched Lanczos run per block of probes (and one per right-hand-side block) therefore serves EVERY eta asked of
+    # this operator: new quadratures on the host, new solutions x(eta) = ||v|| Q (T + d I)^-1 e_1 by one pass over the kept
+    # vectors. A root find or a sweep over eta at fixed rho pays the SpMMs once.
+    KRYLOV_CACHE_BYTES = 32 << 30      # kept Lanczos vectors per operator (beyond it blocks are recomputed per eta)
+
+    def _krylov_bytes(self):
+        return sum(e['basis'].numel() * 8 for e in self._krylov.values() if e.get('basis') is not None)
+
+    @staticmethod
+    def _tridiag_solve(a, b, k):
+        """y = T_k^-1 e_1 for the leading k x k block of the Lanczos tridiagonal (diagonal a, off-diagonal b)"""
+        e1 = numpy.zeros(k)
+        e1[0] = 1.0
+        if k == 1:
+            return e1 / a[0]
+        ab = numpy.zeros((2, k))
+        ab[0, 1:] = b[:k - 1]
+        ab[1, :] = a[:k]
+        try:
+            return scipy.linalg.solveh_banded(ab, e1)
+        except numpy.linalg.LinAlgError:          # T not positive definite: the caller reports it through tmin / resid
+            return numpy.full(k, numpy.inf)
+
+    def _solution_coefficients(self, a, b, vnorm, k):
+        """Coefficients of x = (K + eta I)^-1 v in the kept UNNORMALISED Lanczos vectors u_j (u_0 = v, u_j = beta_{j-1} q_j)
+        and the relative residual beta_k |y_k| of that Lanczos (= CG) solution."""
+        y = self._tridiag_solve(a, b, k)
+        scale = numpy.empty(k)
+        scale[0] = 1.0 / vnorm
+        scale[1:] = 1.0 / b[:k - 1]
+        return vnorm * y * scale, abs(b[k - 1] * y[k - 1])
+
+    def _probe_krylov(self, eta, first, B, keep_basis):
+        """(entry, shift) for the block of probes first .. first+B-1: the cached Lanczos run if there is one (shift =
+        eta - eta_ref), else a new run at eta (picked up from the side-stream prefetch when it matches)."""
+        torch = dev.torch
+        m = int(self.opt['lanczos_degree'])
+        key = ('probes', first, B)
+        ent = self._krylov.get(key)
+        if ent is not None and (ent['basis'] is not None or not keep_basis) and bool(self.opt.get('shift_reuse', True)):
+            return ent, float(eta) - ent['eta_ref']
+        pre = getattr(self, '_prefetched', None)
+        self._prefetched = None
+        if pre is not None and pre[:4] == (float(eta), first, B, keep_basis):
+            V, alpha, beta, basis = pre[4:]
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            a, b = alpha.cpu().numpy(), beta.cpu().numpy()
+        else:
+            if pre is not None:
+                self._side_stream.synchronize()        # an unused prefetch still owns the workspace
+            V = self.probes(first, B)
+            basis = self._new_basis(m, B) if keep_basis else None
+            a, b = self._lanczos(eta, V, m, basis)
+        ent = {'eta_ref': float(eta), 'a': a, 'b': b, 'basis': basis, 'V': V if keep_basis else None, 'Wd': None}
+        if self._krylov_bytes() + (basis.numel() * 8 if basis is not None else 0) <= self.KRYLOV_CACHE_BYTES:
+            self._krylov[key] = ent
+        return ent, 0.0
+
+    def _new_basis(self, m, B):
+        return dev.torch.empty((m, self.n, B), dtype=dev.torch.float64, device='cuda')
 
     def _slq_samples(self, eta, first, B, with_dk=False):
         """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1. With ``with_dk`` a fourth column:
@@ -328,19 +389,8 @@ class SparseEngine(object):
         Lanczos form of CG) when its residual beta_k |y_k| meets the CG tolerance, else from a batched CG solve."""
         torch = dev.torch
         m = int(self.opt['lanczos_degree'])
-        pre = getattr(self, '_prefetched', None)
-        self._prefetched = None
-        if pre is not None and pre[:4] == (float(eta), first, B, with_dk):
-            V, alpha, beta = pre[4:]
-            basis = self._basis(m, B) if with_dk else None
-            torch.cuda.current_stream().wait_stream(self._side_stream)
-            a, b = alpha.cpu().numpy(), beta.cpu().numpy()
-        else:
-            if pre is not None:
-                self._side_stream.synchronize()        # an unused prefetch still owns the workspace
-            V = self.probes(first, B)
-            basis = self._basis(m, B) if with_dk else None
-            a, b = self._lanczos(eta, V, m, basis)
+        ent, shift = self._probe_krylov(eta, first, B, with_dk)
+        a, b = ent['a'] + shift, ent['b']
         out = numpy.empty((B, 4 if with_dk else 3))
         coef = numpy.zeros((m, B))
         vnorm = numpy.sqrt(float(self.n))          # Rademacher probes
@@ -355,32 +405,69 @@ class SparseEngine(object):
                     % (eta, tmin))
             out[c, :3] = numpy.array(vals) * self.n
             if with_dk:
-                e1 = numpy.zeros(k)
-                e1[0] = 1.0
-                if k > 1:
-                    ab = numpy.zeros((2, k))
-                    ab[0, 1:] = b[:k - 1, c]
-                    ab[1, :] = a[:k, c]
-                    y = scipy.linalg.solveh_banded(ab, e1)
-                else:
-                    y = e1 / a[0, c]
-                scale = numpy.empty(k)                  # 1 / ||u_j||: u_0 = v, u_j = beta_{j-1} q_j
-                scale[0] = 1.0 / vnorm
-                scale[1:] = 1.0 / b[:k - 1, c]
-                coef[:k, c] = vnorm * y * scale
-                resid = max(resid, abs(b[k - 1, c] * y[k - 1]))
+                coef[:k, c], r = self._solution_coefficients(a[:, c], b[:, c], vnorm, k)
+                resid = max(resid, r)
         if with_dk:
+            V = ent['V'] if ent['V'] is not None else self.probes(first, B)
+            if ent['Wd'] is None:
+                ent['Wd'] = self.spmm(0.0, V, derivative=True)      # dK v does not depend on eta either
             if resid <= float(self.opt['cg_tol']):
                 U = torch.empty_like(V)
                 cd = torch.from_numpy(coef).cuda()
-                check(lib.gp_block_combine(_p(basis), self.n, B, m, _p(cd), _p(U), dev.stream_ptr()), 'gp_block_combine')
+                check(lib.gp_block_combine(_p(ent['basis']), self.n, B, m, _p(cd), _p(U), dev.stream_ptr()),
+                      'gp_block_combine')
                 self.last_dk_solver = 'lanczos'
             else:
                 U = self.solve_dev(eta, V.clone())
                 self.last_dk_solver = 'cg'
-            Wd = self.spmm(0.0, V, derivative=True)
-            out[:, 3] = self.col_dot(U, Wd)
+            out[:, 3] = self.col_dot(U, ent['Wd'])
         return out
+
+    def solve_rhs_block(self, eta, Rop, key):
+        """S = (K + eta I)^-1 R for the (cached) right-hand-side block of the likelihood, operator space. The first eta
+        asked of this operator is solved by batched CG; from the second DISTINCT eta on, one batched Lanczos run on R
+        (degree ~ twice the CG iteration count) is kept and every eta is served from it (shift invariance), falling
+        back to CG for an eta whose Lanczos residual misses the CG tolerance."""
+        torch = dev.torch
+        eta = float(eta)
+        if not bool(self.opt.get('shift_reuse', True)):
+            return self.solve_dev(eta, Rop.clone())
+        B = Rop.shape[1]
+        ent = self._krylov.get(('rhs', key))
+        if ent is None:
+            self._rhs_etas.add(eta)
+            if len(self._rhs_etas) < 2:
+                return self.solve_dev(eta, Rop.clone())
+            m = int(self.opt.get('solve_degree') or min(128, max(int(self.opt['lanczos_degree']),
+                                                                   2 * int(getattr(self, 'last_cg_iterations', 32)))))
+            basis = self._new_basis(m, B)
+            a, b = self._lanczos(eta, Rop, m, basis)
+            norms = numpy.sqrt(numpy.maximum(self.col_dot(Rop, Rop), 0.0))
+            ent = {'eta_ref': eta, 'a': a, 'b': b, 'basis': basis, 'norms': norms, 'm': m}
+            if self._krylov_bytes() + basis.numel() * 8 <= self.KRYLOV_CACHE_BYTES:
+                self._krylov[('rhs', key)] = ent
+        a, b, m = ent['a'] + (eta - ent['eta_ref']), ent['b'], ent['m']
+        coef = numpy.zeros((m, B))
+        resid = 0.0
+        for c in range(B):
+            if not (ent['norms'][c] > 0.0):
+                continue
+            k = m
+            for j in range(m - 1):
+                if not (b[j, c] > 1e-12 * max(abs(a[0, c]), 1.0)):
+                    k = j + 1
+                    break
+            coef[:k, c], r = self._solution_coefficients(a[:, c], b[:, c], ent['norms'][c], k)
+            if k == m:
+                resid = max(resid, r)
+        if not (resid <= float(self.opt['cg_tol'])):
+            self.last_rhs_solver = 'cg'
+            return self.solve_dev(eta, Rop.clone())
+        S = torch.empty_like(Rop)
+        cd = torch.from_numpy(coef).cuda()
+        check(lib.gp_block_combine(_p(ent['basis']), self.n, B, m, _p(cd), _p(S), dev.stream_ptr()), 'gp_block_combine')
+        self.last_rhs_solver = 'lanczos'
+        return S
 
     @staticmethod
     def _chunks(first, count, batch):
@@ -621,7 +708,7 @@ class SparseEngine(object):
         Rd = self._rhs_block(X, z)
         if bool(self.opt.get('overlap', True)) and (self.method == 'slq' or drho):
             self.prefetch_slq(eta)
-        S = self.solve_dev(eta, Rd.clone())
+        S = self.solve_rhs_block(eta, Rd, (id(X), id(z)))
         out = numpy.zeros(8 + 3 * p * p)
         out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
         out[8 + p * p:8 + 2 * p * p] = self.gram(S, S)[:p, :p].ravel()
