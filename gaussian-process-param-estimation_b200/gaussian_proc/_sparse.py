@@ -157,6 +157,50 @@ def lanczos_quadrature(alpha, beta, funcs, return_size=False):
     return res + (m,) if return_size else res
 
 
+def lanczos_block_quadrature(alpha, beta, vnorm=None):
+    """Batched host part of SLQ for a block of B Lanczos runs (alpha, beta: m x B): one stacked symmetric eigensolve of
+    the B tridiagonals gives, per column, the Gauss quadratures of [log, 1/x, 1/x^2], the smallest Ritz value and - with
+    ``vnorm`` (||v|| per column, or a scalar) - the coefficients of x = A^-1 v in the unnormalised Lanczos vectors
+    (u_0 = v, u_j = beta_{j-1} q_j) together with the relative residual beta_m |y_m| of that Lanczos (= CG) solution.
+    A column whose recurrence broke down (beta ~ 0: invariant subspace) is truncated there.
+    Returns quad (B x 3), tmin (B), coef (m x B) or None, resid (B) or None."""
+    m, B = alpha.shape
+    ks = numpy.full(B, m, dtype=int)
+    for c in range(B):
+        small = numpy.nonzero(~(beta[:m - 1, c] > 1e-12 * max(abs(alpha[0, c]), 1.0)))[0]
+        if small.size:
+            ks[c] = small[0] + 1
+    quad, tmin = numpy.empty((B, 3)), numpy.empty(B)
+    want = vnorm is not None
+    coef = numpy.zeros((m, B)) if want else None
+    resid = numpy.zeros(B) if want else None
+    vn = numpy.broadcast_to(numpy.asarray(vnorm, dtype=float), (B,)) if want else None
+    for k in numpy.unique(ks):
+        cols = numpy.nonzero(ks == k)[0]
+        T = numpy.zeros((cols.size, k, k))
+        idx = numpy.arange(k)
+        T[:, idx, idx] = alpha[:k, cols].T
+        if k > 1:
+            T[:, idx[:-1], idx[1:]] = beta[:k - 1, cols].T
+            T[:, idx[1:], idx[:-1]] = beta[:k - 1, cols].T
+        theta, Y = numpy.linalg.eigh(T)
+        w = Y[:, 0, :] ** 2
+        with numpy.errstate(invalid='ignore', divide='ignore'):
+            quad[cols, 0] = numpy.sum(w * numpy.log(theta), axis=1)
+            quad[cols, 1] = numpy.sum(w / theta, axis=1)
+            quad[cols, 2] = numpy.sum(w / theta ** 2, axis=1)
+            tmin[cols] = theta.min(axis=1)
+            if want:
+                y = numpy.einsum('bij,bj->bi', Y, Y[:, 0, :] / theta)          # T^-1 e_1
+                scale = numpy.empty((cols.size, k))
+                scale[:, 0] = 1.0 / vn[cols]
+                if k > 1:
+                    scale[:, 1:] = 1.0 / beta[:k - 1, cols].T
+                coef[:k, cols] = (vn[cols][:, None] * y * scale).T
+                resid[cols] = numpy.abs(beta[k - 1, cols] * y[:, k - 1]) if k == m else 0.0
+    return quad, tmin, coef, resid
+
+
 class SparseEngine(object):
     """Stochastic logdet / traceinv and CG solves for K + eta I with K in device CSR."""
 
@@ -330,30 +374,6 @@ class SparseEngine(object):
     def _krylov_bytes(self):
         return sum(e['basis'].numel() * 8 for e in self._krylov.values() if e.get('basis') is not None)
 
-    @staticmethod
-    def _tridiag_solve(a, b, k):
-        """y = T_k^-1 e_1 for the leading k x k block of the Lanczos tridiagonal (diagonal a, off-diagonal b)"""
-        e1 = numpy.zeros(k)
-        e1[0] = 1.0
-        if k == 1:
-            return e1 / a[0]
-        ab = numpy.zeros((2, k))
-        ab[0, 1:] = b[:k - 1]
-        ab[1, :] = a[:k]
-        try:
-            return scipy.linalg.solveh_banded(ab, e1)
-        except numpy.linalg.LinAlgError:          # T not positive definite: the caller reports it through tmin / resid
-            return numpy.full(k, numpy.inf)
-
-    def _solution_coefficients(self, a, b, vnorm, k):
-        """Coefficients of x = (K + eta I)^-1 v in the kept UNNORMALISED Lanczos vectors u_j (u_0 = v, u_j = beta_{j-1} q_j)
-        and the relative residual beta_k |y_k| of that Lanczos (= CG) solution."""
-        y = self._tridiag_solve(a, b, k)
-        scale = numpy.empty(k)
-        scale[0] = 1.0 / vnorm
-        scale[1:] = 1.0 / b[:k - 1]
-        return vnorm * y * scale, abs(b[k - 1] * y[k - 1])
-
     def _probe_krylov(self, eta, first, B, keep_basis):
         """(entry, shift) for the block of probes first .. first+B-1: the cached Lanczos run if there is one (shift =
         eta - eta_ref), else a new run at eta (picked up from the side-stream prefetch when it matches)."""
@@ -392,21 +412,15 @@ class SparseEngine(object):
         ent, shift = self._probe_krylov(eta, first, B, with_dk)
         a, b = ent['a'] + shift, ent['b']
         out = numpy.empty((B, 4 if with_dk else 3))
-        coef = numpy.zeros((m, B))
         vnorm = numpy.sqrt(float(self.n))          # Rademacher probes
-        resid = 0.0
-        for c in range(B):
-            vals, tmin, k = lanczos_quadrature(a[:, c], b[:, c], [numpy.log, lambda t: 1.0 / t, lambda t: 1.0 / t ** 2],
-                                               return_size=True)
-            if not (tmin > 0):
-                raise numpy.linalg.LinAlgError(
-                    'K + eta*I (eta=%g) is not positive definite: Lanczos found a Ritz value %.3e. The thresholded '
-                    'Matern matrix is indefinite; use a larger eta (reference: _generate_sparse_correlation.pyx:516-523).'
-                    % (eta, tmin))
-            out[c, :3] = numpy.array(vals) * self.n
-            if with_dk:
-                coef[:k, c], r = self._solution_coefficients(a[:, c], b[:, c], vnorm, k)
-                resid = max(resid, r)
+        quad, tmin, coef, res = lanczos_block_quadrature(a, b, vnorm if with_dk else None)
+        if not (tmin.min() > 0):
+            raise numpy.linalg.LinAlgError(
+                'K + eta*I (eta=%g) is not positive definite: Lanczos found a Ritz value %.3e. The thresholded '
+                'Matern matrix is indefinite; use a larger eta (reference: _generate_sparse_correlation.pyx:516-523).'
+                % (eta, tmin.min()))
+        out[:, :3] = quad * self.n
+        resid = float(res.max()) if with_dk else 0.0
         if with_dk:
             V = ent['V'] if ent['V'] is not None else self.probes(first, B)
             if ent['Wd'] is None:
@@ -447,19 +461,11 @@ class SparseEngine(object):
             if self._krylov_bytes() + basis.numel() * 8 <= self.KRYLOV_CACHE_BYTES:
                 self._krylov[('rhs', key)] = ent
         a, b, m = ent['a'] + (eta - ent['eta_ref']), ent['b'], ent['m']
+        live = numpy.nonzero(ent['norms'] > 0.0)[0]                 # zero (padding) columns stay zero
         coef = numpy.zeros((m, B))
-        resid = 0.0
-        for c in range(B):
-            if not (ent['norms'][c] > 0.0):
-                continue
-            k = m
-            for j in range(m - 1):
-                if not (b[j, c] > 1e-12 * max(abs(a[0, c]), 1.0)):
-                    k = j + 1
-                    break
-            coef[:k, c], r = self._solution_coefficients(a[:, c], b[:, c], ent['norms'][c], k)
-            if k == m:
-                resid = max(resid, r)
+        _, tmin, cf, res = lanczos_block_quadrature(a[:, live], b[:, live], ent['norms'][live])
+        coef[:, live] = cf
+        resid = float(res.max()) if (live.size and tmin.min() > 0) else numpy.inf
         if not (resid <= float(self.opt['cg_tol'])):
             self.last_rhs_solver = 'cg'
             return self.solve_dev(eta, Rop.clone())
@@ -572,11 +578,15 @@ class SparseEngine(object):
     def traceinv_dK(self, eta):
         """Hutchinson estimate of tr((K + eta I)^-1 dK/d rho): mean over probes of (Kn^-1 v)^T (dK v). Samples that the
         SLQ run at this eta already produced (same probe ids, Kn^-1 v from its Lanczos basis) are used first; further
-        rounds, if its own stopping rule asks for them, use batched CG."""
+        rounds, if its own stopping rule asks for them, go through the same kept-Lanczos path (CG when the Lanczos
+        residual misses the tolerance or with reuse_lanczos=False)."""
         if self.K.ddata is None:
             raise ValueError('needs a DeviceCSR generated with with_derivative=True')
 
         def fn(first, width):
+            if bool(self.opt.get('reuse_lanczos', True)):
+                # through the (kept, shift-invariant) Lanczos run of this probe block: reused for every later eta
+                return self._slq_samples(eta, first, width, True)[:, 3:4]
             V = self.probes(first, width)
             U = self.solve_dev(eta, V.clone())
             Wd = self.spmm(0.0, V, derivative=True)
