@@ -273,6 +273,18 @@ def secondary_measurements():
     lgr = loglik_grad()
     torch.cuda.synchronize()
     tl = time.perf_counter() - t0
+    # the reference's headline driver on this matrix: maximum profile likelihood by the root of d l^/d eta
+    # (_profile_likelihood.py:244-415); the kept Krylov runs of the operator serve every eta of the root find
+    import contextlib
+    import io
+    t0 = time.perf_counter()
+    Kr = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True)
+    Kmr = MixedCorrelation(Kr, imate_method='slq', imate_options=opts)
+    with contextlib.redirect_stdout(io.StringIO()):
+        root = ProfileLikelihood.find_log_likelihood_der1_zeros(zs, Xs, Kmr, [10.0, 1e3])
+    torch.cuda.synchronize()
+    tr_ = time.perf_counter() - t0
+    del Kr, Kmr
     # CPU comparator for the sparse leg, bounded (~15 s): the reference's compiled brute-force generator (O(n^2)) at
     # n = 2^13 extrapolated with n^2, and the operation its SLQ / CG estimators are built on - SciPy's CSR x dense-block
     # product with the same number of non-zeros per row - at n = 2^17 extrapolated linearly in nnz.
@@ -319,6 +331,7 @@ def secondary_measurements():
                          'spmm': spm, 'spmm_kernel': 'gp::bcsr8_spmm_dmma_kernel (8x1 row blocks, DMMA.8x8x4)',
                          'evals_per_s': 1.0 / te, 'evals_per_s_new_rho': 1.0 / tn,
                          'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],
+                         'mle_root_find_s': tr_, 'mle_root': {k: float(v) for k, v in root.items()},
                          'eval': 'SLQ logdet + traceinv (degree 30, <= 50 Rademacher probes, batch 16, rtol 1e-2 @ 95 %) + '
                                  'Hutchinson/CG tr(Kn^-1 dK/drho); new_rho adds CSR generation and the row-blocked build; loglik_grad = the '
                                  'whole profile likelihood + gradient through the public API (adds the CG solves for [X z], m = 6)',
