@@ -242,20 +242,26 @@ def secondary_measurements():
                           'useful_GFLOPs': 2.0 * K.nnz * B / ms * 1e-6}
     eta = 10.0     # lambda_min(K) ~ -1.2 for this hard-thresholded matrix: eta = 1 is indefinite
 
-    def evaluate(e):
+    def evaluate(e, eta_):
         e._slq_cache = {}
-        ld_ = e.logdet(eta)
+        ld_ = e.logdet(eta_)
         info_ = dict(e.last_info)
-        ti_ = e.traceinv(eta)
-        tr_ = e.traceinv_dK(eta)
+        ti_ = e.traceinv(eta_)
+        tr_ = e.traceinv_dK(eta_)
         return ld_, info_, ti_, tr_
 
-    evaluate(eng)
+    evaluate(eng, eta)                                 # warm (allocations, kernel attributes)
+    eng_f = SparseEngine(K, 'slq', opts)               # a fresh operator on the same matrix: no kept Krylov runs yet
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ld, info, ti, tr = evaluate(eng)
+    ld, info, ti, tr = evaluate(eng_f, eta)            # first eta of an operator: pays the Lanczos run
     torch.cuda.synchronize()
     te = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    evaluate(eng_f, 2.0 * eta)                         # a further eta: served from the kept (shift-invariant) runs
+    torch.cuda.synchronize()
+    te2 = time.perf_counter() - t0
+    del eng_f
     # the same evaluation at a NEW rho: canonical CSR generation + row-blocked build + estimators (the previous
     # operator is released first, as an optimiser loop would: its buffers go back to the caching allocator)
     nnz, fill = K.nnz, eng.fill_ratio
@@ -263,7 +269,7 @@ def secondary_measurements():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     K2, eng2 = build()
-    evaluate(eng2)
+    evaluate(eng2, eta)
     torch.cuda.synchronize()
     tn = time.perf_counter() - t0
     del K2, eng2
@@ -329,11 +335,12 @@ def secondary_measurements():
                          'nnz': nnz, 'generate_s': tg, 'generate_GBs': (20.0 * nnz + 4.0 * (n + 1)) / tg * 1e-9,
                          'row_blocked_build_s': tb, 'row_blocked_fill_ratio': fill,
                          'spmm': spm, 'spmm_kernel': 'gp::bcsr8_spmm_dmma_kernel (8x1 row blocks, DMMA.8x8x4)',
-                         'evals_per_s': 1.0 / te, 'evals_per_s_new_rho': 1.0 / tn,
+                         'evals_per_s': 1.0 / te, 'evals_per_s_further_eta': 1.0 / te2, 'evals_per_s_new_rho': 1.0 / tn,
                          'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],
                          'mle_root_find_s': tr_, 'mle_root': {k: float(v) for k, v in root.items()},
                          'eval': 'SLQ logdet + traceinv (degree 30, <= 50 Rademacher probes, batch 16, rtol 1e-2 @ 95 %) + '
-                                 'Hutchinson/CG tr(Kn^-1 dK/drho); new_rho adds CSR generation and the row-blocked build; loglik_grad = the '
+                                 'Hutchinson tr(Kn^-1 dK/drho) at the first eta of an operator; further_eta = another eta served from the kept '
+                                 'Krylov runs; new_rho adds CSR generation and the row-blocked build; loglik_grad = the '
                                  'whole profile likelihood + gradient through the public API (adds the CG solves for [X z], m = 6)',
                          'logdet': ld, 'logdet_half_width': float(info['half_width'][0]), 'num_samples': info['num_samples'],
                          'traceinv': ti, 'trace_Kninv_dK': tr, 'cpu_comparator': cpu}
