@@ -1,12 +1,13 @@
-// Kernel-threshold sparse Matern correlation in canonical CSR -- replaces the brute-force O(n^2) OpenMP COO fill +
-// coo->csr of gaussian_proc/generate_correlation/_generate_sparse_correlation.pyx:35-201,472-594 by a uniform cell
-// list (cell edge = taper radius), a count pass, a host scan, a fill pass and a per-row bitonic sort.
+// Kernel-threshold sparse Matern correlation in CSR -- replaces the brute-force O(n^2) OpenMP COO fill + coo->csr of
+// gaussian_proc/generate_correlation/_generate_sparse_correlation.pyx:35-201,472-594 by a uniform cell list (cell edge =
+// taper radius; points of a cell kept in index order by a stable radix sort), a count pass, a device scan of the row
+// pointer, a fill pass and - on demand (gp_csr_sort_rows / sort_rows = 1) - a per-row sort into the canonical CSR.
 //
 // Bit-exact pattern: the keep rule is the reference's strict `K_ij > tau` (:160). The scaled distance is evaluated
 // in the reference's operation order with IEEE division/sqrt and no FMA contraction (this file is compiled with
 // -fmad=false); only exp() can differ from glibc by an ulp, so pairs with |K - tau| <= 8 ulp are not decided on the
 // device: they are listed, re-evaluated on the host with libm in the reference's arithmetic, and the accepted ones
-// are appended to their rows before the sort.
+// are appended to their rows (in that rare case the row pointer is rebuilt on the host).
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_matern.cuh"
@@ -626,7 +627,6 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     CellGrid g;
     make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
     GP_CUDA_CHECK(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * (g.ncells + 1), s));
-    GP_CUDA_CHECK(cudaMemsetAsync(w.cell_fill, 0, sizeof(int) * g.ncells, s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.border_cnt, 0, sizeof(int) * 4, s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int) * 4, s));
     cell_histogram_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, g, w.cell_of, w.cell_start + 1);
