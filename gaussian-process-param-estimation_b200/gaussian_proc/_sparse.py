@@ -215,7 +215,7 @@ class SparseEngine(object):
         self.opt.update(imate_options or {})
         self._ws = {}
         self._krylov = {}          # shift-invariant Lanczos runs, see _probe_krylov / solve_rhs_block
-        self._rhs_etas = set()
+        self._rhs_etas = {}
         self._slq_cache = {}
         self.last_info = {}
         # multi-GPU: (rank, world) -> this engine evaluates its slice of every round of probes; see _run_estimator
@@ -437,7 +437,7 @@ class SparseEngine(object):
             out[:, 3] = self.col_dot(U, ent['Wd'])
         return out
 
-    def solve_rhs_block(self, eta, Rop, key):
+    def solve_rhs_block(self, eta, Rop, key, refs=None):
         """S = (K + eta I)^-1 R for the (cached) right-hand-side block of the likelihood, operator space. The first eta
         asked of this operator is solved by batched CG; from the second DISTINCT eta on, one batched Lanczos run on R
         (degree ~ twice the CG iteration count) is kept and every eta is served from it (shift invariance), falling
@@ -449,15 +449,16 @@ class SparseEngine(object):
         B = Rop.shape[1]
         ent = self._krylov.get(('rhs', key))
         if ent is None:
-            self._rhs_etas.add(eta)
-            if len(self._rhs_etas) < 2:
+            seen = self._rhs_etas.setdefault(key, (set(), refs))[0]      # refs keep X, z alive: the ids stay unique
+            seen.add(eta)
+            if len(seen) < 2:
                 return self.solve_dev(eta, Rop.clone())
             m = int(self.opt.get('solve_degree') or min(128, max(int(self.opt['lanczos_degree']),
                                                                    2 * int(getattr(self, 'last_cg_iterations', 32)))))
             basis = self._new_basis(m, B)
             a, b = self._lanczos(eta, Rop, m, basis)
             norms = numpy.sqrt(numpy.maximum(self.col_dot(Rop, Rop), 0.0))
-            ent = {'eta_ref': eta, 'a': a, 'b': b, 'basis': basis, 'norms': norms, 'm': m}
+            ent = {'eta_ref': eta, 'a': a, 'b': b, 'basis': basis, 'norms': norms, 'm': m, 'refs': refs}
             if self._krylov_bytes() + basis.numel() * 8 <= self.KRYLOV_CACHE_BYTES:
                 self._krylov[('rhs', key)] = ent
         a, b, m = ent['a'] + (eta - ent['eta_ref']), ent['b'], ent['m']
@@ -718,7 +719,7 @@ class SparseEngine(object):
         Rd = self._rhs_block(X, z)
         if bool(self.opt.get('overlap', True)) and (self.method == 'slq' or drho):
             self.prefetch_slq(eta)
-        S = self.solve_rhs_block(eta, Rd, (id(X), id(z)))
+        S = self.solve_rhs_block(eta, Rd, (id(X), id(z)), refs=(X, z))
         out = numpy.zeros(8 + 3 * p * p)
         out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
         out[8 + p * p:8 + 2 * p * p] = self.gram(S, S)[:p, :p].ravel()
