@@ -327,6 +327,27 @@ def test_row_blocked_operator_equals_csr(gp, R=8):
     assert int((bvals != 0).sum()) == Ks.nnz
 
 
+@pytest.mark.parametrize('n', [3, 8, 13, 70])
+def test_row_blocked_operator_tiny_sizes(n):
+    """fewer rows than one block, exactly one block, a ragged last block: products, solves and the estimators still
+    agree with the dense matrix"""
+    import torch
+    from gaussian_proc._sparse import SparseEngine, generate_sparse_correlation
+    numpy.random.seed(n)
+    pts = numpy.random.rand(n, 2)
+    Kd = generate_sparse_correlation(pts, numpy.array([0.3, 0.3]), 0.5, 0.6, device=True, with_derivative=True)
+    eng = SparseEngine(Kd, 'slq', {'min_num_samples': 64, 'max_num_samples': 64, 'lanczos_degree': min(n, 20)})
+    Ks = Kd.to_scipy().toarray()
+    Xh = numpy.random.randn(n, 4)
+    Y = eng.from_op(eng.spmm(0.5, eng.to_op(torch.from_numpy(Xh).cuda()))).cpu().numpy()
+    assert numpy.max(numpy.abs(Y - (Ks @ Xh + 0.5 * Xh))) <= 1e-13
+    eta = 3.0
+    sol = eng.solve(eta, Xh[:, 0])
+    assert numpy.max(numpy.abs(sol - numpy.linalg.solve(Ks + eta * numpy.eye(n), Xh[:, 0]))) <= 1e-6
+    exact = numpy.linalg.slogdet(Ks + eta * numpy.eye(n))[1]
+    assert abs(eng.logdet(eta) - exact) <= max(4.0 / 1.96 * eng.last_info['half_width'][0], 1e-9 * abs(exact))
+
+
 def test_row_blocked_build_search_fallback():
     """Row blocks with more distinct columns than the shared-memory hash table holds are built by the binary-search
     path: an unstructured random symmetric matrix (8 rows share almost nothing) with the identity as row order."""
