@@ -222,8 +222,9 @@ class SparseEngine(object):
         self.probe_range = probe_range
         # Internally the operator works on the ROW-BLOCKED form of the symmetrically permuted matrix P K P^T (rows in
         # the generator's Z-order): 8 consecutive rows share one column list, so one gathered row of the probe block
-        # serves 8 rows of K and four such block-columns are one DMMA.8x8x4 (csrc/gp_sparse_la.cu). Results do not depend on the permutation: probes are hashed with ORIGINAL
-        # row ids. block_rows = 1 (or a K without an order, e.g. from SciPy) keeps plain CSR in the original order.
+        # serves 8 rows of K and four such block-columns are one DMMA.8x8x4 (csrc/gp_sparse_la.cu). Results do not depend
+        # on the permutation: probes are hashed with ORIGINAL row ids. block_rows = 1 (or a K without an order, e.g. from
+        # SciPy) keeps plain CSR in the original order.
         self.order = self.inv_order = None
         self.R = 1
         self.blocked = None
