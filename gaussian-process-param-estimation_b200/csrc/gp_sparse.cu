@@ -568,8 +568,24 @@ __global__ void morton_keys_kernel(const double* __restrict__ points, int64_t n,
         q[k] = v > qmax ? qmax : v;
     }
     unsigned long long key = 0ull;
-    for (int b = mp.bits - 1; b >= 0; --b)
-        for (int k = 0; k < mp.nd; ++k) key = (key << 1) | ((q[k] >> b) & 1ull);
+    if (mp.nd == 2) {
+        // Hilbert curve index (no long jumps between consecutive keys: consecutive rows of the sorted order are always
+        // spatial neighbours, which keeps the fill-in of the 8 x 1 row blocks low)
+        unsigned long long x = q[0], y = q[1];
+        for (unsigned long long s = 1ull << (mp.bits - 1); s > 0; s >>= 1) {
+            const unsigned long long rx = (x & s) ? 1ull : 0ull, ry = (y & s) ? 1ull : 0ull;
+            key += s * s * ((3ull * rx) ^ ry);
+            if (!ry) {
+                if (rx) { x = (s << 1) - 1ull - (x & ((s << 1) - 1ull)); y = (s << 1) - 1ull - (y & ((s << 1) - 1ull)); }
+                const unsigned long long t = x; x = y; y = t;
+            }
+            x &= (s << 1) - 1ull;
+            y &= (s << 1) - 1ull;
+        }
+    } else {
+        for (int b = mp.bits - 1; b >= 0; --b)
+            for (int k = 0; k < mp.nd; ++k) key = (key << 1) | ((q[k] >> b) & 1ull);
+    }
     keys[i] = (int64_t)key;
 }
 
@@ -716,8 +732,8 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     return 0;
 }
 
-// Z-order (Morton) keys of the points over their bounding box (the first min(d, 3) coordinates, 63 / min(d, 3) bits
-// each): a stable sort by this key gives a deterministic, spatially local ordering of the points. The sparse operator
+// Space-filling-curve keys of the points over their bounding box (2-D: Hilbert index, 31 bits per coordinate; otherwise
+// Z-order / Morton over the first min(d, 3) coordinates, 63 / min(d, 3) bits each): a stable sort by this key gives a deterministic, spatially local ordering of the points. The sparse operator
 // uses it internally (row-blocked form, gp_bcsr_*): consecutive rows then have nearly identical patterns.
 int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo_host, const double* hi_host,
                     int64_t* keys_dev, void* stream) {

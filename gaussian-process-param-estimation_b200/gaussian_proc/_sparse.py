@@ -122,7 +122,7 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
                                     _p(indptr), ctypes.byref(nnz), s)
     check(rc, 'gp_matern_sparse_count')
-    # deterministic, spatially local order of the points (stable sort of Z-order keys) for the row-blocked operator
+    # deterministic, spatially local order of the points (stable sort of Hilbert / Z-order keys) for the row-blocked operator
     lo, hi = dev.host_f64(dpts.amin(dim=0).cpu().numpy()), dev.host_f64(dpts.amax(dim=0).cpu().numpy())
     keys = torch.empty(n, dtype=torch.int64, device='cuda')
     check(lib.gp_spatial_keys(_p(dpts), n, d, dev.host_ptr(lo), dev.host_ptr(hi), _p(keys), s), 'gp_spatial_keys')

@@ -74,8 +74,9 @@ int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d);
 int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d,
                            const double* scale_host, double nu, double tau, void* ws, int* indptr_dev,
                            int64_t* nnz_host, void* stream);
-/* Z-order (Morton) keys of the points over the bounding box [lo_host, hi_host] (first min(d,3) coordinates): a stable
- * sort by key is the deterministic, spatially local row order the row-blocked sparse operator (gp_bcsr_*) uses. */
+/* Space-filling-curve keys of the points over the bounding box [lo_host, hi_host] (d = 2: Hilbert index; otherwise
+ * Z-order over the first min(d,3) coordinates): a stable sort by key is the deterministic, spatially local row order the
+ * row-blocked sparse operator (gp_bcsr_*) uses. */
 int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo_host, const double* hi_host,
                     int64_t* keys_dev, void* stream);
 /* sort_rows = 1: canonical CSR (rows sorted by column). sort_rows = 0: rows are left in generation order - enough for
