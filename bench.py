@@ -339,7 +339,7 @@ def secondary_measurements():
                          # 12 nnz + 4 (n + 1) + 16 n B; traffic = dram read + write of one launch from the ncu --set full capture
                          # in profiles/r01_spmm_ncu_summary.md (the kernel is L1-data-pipe bound at B = 16: 91 % of peak)
                          'spmm_roofline': {'bound': 'hbm', 'achieved': spm['B16']['algorithmic_GBs'], 'peak': hbm, 'unit': 'GB/s',
-                                           'frac': spm['B16']['frac_of_measured_hbm'], 'traffic': 4.384e9,
+                                           'frac': spm['B16']['frac_of_measured_hbm'], 'traffic': 4.093e9,
                                            'algorithmic_bytes': 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * 16},
                          'evals_per_s': 1.0 / te, 'evals_per_s_further_eta': 1.0 / te2, 'evals_per_s_new_rho': 1.0 / tn,
                          'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],
