@@ -143,3 +143,14 @@ def host_f64(a):
 
 def host_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_key(a):
+    """Cheap identity + content fingerprint of a host array used as a cache key for its device copy: object id, shape
+    and 16 sampled entries (an in-place edit of the array between two evaluations is then very likely to be noticed)."""
+    arr = numpy.asarray(a)
+    flat = arr.reshape(-1)
+    if flat.size == 0:
+        return (id(a), arr.shape)
+    idx = numpy.linspace(0, flat.size - 1, num=min(16, flat.size)).astype(numpy.int64)
+    return (id(a), arr.shape, tuple(float(v) for v in flat[idx]))

@@ -52,7 +52,7 @@ class FusedQuantities(object):
 
 def _rhs_device(K_mixed, X, z):
     """[X z] zero-padded on the device, cached on the operator while X and z are the same objects."""
-    key = (id(X), id(z))
+    key = (dev.host_key(X), dev.host_key(z))
     cache = getattr(K_mixed, '_rhs_cache', None)
     if cache is not None and cache[0] == key:
         return cache[1]

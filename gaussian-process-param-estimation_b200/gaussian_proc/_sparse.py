@@ -684,7 +684,7 @@ class SparseEngine(object):
         row order is cached per (X, z) objects across engines (an optimiser builds a new operator for every rho but
         keeps X and z); the operator-space permutation of it is cached per engine."""
         torch = dev.torch
-        key = (id(X), id(z))
+        key = (dev.host_key(X), dev.host_key(z))
         if getattr(self, '_rhs_cache', None) is not None and self._rhs_cache[0] == key:
             return self._rhs_cache[1]
         Rd = None
@@ -720,7 +720,7 @@ class SparseEngine(object):
         Rd = self._rhs_block(X, z)
         if bool(self.opt.get('overlap', True)) and (self.method == 'slq' or drho):
             self.prefetch_slq(eta)
-        S = self.solve_rhs_block(eta, Rd, (id(X), id(z)), refs=(X, z))
+        S = self.solve_rhs_block(eta, Rd, (dev.host_key(X), dev.host_key(z)), refs=(X, z))
         out = numpy.zeros(8 + 3 * p * p)
         out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
         out[8 + p * p:8 + 2 * p * p] = self.gram(S, S)[:p, :p].ravel()
