@@ -348,6 +348,24 @@ def test_row_blocked_operator_tiny_sizes(n):
     assert abs(eng.logdet(eta) - exact) <= max(4.0 / 1.96 * eng.last_info['half_width'][0], 1e-9 * abs(exact))
 
 
+@pytest.mark.parametrize('d,scale,nu,dens', [(1, [0.02], 1.5, 0.05), (3, [0.2, 0.3, 0.25], 2.5, 0.02), (2, [0.02, 0.05], 3.3, 0.02)])
+def test_row_blocked_operator_other_dimensions(d, scale, nu, dens):
+    """1-D and 3-D points (Z-order keys), anisotropic scale, general nu: the operator equals the canonical CSR"""
+    import torch
+    from gaussian_proc._sparse import SparseEngine, generate_sparse_correlation
+    numpy.random.seed(17 + d)
+    n = 1234
+    pts = numpy.random.rand(n, d)
+    Kd = generate_sparse_correlation(pts, numpy.array(scale), nu, dens, device=True)
+    eng = SparseEngine(Kd, 'slq', {})
+    assert eng.R == 8
+    Ks = Kd.to_scipy()
+    Xh = numpy.random.randn(n, 8)
+    Y = eng.from_op(eng.spmm(1.0, eng.to_op(torch.from_numpy(Xh).cuda()))).cpu().numpy()
+    ref = Ks @ Xh + Xh
+    assert numpy.max(numpy.abs(Y - ref)) <= 1e-12 * numpy.max(numpy.abs(ref))
+
+
 def test_row_blocked_build_search_fallback():
     """Row blocks with more distinct columns than the shared-memory hash table holds are built by the binary-search
     path: an unstructured random symmetric matrix (8 rows share almost nothing) with the identity as row order."""
