@@ -16,7 +16,7 @@ import numpy
 from . import _device as dev
 from ._device import lib, check
 
-__all__ = ['DeviceCorrelation', 'DenseEngine', 'FLAG_TRACEINV', 'FLAG_INVERSE', 'FLAG_DRHO']
+__all__ = ['DeviceCorrelation', 'DenseEngine', 'EigenEngine', 'FLAG_TRACEINV', 'FLAG_INVERSE', 'FLAG_DRHO']
 
 FLAG_TRACEINV = 1
 FLAG_INVERSE = 2
@@ -221,4 +221,91 @@ class DenseEngine(object):
                                  _p(self.A), _p(W) if W is not None else None, _p(self.potrf_ws), _p(self.ws), _p(out),
                                  dev.stream_ptr())
         check(rc, 'gp_loglik_dense')
+        return out
+
+
+class EigenEngine(object):
+    """``imate_method='eigenvalue'`` -- the method the reference's Likelihood hard-codes (likelihood.py:41,
+    mixed_correlation.py:76-79,127-136,172-181,239-248): ONE symmetric eigendecomposition K = V diag(lam) V^T per
+    correlation matrix, after which EVERY eta costs O(n^2 p) instead of a factorisation:
+
+        a = V^T [X z]  (once)          d_k = 1 / (lam_k + eta)
+        logdet = sum log(lam + eta)    tr Kn^-1 = sum d       tr Kn^-2 = sum d^2
+        G = R^T Kn^-1 R = a^T diag(d) a                       H = S^T S = a^T diag(d^2) a
+        C = V^T dK V  (once, two n^3 GEMMs)   tr(Kn^-1 dK) = sum C_kk d_k   Q = S^T dK S = (d a)^T C (d a)
+
+    (turns an eta sweep / root find at fixed rho from one Cholesky per cell into one eigensolve per rho.)
+    The eigensolver is the cuSOLVER LIBRARY routine behind torch.linalg.eigh (0.46 s at n = 8000 on B200); the two n^3
+    products run on this package's DMMA GEMM; the skinny O(n^2 p) products are library GEMV-class calls. Same out[]
+    layout as DenseEngine.fused / gp_loglik_dense."""
+
+    def __init__(self, K):
+        torch = dev.require_cuda()
+        self.K = K
+        self.n, self.npad = K.n, K.npad
+        self.lam, self.V = torch.linalg.eigh(K.data[:K.n, :K.n])
+        self._a = None
+        self._C = None
+        self._Cdiag = None
+        self._kernel_id = None
+
+    def _projected_rhs(self, R_dev):
+        key = R_dev.data_ptr()
+        if self._a is None or self._a[0] != key:
+            self._a = (key, dev.torch.matmul(self.V.t(), R_dev[:self.n]))
+        return self._a[1]
+
+    def _projected_dK(self):
+        """C = V^T dK V (n x n); dK is generated into a padded buffer, the products run on gp_dgemm_f64."""
+        torch = dev.torch
+        K = self.K
+        if not K.has_kernel():
+            raise ValueError('d/d(correlation_scale) needs a correlation generated by generate_correlation('
+                             '..., device=True) or MixedCorrelation.set_kernel(points, correlation_scale, nu).')
+        if not K.isotropic():
+            raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
+        kid = (K.points.data_ptr(), tuple(K.correlation_scale.tolist()), float(K.nu))
+        if self._C is not None and self._kernel_id == kid:
+            return self._C, self._Cdiag
+        n, npad = self.n, self.npad
+        f64 = torch.float64
+        T1 = torch.empty((npad, npad), dtype=f64, device='cuda')
+        dK = torch.empty((npad, npad), dtype=f64, device='cuda')
+        s = dev.stream_ptr()
+        check(lib.gp_matern_dense(_p(K.points), n, K.points.shape[1], dev.host_ptr(K.correlation_scale), float(K.nu),
+                                  _p(T1), npad, _p(dK), s), 'gp_matern_dense')          # T1 <- K (discarded), dK <- dK/drho
+        Vp = torch.zeros((npad, npad), dtype=f64, device='cuda')
+        Vp[:n, :n].copy_(self.V)
+        # T1 = dK V          (A = dK stored [m][k], B = V stored [k][n])
+        check(lib.gp_dgemm_f64(0, 1, _p(T1), npad, _p(dK), npad, _p(Vp), npad, npad, npad, npad, 1.0, 0.0, 0, 0, s),
+              'gp_dgemm_f64')
+        # C = V^T T1         (A = V stored [k][m], B = T1 stored [k][n]); written over dK
+        check(lib.gp_dgemm_f64(1, 1, _p(dK), npad, _p(Vp), npad, _p(T1), npad, npad, npad, npad, 1.0, 0.0, 0, 0, s),
+              'gp_dgemm_f64')
+        self._C = dK[:n, :n]
+        self._Cdiag = torch.diagonal(self._C).clone()
+        self._kernel_id = kid
+        return self._C, self._Cdiag
+
+    def fused(self, eta, R_dev, p, flags):
+        """Returns out[] (device tensor, layout of gp_loglik_dense); info = 1 when K + eta I is not positive definite."""
+        torch = dev.torch
+        out = torch.zeros(int(lib.gp_loglik_out_len(p)), dtype=torch.float64, device='cuda')
+        sh = self.lam + float(eta)
+        bad = bool((sh <= 0).any().item())
+        if bad:
+            out[4] = 1.0
+            return out
+        d = 1.0 / sh
+        a = self._projected_rhs(R_dev)[:, :p]
+        da = a * d[:, None]
+        out[0] = sh.log().sum()
+        out[1] = d.sum()
+        out[2] = (d * d).sum()
+        out[8:8 + p * p] = torch.matmul(a.t(), da).reshape(-1)
+        out[8 + p * p:8 + 2 * p * p] = torch.matmul(da.t(), da).reshape(-1)
+        if flags & FLAG_DRHO:
+            C, Cdiag = self._projected_dK()
+            out[3] = (Cdiag * d).sum()
+            out[8 + 2 * p * p:8 + 3 * p * p] = torch.matmul(da.t(), torch.matmul(C, da)).reshape(-1)
         return out

@@ -78,7 +78,11 @@ def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False
     if drho:
         flags |= FLAG_DRHO
     Rd = _rhs_device(K_mixed, X, z)
-    out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags)
+    if getattr(K_mixed, 'imate_method', None) == 'eigenvalue':
+        # one eigendecomposition per matrix, O(n^2 p) per eta (the reference's default method, likelihood.py:41)
+        out = K_mixed.eigen_engine().fused(float(eta), Rd, m + 1, flags)
+    else:
+        out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags)
     return (out, n, m, float(eta), flags, dev.torch.cuda.current_stream())
 
 

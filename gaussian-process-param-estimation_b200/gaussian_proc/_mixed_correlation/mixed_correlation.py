@@ -24,7 +24,9 @@ class MixedCorrelation(object):
     'eigenvalue' (the method the reference's Likelihood hard-codes, likelihood.py:41) computes all eigenvalues of K once
     in __init__ like mixed_correlation.py:76-79 -- here with the cuSOLVER symmetric eigensolver behind
     torch.linalg.eigvalsh, a LIBRARY call (own kernel: next) -- after which logdet / traceinv / trace are
-    O(n) reductions over lambda + eta; solves still use the native Cholesky engine.
+    O(n) reductions over lambda + eta; ``solve`` uses the native Cholesky engine, and the fused likelihood evaluation
+    (log-likelihood + gradient) runs on the full eigendecomposition (_dense.EigenEngine): one eigensolve per matrix,
+    O(n^2 p) per eta.
     ``interpolate=True``: tr (K + eta I)^-1 is interpolated in eta from evaluations at ``interpolant_points``
     (_interpolate_traceinv.py, the role of imate.InterpolateTraceInv; rational polynomial scheme, parity unpinned).
     """
@@ -55,9 +57,18 @@ class MixedCorrelation(object):
             self.K = K
             self.engine = DenseEngine(K)
             self.K_eigenvalues = None
+            self._eigen = None
             if imate_method == 'eigenvalue':
                 from .. import _device as dev
                 self.K_eigenvalues = dev.torch.linalg.eigvalsh(K.data[:K.n, :K.n])
+
+    def eigen_engine(self):
+        """Full eigendecomposition of K, computed on first use by the fused likelihood evaluation under
+        imate_method='eigenvalue' (_dense.EigenEngine): every eta is then O(n^2 p)."""
+        if self._eigen is None:
+            from .._dense import EigenEngine
+            self._eigen = EigenEngine(self.K)
+        return self._eigen
 
     # -- extension: generator parameters for d/d(correlation_scale) when K came in as a plain array
     def set_kernel(self, points, correlation_scale, nu):

@@ -63,6 +63,26 @@ class _GpuRowEvaluator(object):
         return out
 
 
+class _GpuEigenRowEvaluator(object):
+    """All eta cells of one rho through ONE eigendecomposition of K(rho) (imate_method='eigenvalue', the reference's
+    default, likelihood.py:41; _dense.EigenEngine): every cell after the eigensolve is O(n^2 p). Pays off for long eta
+    rows (about 30 cells at n = 8000); the eigensolver itself is the cuSOLVER library routine."""
+
+    def __init__(self, points, z, X, nu):
+        from . import _device as dev
+        dev.require_cuda()
+        self.points = numpy.ascontiguousarray(points, dtype=float)
+        self.z, self.X, self.nu = z, X, float(nu)
+
+    def row(self, rho, etas):
+        from .generate_correlation.generate_correlation import generate_dense_correlation
+        from ._mixed_correlation import MixedCorrelation
+        from ._likelihood import ProfileLikelihood
+        K = generate_dense_correlation(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu)
+        Km = MixedCorrelation(K, imate_method='eigenvalue')
+        return numpy.array([ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta) for eta in etas])
+
+
 class _GpuSparseRowEvaluator(object):
     """All eta cells of one rho for the kernel-threshold sparse correlation: the CSR matrix and its row-blocked
     operator are generated once per rho; every eta is one stochastic evaluation (batched SLQ + CG, _sparse.py)."""
@@ -85,11 +105,12 @@ class _GpuSparseRowEvaluator(object):
 
 
 def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, sparse=False, density=1e-3,
-                    imate_options=None):
+                    imate_options=None, method='cholesky'):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
     on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
     `concurrency` cells in flight per GPU (dense), or, with ``sparse``, the stochastic evaluator on the kernel-threshold
-    correlation of the given ``density`` (``imate_options``: estimator settings, see _sparse.DEFAULTS)."""
+    correlation of the given ``density`` (``imate_options``: estimator settings, see _sparse.DEFAULTS).
+    ``method='eigenvalue'`` (dense): one eigendecomposition per rho instead of one Cholesky per cell."""
     rhos = numpy.asarray(rhos, dtype=float)
     etas = numpy.asarray(etas, dtype=float)
     rank, world = gpd.rank_world()
@@ -98,6 +119,8 @@ def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, 
         rows = None
     elif sparse:
         rows = _GpuSparseRowEvaluator(points, z, X, nu, density, imate_options)
+    elif method == 'eigenvalue':
+        rows = _GpuEigenRowEvaluator(points, z, X, nu)
     else:
         rows = _GpuRowEvaluator(points, z, X, nu, concurrency)
     local = numpy.empty(((end - begin) * len(etas), 5))

@@ -369,3 +369,33 @@ def test_trace_interpolation_through_mixed_correlation(gp, problem):
     d_i = ProfileLikelihood.log_likelihood_der1_eta(z, X, Ki, numpy.log10(0.5))
     d_e = ProfileLikelihood.log_likelihood_der1_eta(z, X, Ke, numpy.log10(0.5))
     assert abs(d_i - d_e) <= 0.5 * 2e-2 * abs(Ke.traceinv(0.5)) + 1e-9
+
+
+def test_eigen_engine_matches_cholesky_engine(gp):
+    """imate_method='eigenvalue': the fused evaluation on ONE eigendecomposition (every eta O(n^2 p)) returns the numbers
+    of the Cholesky path: l^, d l^/d eta, d l^/d rho to 1e-9 (eta >= 1e-2), also through likelihood_grid."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood, DirectLikelihood
+    from gaussian_proc.sweep import likelihood_grid
+    from oracle import data_utilities as du
+    numpy.random.seed(3)
+    pts = numpy.random.rand(1100, 2)
+    z, X = du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2)
+    K = gp.generate_correlation(pts, 0.12, 2.5, device=True)
+    Ke, Kc = MixedCorrelation(K, imate_method='eigenvalue'), MixedCorrelation(K)
+    for eta in (1e-2, 0.1, 1.0, 10.0, 300.0):
+        a = ProfileLikelihood.log_likelihood_and_gradient(z, X, Ke, eta)
+        b = ProfileLikelihood.log_likelihood_and_gradient(z, X, Kc, eta)
+        tol = 1e-9 if eta >= 0.1 else 1e-8
+        for x, y in zip(a, b):
+            assert abs(x - y) <= tol * max(abs(y), 1.0), (eta, a, b)
+    h = [0.3, 0.2]
+    ja = DirectLikelihood.log_likelihood_jacobian(z, X, Ke, False, h)
+    jb = DirectLikelihood.log_likelihood_jacobian(z, X, Kc, False, h)
+    assert rel(ja, jb) <= 1e-9
+    with pytest.raises(numpy.linalg.LinAlgError):
+        ProfileLikelihood.log_likelihood_and_gradient(z, X, Ke, -2.0)
+    rhos, etas = [0.1, 0.15], numpy.logspace(-1, 1, 5)
+    Ge = likelihood_grid(pts, z, X, 2.5, rhos, etas, method='eigenvalue')
+    Gc = likelihood_grid(pts, z, X, 2.5, rhos, etas)
+    assert rel(Ge, Gc) <= 1e-9

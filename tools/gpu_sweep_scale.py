@@ -20,6 +20,7 @@ n_rho = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n_eta = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 8000
 sparse = len(sys.argv) > 4 and sys.argv[4] == 'sparse'
+eigen = len(sys.argv) > 4 and sys.argv[4] == 'eigen'
 pts, z, X = make_inputs(n)
 kw = {}
 if sparse:      # configs[3] family: nu = 0.5, rho around 0.005, density 1e-3, eta >= 10 (hard-thresholded K is indefinite)
@@ -31,6 +32,8 @@ else:
     rhos = numpy.linspace(0.05, 0.3, n_rho)
     etas = numpy.logspace(-2, 2, n_eta)
     nu = 2.5
+    if eigen:
+        kw = dict(method='eigenvalue')
 likelihood_grid(pts, z, X, nu, rhos[:world], etas[:min(4, n_eta)], **kw)            # warm-up: one small row per rank
 torch.cuda.synchronize()
 if world > 1:
@@ -44,7 +47,7 @@ if world > 1:
 dt = float(dt.item())
 if rank == 0:
     i, j = numpy.unravel_index(numpy.nanargmax(G[:, :, 0]), G[:, :, 0].shape)
-    print(json.dumps({'world': world, 'n': n, 'sparse': sparse, 'cells': n_rho * n_eta, 'seconds': dt, 'cells_per_s': n_rho * n_eta / dt,
+    print(json.dumps({'world': world, 'n': n, 'sparse': sparse, 'method': 'eigenvalue' if eigen else ('slq' if sparse else 'cholesky'), 'cells': n_rho * n_eta, 'seconds': dt, 'cells_per_s': n_rho * n_eta / dt,
                       'tflops_total': None if sparse else n_rho * n_eta * float(n) ** 3 / dt * 1e-12, 'finite': bool(numpy.isfinite(G).all()),
                       'argmax': {'rho': float(rhos[i]), 'eta': float(etas[j]), 'lp': float(G[i, j, 0]),
                                  'dlp_deta': float(G[i, j, 1]), 'dlp_drho': float(G[i, j, 2])}}))
