@@ -59,12 +59,14 @@ class MixedCorrelation(object):
             self.K_eigenvalues = None
             self._eigen = None
             if imate_method == 'eigenvalue':
-                from .. import _device as dev
-                self.K_eigenvalues = dev.torch.linalg.eigvalsh(K.data[:K.n, :K.n])
+                # ONE symmetric eigensolve (values and vectors: the vectors cost ~10 % more than the values alone)
+                from .._dense import EigenEngine
+                self._eigen = EigenEngine(K)
+                self.K_eigenvalues = self._eigen.lam
 
     def eigen_engine(self):
-        """Full eigendecomposition of K, computed on first use by the fused likelihood evaluation under
-        imate_method='eigenvalue' (_dense.EigenEngine): every eta is then O(n^2 p)."""
+        """The eigendecomposition of K behind imate_method='eigenvalue' (_dense.EigenEngine): the fused likelihood
+        evaluation costs O(n^2 p) per eta on it."""
         if self._eigen is None:
             from .._dense import EigenEngine
             self._eigen = EigenEngine(self.K)
