@@ -196,6 +196,17 @@ def secondary_measurements():
     out['sweep_n8k'] = {'cells': int(G.shape[0] * G.shape[1]), 'cells_per_s': G.shape[0] * G.shape[1] / dt,
                         'workload': 'configs[2] slice: n=8000, 3 rho x 16 eta, l^ + d/d eta + d/d rho per cell',
                         'tflops': G.shape[0] * G.shape[1] * 8000.0 ** 3 / dt * 1e-12}
+    # the same rows through imate_method='eigenvalue' (the reference's default): one eigendecomposition per rho (cuSOLVER
+    # library eigensolver) + O(n^2 p) per eta - pays off on long eta rows
+    etas64 = numpy.logspace(-2, 2, 64)
+    likelihood_grid(pts, z, X, NU, [0.1], etas64[:2], method='eigenvalue')
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Ge = likelihood_grid(pts, z, X, NU, [0.1, 0.2], etas64, method='eigenvalue')
+    torch.cuda.synchronize()
+    dte = time.perf_counter() - t0
+    out['sweep_n8k_eigenvalue'] = {'cells': int(Ge.shape[0] * Ge.shape[1]), 'cells_per_s': Ge.shape[0] * Ge.shape[1] / dte,
+                                   'workload': 'configs[2] rows: n=8000, 2 rho x 64 eta, one library eigensolve per rho'}
     # configs[3]: sparse n = 2^20, nu = 0.5, rho = 0.005, density 1e-3
     n = 2 ** 20
     numpy.random.seed(0)
