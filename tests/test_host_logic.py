@@ -139,3 +139,59 @@ def test_trace_interpolation_rational_polynomial():
     assert abs(six.interpolate(20.0) - exact(20.0)) <= 1e-2 * exact(20.0)
     with pytest.raises(ValueError):
         itp.InterpolateTraceInv(exact, 400, [1.0, 2.0])
+
+
+def test_lanczos_block_quadrature_and_solution_coefficients():
+    """Host part of SLQ (gaussian_proc/_sparse.py::lanczos_block_quadrature) on a NumPy Lanczos run: with m = n steps the
+    Gauss quadratures are exact, the coefficients reproduce A^-1 v from the UNNORMALISED Lanczos vectors, the residual
+    estimate beta_m |y_m| matches the true residual for m < n, and a shift of the diagonal (T(eta) = T + eta I) serves
+    another eta from the same run (shift invariance, mixed_correlation.py:44 AffineMatrixFunction)."""
+    from gaussian_proc._sparse import lanczos_block_quadrature, lanczos_quadrature
+    rng = numpy.random.RandomState(1)
+    n, B = 40, 3
+    M = rng.randn(n, n)
+    A = M @ M.T / n + 0.5 * numpy.eye(n)
+    V = rng.choice([-1.0, 1.0], size=(n, B))
+
+    def lanczos(A, V, m):
+        al, be = numpy.zeros((m, V.shape[1])), numpy.zeros((m, V.shape[1]))
+        U = numpy.zeros((m, n, V.shape[1]))
+        for c in range(V.shape[1]):
+            u, uprev, s, sprev, bprev = V[:, c].copy(), numpy.zeros(n), 1.0 / numpy.linalg.norm(V[:, c]), 0.0, 0.0
+            for j in range(m):
+                U[j, :, c] = u
+                w = s * (A @ u)
+                al[j, c] = s * (u @ w)
+                unext = w - al[j, c] * s * u - bprev * sprev * uprev
+                # full reorthogonalisation keeps the m = n run exact
+                for i in range(j + 1):
+                    q = U[i, :, c] / numpy.linalg.norm(U[i, :, c])
+                    unext -= (q @ unext) * q
+                be[j, c] = numpy.linalg.norm(unext)
+                uprev, sprev, bprev = u, s, be[j, c]
+                u, s = unext, (1.0 / be[j, c] if be[j, c] > 1e-300 else 0.0)
+        return al, be, U
+
+    al, be, U = lanczos(A, V, n)
+    quad, tmin, coef, resid = lanczos_block_quadrature(al, be, numpy.sqrt(float(n)))
+    lam = numpy.linalg.eigvalsh(A)
+    W = numpy.linalg.eigh(A)[1]
+    for c in range(B):
+        w2 = (W.T @ V[:, c]) ** 2 / n
+        assert abs(quad[c, 0] - numpy.sum(w2 * numpy.log(lam))) <= 1e-10
+        assert abs(quad[c, 1] - numpy.sum(w2 / lam)) <= 1e-10
+        x = numpy.einsum('j,ji->i', coef[:, c], U[:, :, c])
+        assert numpy.max(numpy.abs(x - numpy.linalg.solve(A, V[:, c]))) <= 1e-9
+        ref, t, k = lanczos_quadrature(al[:, c], be[:, c], [numpy.log], return_size=True)
+        assert abs(ref[0] - quad[c, 0]) <= 1e-12
+    # truncated run: residual estimate == true relative residual; shifted tridiagonal == run on A + eta I
+    m = 12
+    al, be, U = lanczos(A, V, m)
+    eta = 0.7
+    _, _, coef, resid = lanczos_block_quadrature(al + eta, be, numpy.sqrt(float(n)))
+    for c in range(B):
+        x = numpy.einsum('j,ji->i', coef[:, c], U[:, :, c])
+        true = numpy.linalg.norm(V[:, c] - (A + eta * numpy.eye(n)) @ x) / numpy.linalg.norm(V[:, c])
+        assert abs(resid[c] - true) <= 1e-8 * max(true, 1e-3)
+    al2, be2, _ = lanczos(A + eta * numpy.eye(n), V, m)
+    assert numpy.max(numpy.abs(al2 - (al + eta))) <= 1e-10 and numpy.max(numpy.abs(be2 - be)) <= 1e-10
