@@ -30,15 +30,18 @@ class Likelihood(object):
         """likelihood.py:55-61"""
         return DirectLikelihood.log_likelihood(z, self.X, self.K_mixed, False, hyperparam)
 
-    def maximize_log_likelihood(self, z, plot=False):
+    def maximize_log_likelihood(self, z, plot=False, interval_eta=None):
         """likelihood.py:67-102 ('direct' -> trust-exact over (sigma, sigma0); 'profiled' -> root of d l/d eta on
-        eta in [1e-4, 1e3])."""
+        eta in [1e-4, 1e3], the reference's hard-coded interval :88). ``interval_eta`` overrides it: a hard-thresholded
+        sparse K is indefinite, so its search has to start above -lambda_min(K) (the legacy sparse runs
+        used [1, 1e3], examples/CompareVariousNumberOfPoints.py:72)."""
         if plot:
             raise NotImplementedError('plotting is out of scope of the B200 build')
         if self.likelihood_method == 'direct':
             results = DirectLikelihood.maximize_log_likelihood(z, self.X, self.K_mixed)
         elif self.likelihood_method == 'profiled':
-            results = ProfileLikelihood.find_log_likelihood_der1_zeros(z, self.X, self.K_mixed, [1e-4, 1e+3])
+            results = ProfileLikelihood.find_log_likelihood_der1_zeros(
+                z, self.X, self.K_mixed, [1e-4, 1e+3] if interval_eta is None else list(interval_eta))
         else:
             raise ValueError('"likelihood_method" should be "direct" or "profiled".')
         return results

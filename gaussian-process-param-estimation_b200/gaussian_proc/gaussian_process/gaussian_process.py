@@ -17,9 +17,10 @@ class GaussianProcess(object):
                                      imate_options=imate_options)
         self.results = None
 
-    def train(self, z, plot=False):
-        """Finds the hyperparameters; prints the result dict like the reference (:52-59) and also returns it."""
-        results = self.likelihood.maximize_log_likelihood(z, plot=plot)
+    def train(self, z, plot=False, interval_eta=None):
+        """Finds the hyperparameters; prints the result dict like the reference (:52-59) and also returns it.
+        ``interval_eta``: search interval of the profiled method (default: the reference's [1e-4, 1e3])."""
+        results = self.likelihood.maximize_log_likelihood(z, plot=plot, interval_eta=interval_eta)
         self.results = results
         print(results)
         return results

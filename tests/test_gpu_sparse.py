@@ -199,6 +199,24 @@ def test_likelihood_through_sparse_operator(sparse_problem):
     pts, z, X, Kd = sparse_problem
     lk = Likelihood(X, Kd.to_scipy(), likelihood_method='profiled')
     assert lk.K_mixed.sparse and lk.K_mixed.imate_method == 'slq'
+    # end to end: GaussianProcess.train on a sparse K (root of d l/d eta; the search interval starts above -lambda_min
+    # of the hard-thresholded K) against the oracle's root finder on the densified matrix with exact traces
+    from gaussian_proc import GaussianProcess
+    from gaussian_proc._sparse import generate_sparse_correlation
+    from oracle import likelihood as L, data_utilities as du
+    numpy.random.seed(1)
+    p2 = numpy.random.rand(1500, 2)
+    z2, X2 = du.generate_data(p2, 0.2), du.generate_basis_functions(p2, 2)
+    K2 = generate_sparse_correlation(p2, numpy.array([0.2, 0.2]), 0.5, 0.1, device=True)
+    opts = {'seed': 0, 'lanczos_degree': 60, 'min_num_samples': 512, 'max_num_samples': 512, 'batch': 32, 'cg_tol': 1e-10}
+    res = GaussianProcess(X2, K2, likelihood_method='profiled', imate_options=opts).train(z2, interval_eta=[8.0, 1e3])
+    ref = L.ProfileLikelihood.find_log_likelihood_der1_zeros(z2, X2, L.MixedCorrelation(K2.to_scipy().toarray(), 'cholesky'),
+                                                             [8.0, 1e3])
+    assert res['success'] and ref['success']
+    assert abs(numpy.log10(res['eta']) - numpy.log10(ref['eta'])) <= 0.15        # stochastic traces: 512 probes
+    assert abs(res['sigma0'] - ref['sigma0']) <= 0.05 * ref['sigma0']
+    with pytest.raises(numpy.linalg.LinAlgError):                                  # the reference's [1e-4, 1e3]: indefinite
+        GaussianProcess(X2, K2, likelihood_method='profiled', imate_options={'min_num_samples': 16, 'max_num_samples': 16}).train(z2)
 
 
 def test_sparse_loglik_and_gradient(sparse_problem):
