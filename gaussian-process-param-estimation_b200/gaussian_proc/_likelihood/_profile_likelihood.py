@@ -115,6 +115,10 @@ class ProfileLikelihood(object):
             return numpy.sqrt(numpy.dot(z, z - v) / (n - m))
 
         print('Find root of log likelihood derivative ...')
+        if getattr(K_mixed, 'sparse', False):
+            # the root find asks many eta of this operator: keep the Krylov run of [X z] from the first one on
+            if 'eager_rhs_basis' not in K_mixed.imate_options:
+                K_mixed.engine.opt['eager_rhs_basis'] = True
         f = partial(ProfileLikelihood.log_likelihood_der1_eta, z, X, K_mixed)
         bracket = [numpy.log10(interval_eta[0]), numpy.log10(interval_eta[1])]
         bracket_found, bracket, bracket_values = find_interval_with_sign_change(f, bracket, num_bracket_trials, args=(), )

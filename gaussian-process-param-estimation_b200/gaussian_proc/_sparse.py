@@ -28,7 +28,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
                 lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True, overlap=True,
-                shift_reuse=True, solve_degree=None)
+                shift_reuse=True, solve_degree=None, eager_rhs_basis=False)
 
 
 def _p(t):
@@ -440,9 +440,10 @@ class SparseEngine(object):
 
     def solve_rhs_block(self, eta, Rop, key, refs=None):
         """S = (K + eta I)^-1 R for the (cached) right-hand-side block of the likelihood, operator space. The first eta
-        asked of this operator is solved by batched CG; from the second DISTINCT eta on, one batched Lanczos run on R
-        (degree ~ twice the CG iteration count) is kept and every eta is served from it (shift invariance), falling
-        back to CG for an eta whose Lanczos residual misses the CG tolerance."""
+        asked of this operator is solved by batched CG; from the second DISTINCT eta on (from the first with the option
+        ``eager_rhs_basis``, which sweeps and the root finder set: they know more eta will follow), one batched Lanczos
+        run on R (degree ~ twice the CG iteration count, 48 when unknown) is kept and every eta is served from it (shift
+        invariance), falling back to CG for an eta whose Lanczos residual misses the CG tolerance."""
         torch = dev.torch
         eta = float(eta)
         if not bool(self.opt.get('shift_reuse', True)):
@@ -452,10 +453,10 @@ class SparseEngine(object):
         if ent is None:
             seen = self._rhs_etas.setdefault(key, (set(), refs))[0]      # refs keep X, z alive: the ids stay unique
             seen.add(eta)
-            if len(seen) < 2:
+            if len(seen) < 2 and not bool(self.opt.get('eager_rhs_basis', False)):
                 return self.solve_dev(eta, Rop.clone())
             m = int(self.opt.get('solve_degree') or min(128, max(int(self.opt['lanczos_degree']),
-                                                                   2 * int(getattr(self, 'last_cg_iterations', 32)))))
+                                                                   2 * int(getattr(self, 'last_cg_iterations', 24)))))
             basis = self._new_basis(m, B)
             a, b = self._lanczos(eta, Rop, m, basis)
             norms = numpy.sqrt(numpy.maximum(self.col_dot(Rop, Rop), 0.0))

@@ -93,6 +93,7 @@ class _GpuSparseRowEvaluator(object):
         self.points = numpy.ascontiguousarray(points, dtype=float)
         self.z, self.X, self.nu, self.density = z, X, float(nu), float(density)
         self.options = dict(imate_options or {})
+        self.options.setdefault('eager_rhs_basis', True)      # every row asks several eta of one operator
 
     def row(self, rho, etas):
         from ._sparse import generate_sparse_correlation
