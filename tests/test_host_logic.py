@@ -195,3 +195,25 @@ def test_lanczos_block_quadrature_and_solution_coefficients():
         assert abs(resid[c] - true) <= 1e-8 * max(true, 1e-3)
     al2, be2, _ = lanczos(A + eta * numpy.eye(n), V, m)
     assert numpy.max(numpy.abs(al2 - (al + eta))) <= 1e-10 and numpy.max(numpy.abs(be2 - be)) <= 1e-10
+
+
+def test_recorded_bench_line_follows_the_contract():
+    """The committed bench record (profiles/r01_bench_1gpu_final.json, written by `python bench.py` on a B200) carries
+    every key of the driver's contract: headline metric, roofline, cpu_baseline, e2e, clocks, launch count."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, 'profiles', 'r01_bench_1gpu_final.json')).read().strip().splitlines()[-1])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'cpu_baseline', 'e2e', 'gpu_launches', 'clocks'):
+        assert k in line, k
+    assert line['unit'] == 'evals/s' and line['dtype'] == 'f64' and line['higher_is_better'] is True
+    assert line['vs_baseline'] is None and 'workload' in line['config'] and 'l2' in line['config']
+    r = line['roofline']
+    assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12
+    assert r['traffic'] is None or r['traffic'] > 0
+    assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(line['cpu_baseline'])
+    assert set(('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')) <= set(line['e2e'])
+    assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
+    assert line['gpu_launches'] > 0 and not line['clocks']['reasons']
+    assert abs(line['value'] - line['steps'] * line['n_gpus'] / (line['ms_per_step'] * line['steps'] * 1e-3)) < 1e-9
