@@ -345,12 +345,12 @@ def secondary_measurements():
     out['sparse_n1M'] = {'workload': 'configs[3]: n=2^20 random 2-D points, nu=0.5, rho=0.005, density=1e-3, eta=10',
                          'nnz': nnz, 'generate_s': tg, 'generate_GBs': (20.0 * nnz + 4.0 * (n + 1)) / tg * 1e-9,
                          'row_blocked_build_s': tb, 'row_blocked_fill_ratio': fill,
-                         'spmm': spm, 'spmm_kernel': 'gp::bcsr8_spmm_dmma_kernel (8x1 row blocks, DMMA.8x8x4)',
+                         'spmm': spm, 'spmm_kernel': 'gp::bcsr8_spmm_dmma_kernel<B, DOT, 2> (16x1 row blocks, two DMMA.8x8x4 per gathered fragment)',
                          # the sparse hot kernel against the HBM roofline (B = 16, the estimators' batch): algorithmic bytes =
                          # 12 nnz + 4 (n + 1) + 16 n B; traffic = dram read + write of one launch from the ncu --set full capture
-                         # in profiles/r01_spmm_ncu_summary.md (the kernel is L1-data-pipe bound at B = 16: 91 % of peak)
+                         # in profiles/r01_spmm_ncu_summary.md (16 x 1 blocks: DRAM 77 % of peak, L1 data pipe 70 % at B = 16)
                          'spmm_roofline': {'bound': 'hbm', 'achieved': spm['B16']['algorithmic_GBs'], 'peak': hbm, 'unit': 'GB/s',
-                                           'frac': spm['B16']['frac_of_measured_hbm'], 'traffic': 4.093e9,
+                                           'frac': spm['B16']['frac_of_measured_hbm'], 'traffic': 4.491e9,
                                            'algorithmic_bytes': 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * 16},
                          'evals_per_s': 1.0 / te, 'evals_per_s_further_eta': 1.0 / te2, 'evals_per_s_new_rho': 1.0 / tn,
                          'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],

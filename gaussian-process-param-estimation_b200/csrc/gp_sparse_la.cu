@@ -175,8 +175,11 @@ constexpr int HCAP = 2048, HMAX = 1536;
 
 // Position of (block-column slot, row k) in the value stream: groups of four block-columns are stored in DMMA A-fragment
 // order [row][block-column in group] so that lane (g, t) of the SpMM warp reads 32 consecutive doubles (bptr entries are
-// multiples of 4, R = 8).
-__device__ __forceinline__ int64_t bval_pos(int64_t slot, int k) { return (slot >> 2) * 32 + k * 4 + (slot & 3); }
+// multiples of 4; R = 8 or 16 rows = one or two 8-row fragments).
+template <int R>
+__device__ __forceinline__ int64_t bval_pos(int64_t slot, int k) {
+    return (slot >> 2) * (4 * R) + (k >> 3) * 32 + (k & 7) * 4 + (slot & 3);      // R = 16: two 8-row fragments per group
+}
 
 template <int R, int PASS>
 __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s, const int* len, const int* __restrict__ inv_order,
@@ -212,10 +215,10 @@ __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s,
                     }
                 }
 #pragma unroll
-                for (int kk = 0; kk < R; ++kk) bvals[bval_pos(slot, kk)] = v[kk];
+                for (int kk = 0; kk < R; ++kk) bvals[bval_pos<R>(slot, kk)] = v[kk];
                 if (ddata) {
 #pragma unroll
-                    for (int kk = 0; kk < R; ++kk) bdvals[bval_pos(slot, kk)] = dv[kk];
+                    for (int kk = 0; kk < R; ++kk) bdvals[bval_pos<R>(slot, kk)] = dv[kk];
                 }
             }
             running += __popc(m);
@@ -226,8 +229,7 @@ __device__ __forceinline__ int bcsr_block_search(int lane, int rb, const int* s,
 
 template <int R, int PASS>
 __global__ void __launch_bounds__(128)
-bcsr_build_kernel(  // R == 8: bval_pos is the 8-row fragment layout
-    int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
+bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ inv_order, const int* __restrict__ indptr,
                   const int* __restrict__ indices, const double* __restrict__ data, const double* __restrict__ ddata,
                   int* nblk, const int64_t* __restrict__ bptr, int* bidx, double* bvals, double* bdvals, int* searched) {
     __shared__ int hkey[4][HCAP];
@@ -285,7 +287,7 @@ bcsr_build_kernel(  // R == 8: bval_pos is the 8-row fragment layout
             __syncwarp();
             if (running > HMAX) overflow = true;
             if (PASS == 1 && valid && !overflow) {
-                const int64_t o = bval_pos(base + slot, k);
+                const int64_t o = bval_pos<R>(base + slot, k);
                 bvals[o] = data[s[k] + t];
                 if (ddata) bdvals[o] = ddata[s[k] + t];
                 if (isnew) bidx[base + slot] = inv_order ? inv_order[c] : c;
@@ -312,8 +314,8 @@ bcsr_build_kernel(  // R == 8: bval_pos is the 8-row fragment layout
         bidx[slot] = inv_order ? inv_order[c0] : c0;
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) {
-            bvals[bval_pos(slot, kk)] = 0.0;
-            if (ddata) bdvals[bval_pos(slot, kk)] = 0.0;
+            bvals[bval_pos<R>(slot, kk)] = 0.0;
+            if (ddata) bdvals[bval_pos<R>(slot, kk)] = 0.0;
         }
     }
 }
@@ -327,7 +329,8 @@ bcsr_build_kernel(  // R == 8: bval_pos is the 8-row fragment layout
 // consecutive columns of one Y row. Index and values are streamed past L1 (ld.global.cs): L1 is kept for X.
 // Epilogue: Y = scale[c] (A X + eta X) (scale optional) and, with DOT, partial[cta][c] = sum over the CTA's 64 rows
 // of X[i][c] Y[i][c] (fixed order) - the Lanczos alpha / CG p^T A p reduction without another pass over the vectors.
-template <int B, bool DOT>
+// H = 1: 8 x 1 row blocks; H = 2: 16 x 1 row blocks (two A fragments and two MMAs per gathered B fragment).
+template <int B, bool DOT, int H>
 __global__ void __launch_bounds__(256)
 bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
                        double eta, const double* __restrict__ X, const double* __restrict__ scale, double* __restrict__ Y,
@@ -336,12 +339,14 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;     // DMMA.8x8x4 fragments: A[g][t], B[t][g], D[g][2t .. 2t+1]
     const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const bool live = rb * 8 < n;
+    const bool live = rb * (8 * H) < n;
     if (!DOT && !live) return;
     const int64_t p0 = live ? bptr[rb] : 0, p1 = live ? bptr[rb + 1] : 0;   // p1 - p0 is a multiple of 4
-    double acc[NT][2];
+    double acc[H][NT][2];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[h][j][0] = acc[h][j][1] = 0.0;
     const bool colok = (B >= 8) || (g < B);
     const int coff = (B >= 8) ? g * NT : (colok ? g : 0);
     const double* aptr = bvals + lane;          // A fragment order: element (row g, block-column t) at 4 g + t = lane
@@ -362,44 +367,54 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     int64_t p = p0;
     for (; p + 4 * U <= p1; p += 4 * U) {
         int col[U];
-        double a[U], x[U][NT];
+        double a[U][H], x[U][NT];
 #pragma unroll
         for (int u = 0; u < U; ++u) col[u] = __ldcs(bidx + p + 4 * u + t);
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u] = __ldcs(aptr + (p + 4 * u) * 8);
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < H; ++h) a[u][h] = __ldcs(aptr + (p + 4 * u) * (8 * H) + 32 * h);
 #pragma unroll
         for (int u = 0; u < U; ++u) load_x(col[u], x[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a[u], x[u][j]);
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[h][j][0], acc[h][j][1], a[u][h], x[u][j]);
     }
     for (; p < p1; p += 4) {
         const int col = __ldcs(bidx + p + t);
-        const double a = __ldcs(aptr + p * 8);
-        double x[NT];
+        double a[H], x[NT];
+#pragma unroll
+        for (int h = 0; h < H; ++h) a[h] = __ldcs(aptr + p * (8 * H) + 32 * h);
         load_x(col, x);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, x[j]);
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[h][j][0], acc[h][j][1], a[h], x[j]);
     }
-    const int row = rb * 8 + g;
     constexpr int NC = (B >= 8) ? 2 * NT : 2;               // result columns of this lane, from column c0
     const int c0 = (B >= 8) ? 2 * t * NT : 2 * t;
     double dsum[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) dsum[k] = 0.0;
-    if (live && row < n) {
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            // tile j, fragment column cc in {2t, 2t+1} is the true column cc * NT + j: k = i * NT + j
-            const int i = (B >= 8) ? k / NT : k, j = (B >= 8) ? k % NT : 0;
-            if (B >= 8 || c0 + k < B) {
-                const int64_t o = (int64_t)row * B + c0 + k;
-                const double xv = X[o];
-                double y = acc[j][i] + eta * xv;
-                if (scale) y *= scale[c0 + k];
-                Y[o] = y;
-                if (DOT) dsum[k] = xv * y;
+    for (int h = 0; h < H; ++h) {
+        const int row = rb * (8 * H) + h * 8 + g;
+        if (live && row < n) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                // tile j, fragment column cc in {2t, 2t+1} is the true column cc * NT + j: k = i * NT + j
+                const int i = (B >= 8) ? k / NT : k, j = (B >= 8) ? k % NT : 0;
+                if (B >= 8 || c0 + k < B) {
+                    const int64_t o = (int64_t)row * B + c0 + k;
+                    const double xv = X[o];
+                    double y = acc[h][j][i] + eta * xv;
+                    if (scale) y *= scale[c0 + k];
+                    Y[o] = y;
+                    if (DOT) dsum[k] += xv * y;
+                }
             }
         }
     }
@@ -433,16 +448,24 @@ struct SparseOp {
     int n;
 };
 
-static int bcsr8_parts(int n) { return (((n + 7) / 8) + 7) / 8; }   // CTAs of the row-blocked SpMM = dot partials
+static int bcsr_parts(int n, int R) { return (((n + R - 1) / R) + 7) / 8; }   // CTAs of the row-blocked SpMM = dot partials
+static int bcsr8_parts(int n) { return bcsr_parts(n, 8); }
 
 template <int B>
 static void bcsr8_spmm_launch_b(const SparseOp& A, double eta, const double* X, const double* scale, double* Y,
                                 double* partial, cudaStream_t s) {
-    const int blocks = bcsr8_parts(A.n);
+    const int blocks = bcsr_parts(A.n, A.R);
+    if (A.R == 16) {
+        if (partial)
+            bcsr8_spmm_dmma_kernel<B, true, 2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
+        else
+            bcsr8_spmm_dmma_kernel<B, false, 2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
+        return;
+    }
     if (partial)
-        bcsr8_spmm_dmma_kernel<B, true><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
+        bcsr8_spmm_dmma_kernel<B, true, 1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
     else
-        bcsr8_spmm_dmma_kernel<B, false><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
+        bcsr8_spmm_dmma_kernel<B, false, 1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
 }
 
 // Y = scale (.) ((A + eta I) X); with `partial` also the per-column partial sums of X (.) Y: *nparts rows of B doubles
@@ -466,7 +489,7 @@ static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y
             *nparts = RED_PARTS;
             GP_COUNT(1);
         }
-    } else if (A.R == 8) {
+    } else if (A.R == 8 || A.R == 16) {
         switch (B) {
             case 1: bcsr8_spmm_launch_b<1>(A, eta, X, scale, Y, partial, s); break;
             case 2: bcsr8_spmm_launch_b<2>(A, eta, X, scale, Y, partial, s); break;
@@ -476,7 +499,7 @@ static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y
             case 32: bcsr8_spmm_launch_b<32>(A, eta, X, scale, Y, partial, s); break;
             default: return -2;
         }
-        if (partial) *nparts = bcsr8_parts(n);
+        if (partial) *nparts = bcsr_parts(n, A.R);
         GP_COUNT(1);
     } else {
         return -3;
@@ -631,6 +654,7 @@ static int bcsr_build_any(int64_t R, int pass, int64_t n, const int* order, cons
     if (!indptr || !indices || n <= 0 || n > INT32_MAX || ((order == nullptr) != (inv_order == nullptr))) return -1;
     switch (R) {
         case 8: return bcsr_build<8>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, searched, s);
+        case 16: return bcsr_build<16>(pass, (int)n, order, inv_order, indptr, indices, data, ddata, nblk, bptr, bidx, bvals, bdvals, searched, s);
         default: return -3;
     }
 }
@@ -818,7 +842,7 @@ int gp_lanczos(const int* indptr, const int* indices, const double* data, int64_
 int gp_bcsr_lanczos(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                     const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws,
                     void* stream) {
-    if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
+    if (!bptr || n <= 0 || n > INT32_MAX || (R != 8 && R != 16)) return -1;
     return lanczos_run(bcsr_op(R, bptr, bidx, bvals, n), eta, V, B, m, alpha_dev, beta_dev, basis_dev, ws, stream);
 }
 
@@ -842,7 +866,7 @@ int gp_cg_solve(const int* indptr, const int* indices, const double* data, int64
 
 int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta, double* R0,
                      double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream) {
-    if (!bptr || n <= 0 || n > INT32_MAX || R != 8) return -1;
+    if (!bptr || n <= 0 || n > INT32_MAX || (R != 8 && R != 16)) return -1;
     return cg_run(bcsr_op(R, bptr, bidx, bvals, n), eta, R0, X, B, tol, maxiter, iters_host, ws, stream);
 }
 

@@ -27,7 +27,7 @@ __all__ = ['DeviceCSR', 'SparseEngine', 'generate_sparse_correlation', 'estimate
 
 # imate's documented defaults for the stochastic estimators
 DEFAULTS = dict(min_num_samples=10, max_num_samples=50, error_rtol=1e-2, error_atol=None, confidence_level=0.95,
-                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=8, reuse_lanczos=True, overlap=True,
+                lanczos_degree=20, seed=0, batch=16, cg_tol=1e-6, cg_maxiter=2000, block_rows=16, reuse_lanczos=True, overlap=True,
                 shift_reuse=True, solve_degree=None, eager_rhs_basis=False)
 
 
@@ -228,9 +228,9 @@ class SparseEngine(object):
         self.order = self.inv_order = None
         self.R = 1
         self.blocked = None
-        R = int(self.opt.get('block_rows', 8))
-        if R not in (1, 8):
-            raise ValueError('block_rows should be 8 (row-blocked, FP64 tensor-core SpMM) or 1 (plain CSR).')
+        R = int(self.opt.get('block_rows', 16))
+        if R not in (1, 8, 16):
+            raise ValueError('block_rows should be 8 or 16 (row-blocked, FP64 tensor-core SpMM) or 1 (plain CSR).')
         if K.order is not None and R > 1:
             self._build_blocked(K, R)
 

@@ -314,8 +314,9 @@ def test_krylov_runs_are_reused_across_eta(sparse_problem):
         ProfileLikelihood.log_likelihood_and_gradient(z, X, Ka, 0.05)
 
 
-def test_row_blocked_operator_equals_csr(gp, R=8):
-    """The row-blocked operator (8 x 1 blocks of the Z-order permuted matrix, zero filled, DMMA SpMM) is the same linear map as the
+@pytest.mark.parametrize('R', [8, 16])
+def test_row_blocked_operator_equals_csr(gp, R):
+    """The row-blocked operator (8 x 1 or 16 x 1 blocks of the curve-ordered matrix, zero filled, DMMA SpMM) is the same linear map as the
     canonical CSR: products against the SciPy matrix to rounding, for K and for dK/drho, n not a multiple of R."""
     import torch
     from gaussian_proc._sparse import SparseEngine, generate_sparse_correlation
@@ -376,7 +377,7 @@ def test_row_blocked_operator_other_dimensions(d, scale, nu, dens):
     pts = numpy.random.rand(n, d)
     Kd = generate_sparse_correlation(pts, numpy.array(scale), nu, dens, device=True)
     eng = SparseEngine(Kd, 'slq', {})
-    assert eng.R == 8
+    assert eng.R == 16
     Ks = Kd.to_scipy()
     Xh = numpy.random.randn(n, 8)
     Y = eng.from_op(eng.spmm(1.0, eng.to_op(torch.from_numpy(Xh).cuda()))).cpu().numpy()
@@ -397,7 +398,7 @@ def test_row_blocked_build_search_fallback():
     Kd = DeviceCSR.from_scipy(A)
     Kd.order = torch.arange(n, dtype=torch.int32, device='cuda')
     eng = SparseEngine(Kd, 'slq', {})
-    assert eng.R == 8 and eng.fill_ratio > 4.0          # ~ 8 x 480 distinct columns per block: above the hash capacity
+    assert eng.R == 16 and eng.fill_ratio > 4.0         # ~ 16 x 480 distinct columns per block: above the hash capacity
     Xh = rng.randn(n, 16)
     Y = eng.from_op(eng.spmm(0.0, eng.to_op(torch.from_numpy(Xh).cuda()))).cpu().numpy()
     ref = A @ Xh
@@ -412,9 +413,11 @@ def test_internal_permutation_does_not_change_results(sparse_problem):
     from gaussian_proc._sparse import SparseEngine
     pts, z, X, Kd = sparse_problem
     opts = {'seed': 3, 'lanczos_degree': 25, 'min_num_samples': 16, 'max_num_samples': 16}
-    a = SparseEngine(Kd, 'slq', dict(opts, block_rows=8))
+    a = SparseEngine(Kd, 'slq', dict(opts, block_rows=16))
     b = SparseEngine(Kd, 'slq', dict(opts, block_rows=1))
-    a2 = SparseEngine(Kd, 'slq', dict(opts, block_rows=8))
+    a2 = SparseEngine(Kd, 'slq', dict(opts, block_rows=16))
+    a8 = SparseEngine(Kd, 'slq', dict(opts, block_rows=8))
+    assert abs(a8.logdet(2.0) - b.logdet(2.0)) <= 1e-10 * abs(b.logdet(2.0))
     assert a.order is not None and b.order is None
     assert a.logdet(2.0) == a2.logdet(2.0)
     assert abs(a.logdet(2.0) - b.logdet(2.0)) <= 1e-10 * abs(b.logdet(2.0))

@@ -21,7 +21,7 @@ gen()
 out['t_generate_s'], K = timed(gen)
 out['nnz'] = K.nnz
 out['generate_GBs'] = (20.0 * K.nnz + 4.0 * (n + 1)) / out['t_generate_s'] * 1e-9
-for R in (1, 8):
+for R in (1, 8, 16):
     SparseEngine(K, 'slq', {'block_rows': R})
     t, e = timed(lambda: SparseEngine(K, 'slq', {'block_rows': R}))
     out['R%d' % R] = {'build_s': t, 'fill_ratio': getattr(e, 'fill_ratio', 1.0)}
