@@ -8,6 +8,9 @@
 
 namespace gp {
 
+#ifndef GP_SPMM_U
+#define GP_SPMM_U 4
+#endif
 constexpr int RED_PARTS = 592;  // CTAs of the column reductions (4 per SM)
 
 // ---- Y = (K + eta I) X, one warp per row; lane = (q, c): q-th nonzero of the current group, column c ---------
@@ -363,7 +366,7 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
             }
         }
     };
-    constexpr int U = (NT <= 2) ? 4 : 2;       // steps in flight per warp: all loads of U steps are issued before their MMAs
+    constexpr int U = (NT <= 2) ? GP_SPMM_U : 2;       // steps in flight per warp: all loads of U steps are issued before their MMAs
     int64_t p = p0;
     for (; p + 4 * U <= p1; p += 4 * U) {
         int col[U];

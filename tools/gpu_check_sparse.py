@@ -61,7 +61,7 @@ bptr, bidx, bvals, _ = eng.blocked
 al = torch.empty((30, 16), dtype=torch.float64, device='cuda'); be = torch.empty((30, 16), dtype=torch.float64, device='cuda')
 ws = eng._workspace(16)
 def lz():
-    dev.lib.gp_bcsr_lanczos(8, P(bptr), P(bidx), P(bvals), n, 10.0, P(V), 16, 30, P(al), P(be), None, P(ws), dev.stream_ptr())
+    dev.lib.gp_bcsr_lanczos(eng.R, P(bptr), P(bidx), P(bvals), n, 10.0, P(V), 16, 30, P(al), P(be), None, P(ws), dev.stream_ptr())
 lz()
 t, _ = timed(lz, 3)
 out['lanczos30_B16_ms'] = t * 1e3
