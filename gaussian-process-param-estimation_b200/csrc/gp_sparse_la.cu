@@ -8,6 +8,9 @@
 
 namespace gp {
 
+#ifndef GP_SPMM_MINB
+#define GP_SPMM_MINB 1
+#endif
 #ifndef GP_SPMM_U
 #define GP_SPMM_U 4
 #endif
@@ -334,7 +337,7 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
 // of X[i][c] Y[i][c] (fixed order) - the Lanczos alpha / CG p^T A p reduction without another pass over the vectors.
 // H = 1: 8 x 1 row blocks; H = 2: 16 x 1 row blocks (two A fragments and two MMAs per gathered B fragment).
 template <int B, bool DOT, int H>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GP_SPMM_MINB)
 bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
                        double eta, const double* __restrict__ X, const double* __restrict__ scale, double* __restrict__ Y,
                        double* __restrict__ partial) {
