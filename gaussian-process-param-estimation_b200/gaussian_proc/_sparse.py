@@ -633,6 +633,10 @@ class SparseEngine(object):
             raise numpy.linalg.LinAlgError('CG did not converge in %d iterations (eta=%g)' % (it.value, eta))
         return X
 
+    def _max_block(self):
+        """widest column block handed to the SpMM: the 16 x 1 row-blocked kernel is tuned for B <= 16"""
+        return 16 if self.blocked is not None and self.R == 16 else 32
+
     def solve(self, eta, Y):
         """mixed_correlation.py:280-299 for sparse K: CG per column with rtol 1e-6 (batched on the device)."""
         torch = dev.torch
@@ -641,8 +645,9 @@ class SparseEngine(object):
         Y2 = Y.reshape(self.n, -1)
         out = numpy.empty_like(Y2)
         k = Y2.shape[1]
-        for c0 in range(0, k, 32):
-            blk = Y2[:, c0:c0 + 32]
+        W = self._max_block()
+        for c0 in range(0, k, W):
+            blk = Y2[:, c0:c0 + W]
             B = 1
             while B < blk.shape[1]:
                 B *= 2
@@ -661,8 +666,9 @@ class SparseEngine(object):
         B = 1
         while B < k:
             B *= 2
-        if B > 32:
-            return numpy.hstack([self.matmul(X2[:, c:c + 32]) for c in range(0, k, 32)])
+        W = self._max_block()
+        if B > W:
+            return numpy.hstack([self.matmul(X2[:, c:c + W]) for c in range(0, k, W)])
         Xd = torch.zeros((self.n, B), dtype=torch.float64, device='cuda')
         Xd[:, :k].copy_(torch.from_numpy(numpy.ascontiguousarray(X2)))
         res = self.from_op(self.spmm(0.0, self.to_op(Xd)))[:, :k].cpu().numpy()

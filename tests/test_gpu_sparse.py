@@ -425,6 +425,10 @@ def test_internal_permutation_does_not_change_results(sparse_problem):
     assert abs(a.traceinv_dK(2.0) - b.traceinv_dK(2.0)) <= 1e-7 * abs(b.traceinv_dK(2.0))    # CG stops at rtol 1e-6
     assert numpy.max(numpy.abs(a.solve(2.0, z) - b.solve(2.0, z))) <= 1e-6 * numpy.max(numpy.abs(b.solve(2.0, z)))
     assert numpy.max(numpy.abs(a.matmul(X) - b.matmul(X))) <= 1e-12
+    wide = numpy.random.RandomState(0).randn(a.n, 37)               # more columns than one SpMM block
+    assert numpy.max(numpy.abs(a.matmul(wide) - b.matmul(wide))) <= 1e-11
+    sw = a.solve(2.0, wide[:, :20])
+    assert numpy.max(numpy.abs((Kd.to_scipy() @ sw + 2.0 * sw) - wide[:, :20])) <= 1e-5 * numpy.max(numpy.abs(wide))
     Va = a.from_op(a.probes(0, 4)).cpu().numpy()
     assert (Va == b.probes(0, 4).cpu().numpy()).all()
 
