@@ -217,3 +217,28 @@ def test_recorded_bench_line_follows_the_contract():
     assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
     assert line['gpu_launches'] > 0 and not line['clocks']['reasons']
     assert abs(line['value'] - line['steps'] * line['n_gpus'] / (line['ms_per_step'] * line['steps'] * 1e-3)) < 1e-9
+
+
+def test_sparse_engine_host_helpers():
+    """Pure host helpers of the sparse engine: power-of-two probe chunks, the first chunk a rank evaluates (what the
+    side-stream prefetch uses), and the content fingerprint of cached host arrays."""
+    from gaussian_proc._sparse import SparseEngine, DEFAULTS
+    from gaussian_proc import _device as dev
+    assert SparseEngine._chunks(0, 16, 16) == [(0, 16)]
+    assert SparseEngine._chunks(5, 13, 8) == [(5, 8), (13, 4), (17, 1)]
+    assert SparseEngine._chunks(3, 0, 8) == []
+    eng = object.__new__(SparseEngine)
+    eng.opt = dict(DEFAULTS, max_num_samples=50, batch=16)
+    eng.probe_range = None
+    assert eng._first_chunk() == (0, 16)
+    eng.probe_range = (1, 2)          # second of two ranks: the round of 32 probes is cut into 16 + 16
+    assert eng._first_chunk() == (16, 16)
+    eng.opt = dict(DEFAULTS, max_num_samples=10, batch=16)
+    eng.probe_range = (1, 4)          # 10 probes over 4 ranks: 3 each, rank 1 takes ids 3, 4, 5 -> first chunk (3, 2)
+    assert eng._first_chunk() == (3, 2)
+    a = numpy.arange(100.0)
+    k1 = dev.host_key(a)
+    assert dev.host_key(a) == k1
+    a[0] = -1.0                        # an in-place edit of a sampled entry changes the key
+    assert dev.host_key(a) != k1
+    assert dev.host_key(numpy.zeros((0, 3)))[1] == (0, 3)
