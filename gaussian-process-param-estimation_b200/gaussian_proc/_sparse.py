@@ -266,11 +266,14 @@ class SparseEngine(object):
         self.order, self.inv_order = order, inv.to(torch.int64)
 
     # ---- plumbing ----------------------------------------------------------------------------------------------
-    def _workspace(self, B):
+    def _workspace(self, B, side=False):
+        """Krylov workspace for column blocks of width B; ``side``: the separate one of the prefetch stream (a Lanczos
+        run there may overlap a CG / Lanczos run of the same width on the main stream)."""
         torch = dev.torch
-        if B not in self._ws:
-            self._ws[B] = torch.empty(lib.gp_krylov_workspace_bytes(self.n, B) // 8 + 8, dtype=torch.float64, device='cuda')
-        return self._ws[B]
+        key = ('side', B) if side else B
+        if key not in self._ws:
+            self._ws[key] = torch.empty(lib.gp_krylov_workspace_bytes(self.n, B) // 8 + 8, dtype=torch.float64, device='cuda')
+        return self._ws[key]
 
     def spmm(self, eta, X_dev, derivative=False):
         """(K + eta I) X, or (dK/drho + eta I) X with ``derivative``, in OPERATOR space (rows in self.order when the
@@ -307,7 +310,7 @@ class SparseEngine(object):
         alpha, beta = self._lanczos_launch(eta, V, m, basis)
         return alpha.cpu().numpy(), beta.cpu().numpy()
 
-    def _lanczos_launch(self, eta, V, m, basis=None, alpha=None, beta=None):
+    def _lanczos_launch(self, eta, V, m, basis=None, alpha=None, beta=None, side=False):
         """enqueues the batched Lanczos run on torch's current stream; returns the device (alpha, beta)"""
         torch = dev.torch
         B = V.shape[1]
@@ -317,11 +320,11 @@ class SparseEngine(object):
         if self.blocked is not None:
             bptr, bidx, bvals, _ = self.blocked
             check(lib.gp_bcsr_lanczos(self.R, _p(bptr), _p(bidx), _p(bvals), self.n, float(eta), _p(V), B, m, _p(alpha),
-                                      _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_bcsr_lanczos')
+                                      _p(beta), bp, _p(self._workspace(B, side)), dev.stream_ptr()), 'gp_bcsr_lanczos')
         else:
             K = self.K
             check(lib.gp_lanczos(_p(K.indptr), _p(K.indices), _p(K.data), self.n, float(eta), _p(V), B, m, _p(alpha),
-                                 _p(beta), bp, _p(self._workspace(B)), dev.stream_ptr()), 'gp_lanczos')
+                                 _p(beta), bp, _p(self._workspace(B, side)), dev.stream_ptr()), 'gp_lanczos')
         return alpha, beta
 
     def _first_chunk(self):
@@ -357,12 +360,12 @@ class SparseEngine(object):
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
         basis = self._new_basis(m, B) if with_dk else None
-        self._workspace(B)
+        self._workspace(B, side=True)
         cur = torch.cuda.current_stream()
         self._side_stream.wait_stream(cur)
         with torch.cuda.stream(self._side_stream):
             self.probes(first, B, out=V)
-            self._lanczos_launch(eta, V, m, basis, alpha, beta)
+            self._lanczos_launch(eta, V, m, basis, alpha, beta, side=True)
         self._prefetched = (float(eta), first, B, with_dk, V, alpha, beta, basis)
 
     # The Krylov space of K + eta I does not depend on eta and the Lanczos tridiagonal only shifts: T(eta) = T(eta_ref) +

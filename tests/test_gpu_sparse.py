@@ -314,6 +314,28 @@ def test_krylov_runs_are_reused_across_eta(sparse_problem):
         ProfileLikelihood.log_likelihood_and_gradient(z, X, Ka, 0.05)
 
 
+def test_sparse_loglik_wide_basis(sparse_problem):
+    """m + 1 > 8 right-hand sides: the [X z] block is 16 columns wide, the same width as the probe block whose Lanczos
+    run overlaps its solve on the side stream (separate workspaces). Deterministic ingredients against dense solves."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import _fused
+    pts, z, X, Kd = sparse_problem
+    x, y = pts[:, 0], pts[:, 1]
+    X10 = numpy.stack([numpy.ones_like(x), x, y, x * x, x * y, y * y, x ** 3, x * x * y, x * y * y, y ** 3], axis=1)
+    eta = 2.0
+    Km = MixedCorrelation(Kd, imate_method='slq', imate_options={'seed': 0, 'lanczos_degree': 40, 'cg_tol': 1e-11})
+    q1 = _fused.evaluate(z, X10, Km, eta, traceinv=True, drho=True)
+    q2 = _fused.evaluate(z, X10, Km, 5.0, traceinv=True, drho=True)          # second eta: kept Krylov runs
+    Ks = Kd.to_scipy().toarray()
+    R = numpy.c_[X10, z]
+    for q, e in ((q1, eta), (q2, 5.0)):
+        S = numpy.linalg.solve(Ks + e * numpy.eye(Ks.shape[0]), R)
+        assert numpy.max(numpy.abs(q.G - R.T @ S)) <= 1e-8 * numpy.max(numpy.abs(R.T @ S))
+        assert numpy.max(numpy.abs(q.H - S.T @ S)) <= 1e-8 * numpy.max(numpy.abs(S.T @ S))
+        exact = numpy.linalg.slogdet(Ks + e * numpy.eye(Ks.shape[0]))[1]
+        assert abs(q.logdet_Kn - exact) <= 2e-2 * abs(exact)          # the estimator stops at a 1 % half width
+
+
 @pytest.mark.parametrize('R', [8, 16])
 def test_row_blocked_operator_equals_csr(gp, R):
     """The row-blocked operator (8 x 1 or 16 x 1 blocks of the curve-ordered matrix, zero filled, DMMA SpMM) is the same linear map as the
