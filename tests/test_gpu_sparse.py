@@ -145,6 +145,21 @@ def test_spmm_dot_solve(sparse_problem):
     assert abs(Km.trace(0.5) - (S.diagonal().sum() + 0.5 * 3000)) <= 1e-9
 
 
+def test_slq_samples_equal_the_cpu_oracle_per_probe(sparse_problem):
+    """Same seed -> same Rademacher probes (hash restated in oracle/slq.py) -> the device SLQ samples [log, 1/x, 1/x^2]
+    equal an independent NumPy Lanczos + quadrature PER PROBE (not only in distribution)."""
+    from gaussian_proc._sparse import SparseEngine
+    from oracle import slq
+    pts, z, X, Kd = sparse_problem
+    eng = SparseEngine(Kd, 'slq', {'seed': 11, 'lanczos_degree': 20, 'block_rows': 1})
+    assert (eng.probes(4, 4).cpu().numpy() == slq.rademacher(eng.n, 4, 11, 4)).all()
+    ref = slq.slq_samples(Kd.to_scipy(), 2.0, 11, 4, 4, 20)
+    for R in (1, 16):
+        e = SparseEngine(Kd, 'slq', {'seed': 11, 'lanczos_degree': 20, 'block_rows': R})
+        got = e._slq_samples(2.0, 4, 4)
+        assert numpy.max(numpy.abs(got - ref) / numpy.abs(ref)) <= 1e-9, (R, got, ref)
+
+
 def test_probes_are_batching_invariant(sparse_problem):
     from gaussian_proc._sparse import SparseEngine
     eng = SparseEngine(sparse_problem[3])
