@@ -1,4 +1,5 @@
-// Sparse (CSR) operator K + eta*I on blocks of probe / right-hand-side columns: SpMM, batched Lanczos (stochastic
+// Sparse operator K + eta*I (plain CSR, or the row-blocked form whose SpMM runs on the FP64 tensor cores) on blocks of
+// probe / right-hand-side columns: SpMM, batched Lanczos (stochastic
 // Lanczos quadrature for logdet and trace of the inverse) and batched CG (solves, Hutchinson tr(Kn^-1 dK)).
 // Replaces what the reference reaches through imate's 'slq' / 'hutchinson' methods and scipy.sparse.linalg.cg
 // (gaussian_proc/_mixed_correlation/mixed_correlation.py:193-209,263-268; _linear_solver.py:49-68, tol = 1e-6).
@@ -155,7 +156,7 @@ __global__ void rademacher_kernel(int64_t n, int B, uint64_t seed, int64_t probe
     V[idx] = (z & 1ull) ? 1.0 : -1.0;
 }
 
-// ---- row-blocked operator: R = 8 consecutive rows share one column list (8 x 1 blocks, zero filled) -------------
+// ---- row-blocked operator: R = 8 or 16 consecutive rows share one column list (R x 1 blocks, zero filled) ---------
 // Rows that are neighbours in a spatially sorted order have almost the same pattern, so one gathered row of X serves
 // R rows of K: gather traffic (the L1/L2-bound part of a multi-column SpMM) drops ~R-fold and the column index is
 // amortised over R values. Block-columns of a row block: [all columns of row 0][columns of row 1 not in row 0]...
@@ -326,7 +327,7 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
     }
 }
 
-// Y = (K + eta I) X on the row-blocked operator (R = 8) with FP64 tensor-core MMAs. One warp per row block. Four
+// Y = (K + eta I) X on the row-blocked operator (R = 8 H rows per block, H = 1 or 2) with FP64 tensor-core MMAs. One warp per row block. Four
 // block-columns form one DMMA.8x8x4: A (8 rows x 4 block-columns) is exactly 256 contiguous bytes of the value stream
 // (one 8-byte load per lane, no broadcast), B (4 x 8) holds the four gathered rows of X restricted to 8 columns, and the
 // 8 x 8 accumulator stays in two registers per lane for the whole row block - no cross-lane reduction. For B = 16 / 32
@@ -444,7 +445,7 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     }
 }
 
-// the operator a Krylov routine works on: plain CSR (R = 1) or the row-blocked form (R = 8)
+// the operator a Krylov routine works on: plain CSR (R = 1) or the row-blocked form (R = 8 or 16)
 struct SparseOp {
     int R;                 // 1: CSR (ptr32, idx, val); > 1: row-blocked (ptr64, idx, val)
     const int* ptr32;

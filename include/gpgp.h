@@ -149,8 +149,8 @@ int gp_csr_spmm(const int* indptr, const int* indices, const double* data, int64
  * row = row_map[i] when row_map (device int32, n) is given (internally permuted operators), else i. */
 int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_offset, const int* row_map,
                   void* stream);
-/* Row-blocked form of a (symmetrically permuted) CSR matrix: R = 8 consecutive rows share one list of block-columns
- * (8 x 1 blocks, zero filled; the list is padded with zero blocks to a multiple of 4 = one DMMA.8x8x4 k-step). New row r = old row order[r], new column = inv_order[old column] (both
+/* Row-blocked form of a (symmetrically permuted) CSR matrix: R = 8 or 16 consecutive rows share one list of block-columns
+ * (R x 1 blocks, zero filled; the list is padded with zero blocks to a multiple of 4 = one DMMA.8x8x4 k-step). New row r = old row order[r], new column = inv_order[old column] (both
  * NULL: no permutation); the source rows must be sorted. With a spatially local order (gp_spatial_keys) neighbouring
  * rows have nearly the same pattern: one gathered row of X then serves R rows of K and the index is amortised.
  *   gp_bcsr_count: nblk[rb] = number of block-columns of row block rb (ceil(n/R) entries); the caller's exclusive
@@ -158,13 +158,15 @@ int gp_rademacher(double* V, int64_t n, int64_t B, uint64_t seed, int64_t probe_
  *                  when some row block exceeded the shared-memory hash table and used the binary-search path, which
  *                  requires SORTED source rows (the hash path does not).
  *   gp_bcsr_fill : nblocks = bptr[last]; bidx (int32, nblocks), bvals / bdvals (f64, R * nblocks): every group of four
- *                  block-columns is stored in DMMA A-fragment order, value (slot s, row k) at 32 (s/4) + 4 k + s%4. */
+ *                  block-columns is stored in DMMA A-fragment order (one 8-row fragment after the other), value
+ *                  (slot s, row k) at 4 R (s/4) + 32 (k/8) + 4 (k%8) + s%4. */
 int gp_bcsr_count(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                   int* nblk, int* needs_sorted_dev, void* stream);
 int gp_bcsr_fill(int64_t R, int64_t n, const int* order, const int* inv_order, const int* indptr, const int* indices,
                  const double* data, const double* ddata, const int64_t* bptr, int64_t nblocks, int* bidx, double* bvals,
                  double* bdvals, void* stream);
-/* Y = (K + eta I) X on the row-blocked operator (FP64 tensor-core MMAs: 4 block-columns x 8 rows x 8 columns) */
+/* Y = (K + eta I) X on the row-blocked operator (FP64 tensor-core MMAs: 4 block-columns x 8 rows x 8 columns; with
+ * R = 16 two MMAs share each gathered fragment of X). Tuned for B <= 16. */
 int gp_bcsr_spmm(int64_t R, const int64_t* bptr, const int* bidx, const double* bvals, int64_t n, double eta,
                  const double* X, int64_t B, double* Y, void* stream);
 /* workspace for gp_col_dot / gp_lanczos / gp_cg_solve */
