@@ -27,7 +27,17 @@ import sys
 import threading
 import time
 
-import numpy
+# torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs (cpu_baseline, --impl reference) must run on all host
+# cores, so the BLAS / OpenMP pools are sized before numpy loads them (pin_host_threads() re-asserts it at run time)
+if os.environ.get('GP_BENCH_KEEP_THREADS', '0') == '0':
+    try:
+        _ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        _ncpu = os.cpu_count() or 1
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(_ncpu)
+
+import numpy  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -103,68 +113,138 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_sample(n_sample, n_full, repeats=1):
-    """Times the reference's CPU algorithm for ONE loglik+grad evaluation (correlation
-    generation + DirectLikelihood.log_likelihood + log_likelihood_jacobian, Cholesky method, i.e. 4 dposv solves, one
-    logdet, one explicit-inverse trace) at n_sample points and extrapolates to n_full with n^2 (generation) and n^3
-    (factorisations). Generation uses the compiled reference (oracle/_ref, OpenMP) when it is there."""
+WORKLOAD = ('configs[1]: dense Matern nu=2.5, n=%d random 2-D points (seed 0), m=6 (Poly-2 basis), '
+            'one (eta, rho) cell per step per GPU, eta in {1e-2,1e-1,1,10}, rho ~ 0.1')
+
+
+def bench_config(n, npad, C):
+    """The `config` object of the JSON line - identical in both arms (same workload, same keys)."""
+    return {'workload': WORKLOAD % n,
+            'l2': 'inputs larger than L2 (K = %.1f GB per evaluation)' % (npad * npad * 8e-9),
+            'parallelism': 'independent cells per GPU (replicas), results all-gathered',
+            'cells_in_flight': C}
+
+
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+_THREAD_LIMIT = []
+
+
+def pin_host_threads():
+    """BLAS / OpenMP pools of this process -> all host cores, whatever the launcher exported."""
+    nthr = host_threads()
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        _THREAD_LIMIT.append(threadpool_limits(limits=nthr))
+        blas = [i.get('num_threads') for i in threadpool_info() if i.get('user_api') == 'blas']
+        return max(blas) if blas else nthr
+    except Exception:  # noqa: BLE001
+        return nthr
+
+
+def cpu_evaluation(n, method='cholesky', idx=0):
+    """ONE loglik+grad evaluation of the reference's CPU algorithm at n points, timed: Matern
+    generation (compiled reference Cython when oracle/_ref is there, else the oracle's C restatement) +
+    DirectLikelihood.log_likelihood + log_likelihood_jacobian (_direct_likelihood.py:31-157: 4 dposv solves, one logdet,
+    one trace of the inverse; `method` = the imate method behind logdet / traceinv: 'cholesky', or 'eigenvalue' - the one
+    likelihood.py:41 hard-codes - which adds one eigvalsh per correlation matrix). Returns (seconds_generation,
+    seconds_likelihood, kind)."""
     from oracle import likelihood as L
     from oracle import matern
-    pts, z, X = make_inputs(n_sample)
+    pts, z, X = make_inputs(n)
+    eta, rho = cell(idx)
+    scale = numpy.array([rho, rho])
     kind = 'port'
-    gen = lambda: matern.generate_dense_correlation(pts, numpy.array([0.1, 0.1]), NU)   # noqa: E731
+    gen = lambda: matern.generate_dense_correlation(pts, scale, NU)   # noqa: E731
     try:
         from oracle import ref_loader
         cy = ref_loader.load_cython()
-        gen = lambda: cy.generate_dense_correlation(pts, numpy.array([0.1, 0.1]), NU, False)  # noqa: E731
+        gen = lambda: cy.generate_dense_correlation(pts, scale, NU, False)  # noqa: E731
         kind = 'port (likelihood) + reference (compiled Cython generator)'
     except Exception:  # noqa: BLE001
         pass
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        K = gen()
-        t1 = time.perf_counter()
-        Km = L.MixedCorrelation(K, 'cholesky')
-        L.DirectLikelihood.log_likelihood(z, X, Km, False, [0.3, 0.3 * numpy.sqrt(0.1)])
-        L.DirectLikelihood.log_likelihood_jacobian(z, X, Km, False, [0.3, 0.3 * numpy.sqrt(0.1)])
-        t2 = time.perf_counter()
-        cur = (t1 - t0, t2 - t1)
-        best = cur if best is None or sum(cur) < sum(best) else best
-    s = n_full / float(n_sample)
-    t_full = best[0] * s ** 2 + best[1] * s ** 3
-    cores = os.cpu_count()
-    try:
-        from threadpoolctl import threadpool_info
-        blas = [i.get('num_threads') for i in threadpool_info() if i.get('user_api') == 'blas']
-        cores = max(blas) if blas else cores
-    except Exception:  # noqa: BLE001
-        pass
-    return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': cores, 'kind': kind,
-            'sample': 'one evaluation (Matern generation %.2fs + DirectLikelihood l and jacobian %.2fs, Cholesky method) '
-                      'at n=%d, extrapolated to n=%d with n^2 / n^3' % (best[0], best[1], n_sample, n_full),
-            'seconds_per_eval_extrapolated': t_full}
+    sigma = 0.3
+    hyper = [sigma, sigma * numpy.sqrt(eta)]
+    t0 = time.perf_counter()
+    K = gen()
+    t1 = time.perf_counter()
+    Km = L.MixedCorrelation(K, method)
+    L.DirectLikelihood.log_likelihood(z, X, Km, False, hyper)
+    L.DirectLikelihood.log_likelihood_jacobian(z, X, Km, False, hyper)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, kind
+
+
+def cpu_sample(n_full, sizes=(4000, 8000), repeats=3, full=True, eigen=True):
+    """The reference's CPU path on this box's host cores: best of `repeats` at each n in `sizes`, the fitted exponent,
+    and (full=True) ONE measured evaluation at n_full - the value is then a measurement, not an extrapolation."""
+    cores = pin_host_threads()
+    rows, kind = [], 'port'
+    for ns in sizes:
+        best = None
+        for r in range(repeats):
+            tg, tl, kind = cpu_evaluation(ns, 'cholesky', r)
+            best = (tg, tl) if best is None or tg + tl < sum(best) else best
+        rows.append({'n': ns, 'generation_s': best[0], 'likelihood_s': best[1], 'seconds': sum(best)})
+    exponent = None
+    if len(rows) >= 2:
+        exponent = float(numpy.log(rows[-1]['seconds'] / rows[0]['seconds']) / numpy.log(rows[-1]['n'] / float(rows[0]['n'])))
+    s = n_full / float(rows[-1]['n'])
+    t_fit = rows[-1]['generation_s'] * s ** 2 + rows[-1]['likelihood_s'] * s ** 3
+    out = {'unit': UNIT, 'cores': cores, 'kind': kind, 'samples': rows, 'fitted_exponent': exponent,
+           'seconds_per_eval_n3_fit_from_largest_sample': t_fit}
+    if eigen:
+        ns = rows[-1]['n']
+        tg, tl, _ = cpu_evaluation(ns, 'eigenvalue', 0)
+        out['eigenvalue_method'] = {'n': ns, 'generation_s': tg, 'likelihood_s': tl,
+                                    'note': "imate_method='eigenvalue' (likelihood.py:41): one eigvalsh per matrix + the same 4 dposv"}
+    if full:
+        tg, tl, _ = cpu_evaluation(n_full, 'cholesky', 0)
+        out.update({'value': 1.0 / (tg + tl), 'extrapolated': False, 'seconds_per_eval': tg + tl,
+                    'sample': 'ONE measured evaluation at n=%d (Matern generation %.1fs + DirectLikelihood l and jacobian '
+                              '%.1fs, Cholesky method, %d threads); smaller n best-of-%d: %s'
+                              % (n_full, tg, tl, cores, repeats,
+                                 ', '.join('n=%d %.2fs' % (r_['n'], r_['seconds']) for r_ in rows))})
+    else:
+        out.update({'value': 1.0 / t_fit, 'extrapolated': True, 'seconds_per_eval': t_fit,
+                    'sample': 'best of %d at n=%d (generation %.2fs + likelihood %.2fs), scaled with n^2 / n^3 to n=%d'
+                              % (repeats, rows[-1]['n'], rows[-1]['generation_s'], rows[-1]['likelihood_s'], n_full)})
+    return out
 
 
 def run_reference(args):
+    """The CPU arm. value = 1 / (measured seconds of ONE n = 20 000 evaluation on all host cores); every --steps step is
+    a bounded sample (one whole evaluation at n = GP_BENCH_CPU_N, default 4000) whose wall time is ms_per_step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n = int(os.environ.get('GP_BENCH_N', '20000'))
-    ns = int(os.environ.get('GP_BENCH_CPU_N', '3000'))
-    for _ in range(args.warmup):
-        cpu_sample(min(ns, 1000), n)
+    ns = int(os.environ.get('GP_BENCH_CPU_N', '4000'))
+    full = os.environ.get('GP_BENCH_CPU_FULL', '1') != '0'
+    cores = pin_host_threads()
+    for w in range(args.warmup):
+        cpu_evaluation(min(ns, 2000), 'cholesky', w)
     t0 = time.perf_counter()
-    vals = [cpu_sample(ns, n) for _ in range(args.steps)]
+    steps = [cpu_evaluation(ns, 'cholesky', s_) for s_ in range(args.steps)]
     wall = time.perf_counter() - t0
-    v = statistics.mean([x['value'] for x in vals])
-    base = dict(vals[0])
-    base['value'] = v
+    base = cpu_sample(n, sizes=(ns, 2 * ns), repeats=1, full=full)
+    base['step_sample'] = {'n': ns, 'steps': args.steps, 'mean_s': wall / max(args.steps, 1),
+                           'min_s': min(a + b for a, b, _ in steps), 'max_s': max(a + b for a, b, _ in steps)}
+    base['cores'] = cores
+    v = base['value']
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 / v, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: dense Matern nu=2.5, n=%d random 2-D points, m=6 (Poly-2)' % n,
-                       'sample_wall_s': wall},
+            'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': bench_config(n, -(-n // 128) * 128, 2),
+            'step_definition': 'a step is a bounded sample: one whole reference evaluation at n=%d; value = 1 / seconds of '
+                               'the one evaluation measured at n=%d in this run (extrapolated: %s); the CPU arm does not '
+                               'scale with --gpus (one host)' % (ns, n, base['extrapolated']),
             'cpu_baseline': base,
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -549,11 +629,7 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': 'configs[1]: dense Matern nu=2.5, n=%d random 2-D points (seed 0), m=6 (Poly-2 basis), '
-                                       'one (eta, rho) cell per step per GPU, eta in {1e-2,1e-1,1,10}, rho ~ 0.1' % n,
-                           'l2': 'inputs larger than L2 (K = %.1f GB per evaluation)' % (npad * npad * 8e-9),
-                           'parallelism': 'independent cells per GPU (replicas), results all-gathered',
-                           'cells_in_flight': C},
+                'config': bench_config(n, npad, C),
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
         if world == 1 and not args.no_secondary:
             del hp, hz, hX
@@ -563,7 +639,7 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001 -- the headline must still print
                 line['secondary'] = {'error': repr(e)[:300]}
         if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_sample(int(os.environ.get('GP_BENCH_CPU_N', '3000')), n)
+            line['cpu_baseline'] = cpu_sample(n, full=os.environ.get('GP_BENCH_CPU_FULL', '1') != '0')
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -11,8 +11,12 @@
 // Triangular operands are exploited by restricting each tile's k-range, never by element masks.
 #include "gp_common.cuh"
 #include "gp_internal.h"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <utility>
 #include <vector>
 
@@ -30,6 +34,40 @@ struct GemmProfile {
     cudaEvent_t ref = nullptr;  // time origin for the union of the (possibly concurrent) launch intervals
 };
 static GemmProfile g_prof;
+static std::mutex g_prof_mutex;
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property of a kernel: done once per (device, kernel)
+static std::mutex g_cfg_mutex;
+static std::set<std::pair<int, const void*>> g_cfg_done;
+
+int configure_once(const void* func, int smem_bytes) {
+    int dev = 0;
+    GP_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    std::pair<int, const void*> key(dev, func);
+    if (g_cfg_done.count(key)) return 0;
+    GP_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    g_cfg_done.insert(key);
+    return 0;
+}
+
+// when profiling is on: records the start event on `stream`, books the flops and returns the stop event to record
+// after the launch (nullptr when profiling is off)
+static cudaEvent_t profile_begin(double flops, cudaStream_t stream) {
+    if (!g_prof.on) return nullptr;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    while (g_prof.pool.size() < g_prof.used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        g_prof.pool.push_back(e);
+    }
+    cudaEvent_t e0 = g_prof.pool[g_prof.used++];
+    cudaEvent_t e1 = g_prof.pool[g_prof.used++];
+    g_prof.flops += flops;
+    g_prof.launches++;
+    cudaEventRecord(e0, stream);
+    return e1;
+}
 
 static double tile_flops(int tiles_m, int tiles_n, int bn, int K, int krange, int tmask) {
     double kt = 0.0;  // sum over computed tiles of their k extent
@@ -233,39 +271,351 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
     }
 }
 
+
+// =====================================================================================================================
+// TMA + mbarrier variant (the default): the same tile shapes, warp tiles, k-range logic and epilogue, but the k-slabs
+// are moved by ONE producer warp with cp.async.bulk.tensor (SASS: UTMALDG) into a ring of 128-byte-swizzled shared tiles
+// guarded by full/empty mbarriers; the consumer warps never meet in a CTA barrier inside the main loop.
+//
+// Shared layouts (hardware SWIZZLE_128B: 16-byte chunk index ^= row & 7 inside 1024-byte groups):
+//   K-major operand  ([mn][k], T = 0): one 2-D box {16 k, ROWS mn}; row = mn (128 B each).
+//   MN-major operand ([k][mn], T = 1): ROWS/16 boxes of a 5-D view {16 mn, kbit1, kbit0, k>>3, kbit2} (2 KB each); the box
+//                    row is r = kbit1 | kbit0<<1 | kbit3<<2 | kbit2<<3.
+// Inside a slab of 16 k the MMA step kk (0..3) gives lane t (0..3) the logical k = (t&1) | kk<<1 | (t>>1)<<3 - the same
+// permutation for A and B, so the product is unchanged - which makes the 8-byte fragment loads of both layouts
+// bank-conflict free (each half-warp covers 16 distinct 8-byte bank groups).
+// =====================================================================================================================
+template <int BN_>
+struct TCfg {
+    static constexpr int BN = BN_;
+    static constexpr int BK = 16;
+    static constexpr int STAGES = (BN_ == 128) ? 6 : 4;
+    static constexpr int WARPS_N = BN_ / WN;
+    static constexpr int CONSUMER_WARPS = (BM / WM) * WARPS_N;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;            // + the TMA producer warp
+    static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN_ * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;   // tiles + barriers + alignment slack
+    static constexpr int MIN_CTAS = (BN_ == 128) ? 1 : 2;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// byte offset of the fragment element (tile-local mn, MMA step kk, lane column t) inside an operand tile
+template <int T>
+__device__ __forceinline__ uint32_t frag_off(int mn, int kk, int t) {
+    if (T == 0) {
+        int chunk = (kk | ((t >> 1) << 2)) ^ (mn & 7);
+        return (uint32_t)(mn * 128 + (chunk << 4) + ((t & 1) << 3));
+    }
+    int r = (kk & 1) | ((t & 1) << 1) | ((t >> 1) << 2) | ((kk >> 1) << 3);
+    int ml = mn & 15;
+    int chunk = (ml >> 1) ^ (r & 7);
+    return (uint32_t)((mn >> 4) * 2048 + r * 128 + (chunk << 4) + ((ml & 1) << 3));
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+template <int AT, int BT, int BN_>
+__global__ void __launch_bounds__(TCfg<BN_>::THREADS, TCfg<BN_>::MIN_CTAS)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C, int64_t ldc,
+                 int tiles_m, int tiles_n, int K, double alpha, double beta, int krange, int tmask) {
+    using G = TCfg<BN_>;
+    constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    int bid = blockIdx.x;
+    int group_sz = RASTER_GROUP * tiles_n;
+    int grp = bid / group_sz;
+    int first_m = grp * RASTER_GROUP;
+    int rows_in_grp = min(RASTER_GROUP, tiles_m - first_m);
+    int rem = bid - grp * group_sz;
+    int tm = first_m + rem % rows_in_grp;
+    int tn = rem / rows_in_grp;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if (tmask == TM_LOWER && n0 >= m0 + BM) return;
+
+    int kbeg = 0, kend = K;
+    if (krange == KR_A_LOWER) kend = min(K, m0 + BM);
+    else if (krange == KR_B_LOWER) kbeg = min(n0, K);
+    else if (krange == KR_TN_LOWER) kbeg = min(max(m0, n0), K);
+    kbeg = (kbeg / BK) * BK;
+    const int KT = (kend - kbeg) / BK;
+
+    const uint32_t base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * G::STAGE_BYTES;      // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), G::CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == G::CONSUMER_WARPS) {
+        // ===== producer warp: one lane issues the bulk tensor copies =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                if (kt >= STAGES) mbar_wait(bars + 8 * (STAGES + s), ((kt / STAGES) - 1) & 1);
+                const uint32_t full = bars + 8 * s;
+                const uint32_t sa = base + s * G::STAGE_BYTES, sb = sa + G::A_BYTES;
+                const int k0 = kbeg + kt * BK;
+                mbar_expect_tx(full, G::STAGE_BYTES);
+                if (AT == 0) {
+                    tma_load_2d(sa, &mapA, full, k0, m0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 16; ++j) tma_load_5d(sa + j * 2048, &mapA, full, m0 + 16 * j, 0, 0, k0 >> 3, 0);
+                }
+                if (BT == 0) {
+                    tma_load_2d(sb, &mapB, full, k0, n0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 16; ++j) tma_load_5d(sb + j * 2048, &mapB, full, n0 + 16 * j, 0, 0, k0 >> 3, 0);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp / G::WARPS_N) * WM, wn = (warp % G::WARPS_N) * WN;
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (beta != 0.0) {
+        constexpr int LINES = BM * BN / 16;
+        constexpr int CT = G::CONSUMER_WARPS * 32;
+#pragma unroll
+        for (int i = 0; i < LINES / CT; ++i) {
+            int line = tid + i * CT;
+            const double* pc = C + (int64_t)(m0 + line / (BN / 16)) * ldc + n0 + ((line % (BN / 16)) << 4);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
+        }
+    }
+
+    // per-thread fragment offsets (bytes) inside the A and B tiles for the four MMA steps of a slab
+    uint32_t aoff[4], boff[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        aoff[kk] = frag_off<AT>(wm + g, kk, t);
+        boff[kk] = frag_off<BT>(wn + g, kk, t);
+    }
+    // fragment i sits 8 mn further: K-major +8 rows = +1024 B; MN-major +8 mn = half a box: chunk bit 2 flips (+/- 64 B)
+    // for odd i and every second i moves one box (2048 B) on
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        mbar_wait(bars + 8 * s, (kt / STAGES) & 1);
+        const uint32_t sa = base + s * G::STAGE_BYTES, sb = sa + G::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                uint32_t o = (AT == 0) ? aoff[kk] + i * 1024 : ((aoff[kk] ^ ((i & 1) << 6)) + (i >> 1) * 2048);
+                a[i] = lds_f64(sa + o);
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                uint32_t o = (BT == 0) ? boff[kk] + j * 1024 : ((boff[kk] ^ ((j & 1) << 6)) + (j >> 1) * 2048);
+                b[j] = lds_f64(sb + o);
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
+
+    // epilogue (identical to the cp.async variant)
+    const bool diag = (tmask == TM_LOWER) && (n0 + BN - 1 > m0);
+    if (beta != 0.0 && !diag) {
+#pragma unroll
+        for (int i = 0; i < MI; i += 2) {
+            double2 o[2][NI];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                    o[ii][j] = *reinterpret_cast<const double2*>(C + (int64_t)(m0 + wm + (i + ii) * 8 + g) * ldc + n0 + wn + j * 8 + 2 * t);
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    double2 v;
+                    v.x = alpha * acc[i + ii][j][0] + beta * o[ii][j].x;
+                    v.y = alpha * acc[i + ii][j][1] + beta * o[ii][j].y;
+                    *reinterpret_cast<double2*>(C + (int64_t)(m0 + wm + (i + ii) * 8 + g) * ldc + n0 + wn + j * 8 + 2 * t) = v;
+                }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int grow = m0 + wm + i * 8 + g;
+        double* crow = C + (int64_t)grow * ldc;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int gcol = n0 + wn + j * 8 + 2 * t;
+            if (diag && gcol > grow) continue;
+            double2 v;
+            v.x = alpha * acc[i][j][0];
+            v.y = alpha * acc[i][j][1];
+            double2* p = reinterpret_cast<double2*>(crow + gcol);
+            if (beta != 0.0) {
+                double2 o = *p;
+                v.x += beta * o.x;
+                v.y += beta * o.y;
+            }
+            if (diag && gcol + 1 > grow) {
+                crow[gcol] = v.x;
+            } else {
+                *p = v;
+            }
+        }
+    }
+}
+
+// ---- tensor maps --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_encode_state = 0;   // 0 unknown, 1 ready, -1 unavailable
+
+static int encode_init() {
+    if (g_encode_state) return g_encode_state;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        g_encode_state = -1;
+        return -1;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    g_encode_state = 1;
+    return 1;
+}
+
+// operand `P` (logical rows = mn extent, K columns) with leading dimension ld; T = 0: stored [mn][k], T = 1: stored [k][mn]
+static int make_map(CUtensorMap* map, int T, const double* P, int64_t ld, int mn, int K, int rows_per_box) {
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r;
+    if (T == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)mn};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+        cuuint32_t box[2] = {16, (cuuint32_t)rows_per_box};
+        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)P, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[5] = {(cuuint64_t)mn, 2, 2, (cuuint64_t)(K / 8), 2};
+        cuuint64_t strides[4] = {(cuuint64_t)ld * 16, (cuuint64_t)ld * 8, (cuuint64_t)ld * 64, (cuuint64_t)ld * 32};
+        cuuint32_t box[5] = {16, 2, 2, 2, 2};
+        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)P, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 2000;
+}
+
 static int g_force_bn = -1;  // GP_GEMM_BN=64|128 overrides the tile-shape choice (tuning / A-B measurements)
 
 template <int AT, int BT, int BN_>
 static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                        int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
     using G = Cfg<BN_>;
-    static bool configured = false;
-    if (!configured) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<AT, BT, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-        configured = true;
-    }
     if (K % G::BK) return -1;
     int tiles_m = M / BM, tiles_n = N / BN_;
     if (tiles_m == 0 || tiles_n == 0) return 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_prof.on) {
-        while (g_prof.pool.size() < g_prof.used + 2) {
-            cudaEvent_t e;
-            GP_CUDA_CHECK(cudaEventCreate(&e));
-            g_prof.pool.push_back(e);
-        }
-        e0 = g_prof.pool[g_prof.used++];
-        e1 = g_prof.pool[g_prof.used++];
-        g_prof.flops += tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask);
-        g_prof.launches++;
-        cudaEventRecord(e0, stream);
-    }
+    int rc = configure_once((const void*)dgemm_dmma_kernel<AT, BT, BN_>, G::SMEM);
+    if (rc) return rc;
+    cudaEvent_t e1 = profile_begin(tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask), stream);
     dgemm_dmma_kernel<AT, BT, BN_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
         C, ldc, A, lda, B, ldb, tiles_m, tiles_n, K, alpha, beta, krange, tmask);
     if (e1) cudaEventRecord(e1, stream);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
+}
+
+static int g_impl = -1;      // GP_GEMM_IMPL=cpasync selects the older cp.async kernel (A-B measurements); default: TMA
+
+template <int AT, int BT, int BN_>
+static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                           int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
+    using G = TCfg<BN_>;
+    if (K % G::BK) return -1;
+    int tiles_m = M / BM, tiles_n = N / BN_;
+    if (tiles_m == 0 || tiles_n == 0) return 0;
+    int rc = configure_once((const void*)dgemm_tma_kernel<AT, BT, BN_>, G::SMEM);
+    if (rc) return rc;
+    CUtensorMap mapA, mapB;
+    if ((rc = make_map(&mapA, AT, A, lda, M, K, BM))) return rc;
+    if ((rc = make_map(&mapB, BT, B, ldb, N, K, BN_))) return rc;
+    cudaEvent_t e1 = profile_begin(tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask), stream);
+    dgemm_tma_kernel<AT, BT, BN_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
+        mapA, mapB, C, ldc, tiles_m, tiles_n, K, alpha, beta, krange, tmask);
+    if (e1) cudaEventRecord(e1, stream);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int BN_>
+static int launch_tma_bn(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                         int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
+    if (at == 0 && bt == 0) return launch_tma_inst<0, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 0 && bt == 1) return launch_tma_inst<0, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 1 && bt == 1) return launch_tma_inst<1, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    if (at == 1 && bt == 0) return launch_tma_inst<1, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    return -4;
 }
 
 template <int BN_>
@@ -290,6 +640,14 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
     // a CTA that overwrites an operand must own the whole row block it reads: the in-place panel solve needs BN = 128
     bool aliased = (C == A) || (C == B);
     int bn = aliased ? 128 : (g_force_bn == 128 ? 128 : 64);
+    if (g_impl < 0) {
+        const char* e = getenv("GP_GEMM_IMPL");
+        g_impl = (e && !strcmp(e, "cpasync")) ? 0 : 1;
+    }
+    if (g_impl == 1 && encode_init() == 1) {
+        if (bn == 128) return launch_tma_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+        return launch_tma_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+    }
     if (bn == 128) return launch_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     return launch_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
 }

@@ -25,6 +25,9 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
                  const double* B, int64_t ldb, int M, int N, int K, double alpha, double beta,
                  int krange, int tmask, cudaStream_t stream);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel); thread-safe
+int configure_once(const void* func, int smem_bytes);
+
 int profile_enable(int on);
 int profile_read(double* ms_sum, double* ms_union, double* flops, long long* launches);
 
