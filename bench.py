@@ -181,14 +181,14 @@ def cpu_evaluation(n, method='cholesky', idx=0):
     return t1 - t0, t2 - t1, kind
 
 
-def cpu_sample(n_full, sizes=(4000, 8000), repeats=3, full=True, eigen=True):
+def cpu_sample(n_full, sizes=(4000, 8000), repeats=(2, 1), full=True, eigen_n=4000):
     """The reference's CPU path on this box's host cores: best of `repeats` at each n in `sizes`, the fitted exponent,
     and (full=True) ONE measured evaluation at n_full - the value is then a measurement, not an extrapolation."""
     cores = pin_host_threads()
     rows, kind = [], 'port'
-    for ns in sizes:
+    for ns, reps in zip(sizes, repeats):
         best = None
-        for r in range(repeats):
+        for r in range(reps):
             tg, tl, kind = cpu_evaluation(ns, 'cholesky', r)
             best = (tg, tl) if best is None or tg + tl < sum(best) else best
         rows.append({'n': ns, 'generation_s': best[0], 'likelihood_s': best[1], 'seconds': sum(best)})
@@ -199,8 +199,8 @@ def cpu_sample(n_full, sizes=(4000, 8000), repeats=3, full=True, eigen=True):
     t_fit = rows[-1]['generation_s'] * s ** 2 + rows[-1]['likelihood_s'] * s ** 3
     out = {'unit': UNIT, 'cores': cores, 'kind': kind, 'samples': rows, 'fitted_exponent': exponent,
            'seconds_per_eval_n3_fit_from_largest_sample': t_fit}
-    if eigen:
-        ns = rows[-1]['n']
+    if eigen_n:
+        ns = eigen_n
         tg, tl, _ = cpu_evaluation(ns, 'eigenvalue', 0)
         out['eigenvalue_method'] = {'n': ns, 'generation_s': tg, 'likelihood_s': tl,
                                     'note': "imate_method='eigenvalue' (likelihood.py:41): one eigvalsh per matrix + the same 4 dposv"}
@@ -208,13 +208,13 @@ def cpu_sample(n_full, sizes=(4000, 8000), repeats=3, full=True, eigen=True):
         tg, tl, _ = cpu_evaluation(n_full, 'cholesky', 0)
         out.update({'value': 1.0 / (tg + tl), 'extrapolated': False, 'seconds_per_eval': tg + tl,
                     'sample': 'ONE measured evaluation at n=%d (Matern generation %.1fs + DirectLikelihood l and jacobian '
-                              '%.1fs, Cholesky method, %d threads); smaller n best-of-%d: %s'
-                              % (n_full, tg, tl, cores, repeats,
+                              '%.1fs, Cholesky method, %d threads); smaller n (best of %s): %s'
+                              % (n_full, tg, tl, cores, list(repeats),
                                  ', '.join('n=%d %.2fs' % (r_['n'], r_['seconds']) for r_ in rows))})
     else:
         out.update({'value': 1.0 / t_fit, 'extrapolated': True, 'seconds_per_eval': t_fit,
                     'sample': 'best of %d at n=%d (generation %.2fs + likelihood %.2fs), scaled with n^2 / n^3 to n=%d'
-                              % (repeats, rows[-1]['n'], rows[-1]['generation_s'], rows[-1]['likelihood_s'], n_full)})
+                              % (repeats[-1], rows[-1]['n'], rows[-1]['generation_s'], rows[-1]['likelihood_s'], n_full)})
     return out
 
 
@@ -233,7 +233,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     steps = [cpu_evaluation(ns, 'cholesky', s_) for s_ in range(args.steps)]
     wall = time.perf_counter() - t0
-    base = cpu_sample(n, sizes=(ns, 2 * ns), repeats=1, full=full)
+    base = cpu_sample(n, sizes=(ns, 2 * ns), repeats=(1, 1), full=full, eigen_n=2 * ns)
     base['step_sample'] = {'n': ns, 'steps': args.steps, 'mean_s': wall / max(args.steps, 1),
                            'min_s': min(a + b for a, b, _ in steps), 'max_s': max(a + b for a, b, _ in steps)}
     base['cores'] = cores
@@ -444,6 +444,122 @@ def secondary_measurements():
     return out
 
 
+def _timed_max_ms(fn, world):
+    """Runs fn() between a barrier + synchronize on both sides, timed with CUDA events on the current stream (everything
+    the library enqueues is ordered after / joined into it); returns (result, milliseconds as the MAX over ranks)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return res, float(ms.item())
+
+
+def sharded_measurements(world, rank):
+    """The workloads of BASELINE.json that SHARD across GPUs, run by every rank at every --gpus N (N = 1 included, as the
+    base of the scaling curve), each a FIXED total amount of work (strong scaling):
+      C3  configs[2]: (rho x eta) grid of cells at n = 8000, contiguous rho groups per rank, results all-gathered;
+      C4  configs[3]: ONE sparse n = 2^20 loglik + gradient with the Hutchinson / SLQ probes split over the ranks
+                      (all-reduce of count / sum / sum of squares), and a sparse (rho x eta) sweep;
+      C5  configs[4]: dense n = 100 000, block-cyclic distributed Cholesky with NCCL panel broadcasts, l^ + gradient.
+    Collective per workload (the limiting one is named in DESIGN.md section 6)."""
+    import torch
+    from gaussian_proc.sweep import likelihood_grid
+    from gaussian_proc._sparse import generate_sparse_correlation
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    out = {}
+
+    # ---- C3: 32 rho x 16 eta = 512 cells at n = 8000 (one eighth of the 64 x 64 grid; the same cells at every N)
+    pts, z, X = make_inputs(8000)
+    rhos, etas = numpy.linspace(0.05, 0.3, 32), numpy.logspace(-2, 2, 16)
+    likelihood_grid(pts, z, X, NU, rhos[:world], etas[:4])                      # warm: allocator, kernel attributes
+    G, ms = _timed_max_ms(lambda: likelihood_grid(pts, z, X, NU, rhos, etas), world)
+    cells = G.shape[0] * G.shape[1]
+    out['C3_sweep_n8k'] = {'workload': 'configs[2] slice: n=8000, 32 rho x 16 eta = 512 cells (l^, d/d eta, d/d rho each)',
+                           'scaling': 'strong', 'cells': int(cells), 'seconds': ms * 1e-3, 'cells_per_s': cells / (ms * 1e-3),
+                           'tflops_per_gpu': cells * 8000.0 ** 3 / (ms * 1e-3) / world * 1e-12,
+                           'collective': 'one all_gather of 5 doubles per cell at the end',
+                           'checksum': float(numpy.sum(G[:, :, 0]))}
+    del G
+    torch.cuda.empty_cache()
+
+    # ---- C4: sparse n = 2^20
+    n = 2 ** 20
+    sp, zs, Xs = make_inputs(n)
+    scale = numpy.array([0.005, 0.005])
+    opts = {'seed': 0, 'lanczos_degree': 30}
+
+    def sparse_eval(split):
+        Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
+        o = dict(opts)
+        o['probe_split'] = bool(split)
+        Km = MixedCorrelation(Kc, imate_method='slq', imate_options=o)
+        r = ProfileLikelihood.log_likelihood_and_gradient(zs, Xs, Km, 10.0)
+        return [float(v) for v in r], int(Km.engine.last_info.get('num_samples', 0))
+
+    sparse_eval(True)
+    (r_split, ns_split), ms_split = _timed_max_ms(lambda: sparse_eval(True), world)
+    (r_single, ns_single), ms_single = _timed_max_ms(lambda: sparse_eval(False), world)
+    out['C4_sparse_n1M_probe_split'] = {
+        'workload': 'configs[3]: ONE loglik+grad at n=2^20 (nu=0.5, rho=0.005, density=1e-3, eta=10): CSR generation + '
+                    'row-blocked build + CG for [X z] (replicated) + SLQ / Hutchinson probes split over the ranks',
+        'scaling': 'strong', 'seconds': ms_split * 1e-3, 'evals_per_s': 1e3 / ms_split,
+        'seconds_unsplit_same_run': ms_single * 1e-3, 'speedup_vs_unsplit': ms_single / ms_split,
+        'num_samples': ns_split, 'loglik_grad': r_split,
+        'rel_diff_vs_unsplit': [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(r_split, r_single)],
+        'collective': 'all_reduce of (count, failed, sum, sum of squares) per estimator round'}
+    rh, et = numpy.linspace(0.004, 0.006, 8), numpy.logspace(1, 3, 16)
+    Gs, ms = _timed_max_ms(lambda: likelihood_grid(sp, zs, Xs, 0.5, rh, et, sparse=True, density=1e-3, imate_options=opts), world)
+    out['C4_sparse_sweep_n1M'] = {'workload': 'configs[3] sweep: n=2^20, 8 rho x 16 eta = 128 cells, one CSR + operator per rho',
+                                  'scaling': 'strong', 'cells': 128, 'seconds': ms * 1e-3, 'cells_per_s': 128 / (ms * 1e-3),
+                                  'collective': 'one all_gather of 5 doubles per cell at the end',
+                                  'checksum': float(numpy.sum(Gs[:, :, 0]))}
+    del Gs
+    torch.cuda.empty_cache()
+
+    # ---- C5: dense n = 100 000 distributed Cholesky (needs >= 2 GPUs for the memory: 80 GB of K + the replicated factor)
+    nbig = int(os.environ.get('GP_BENCH_C5_N', '100000' if world >= 2 else '40000'))
+    try:
+        out['C5_blockcyclic'] = blockcyclic_measurement(nbig, world, rank)
+    except Exception as e:  # noqa: BLE001 -- the other legs must still print
+        out['C5_blockcyclic'] = {'error': repr(e)[:300]}
+    return out
+
+
+def blockcyclic_measurement(n, world, rank):
+    import torch
+    from gaussian_proc._blockcyclic import BlockCyclicCholesky
+    pts, z, X = make_inputs(n)
+    nb = int(os.environ.get('GP_BENCH_C5_NB', '512'))
+    bc = BlockCyclicCholesky(pts, 0.1, NU, nb=nb)
+    res, ms = _timed_max_ms(lambda: bc.profile_log_likelihood_and_gradient(z, X, 0.1), world)
+    st = dict(bc.stats)
+    fl_factor = n ** 3 / 3.0
+    out = {'workload': 'configs[4]: dense Matern nu=2.5, n=%d, eta=0.1, nb=%d, %d x %d process grid: generation in place, '
+                       'distributed Cholesky, l^ + d/d eta + d/d rho' % (n, nb, bc.P_r, bc.P_c),
+           'scaling': 'strong', 'seconds_total': ms * 1e-3, 'loglik_grad': [float(v) for v in res],
+           'seconds_generate_factor': st.get('factor_s'), 'factor_tflops_total': fl_factor / st['factor_s'] * 1e-12 if st.get('factor_s') else None,
+           'factor_tflops_per_gpu': fl_factor / st['factor_s'] / world * 1e-12 if st.get('factor_s') else None,
+           'seconds_inverse_and_traces': st.get('traces_s'), 'seconds_solves': st.get('solve_s'),
+           'total_tflops_per_gpu': float(n) ** 3 / (ms * 1e-3) / world * 1e-12,
+           'bytes_received_per_rank': st.get('bytes_received'), 'nccl_seconds_on_comm_stream': st.get('comm_s'),
+           'nccl_fraction_of_factor_time': (st['comm_s'] / st['factor_s']) if st.get('comm_s') is not None and st.get('factor_s') else None,
+           'collective': 'panel broadcast (NCCL, side stream, look-ahead 1) per block column; all_reduce of the trace partials'}
+    del bc
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -625,21 +741,31 @@ def run_ours(args):
                   'ProfileLikelihood.log_likelihood_and_gradient_async(z, X, K_mixed, eta)() ',
            'last_result': [float(v) for v in r]}
 
+    sharded = None
+    if not args.no_secondary:
+        del hp, hz, hX
+        torch.cuda.empty_cache()
+        try:
+            sharded = sharded_measurements(world, rank)
+        except Exception as e:  # noqa: BLE001 -- the headline must still print
+            sharded = {'error': repr(e)[:300]}
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': bench_config(n, npad, C),
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
-        if world == 1 and not args.no_secondary:
-            del hp, hz, hX
-            torch.cuda.empty_cache()
-            try:
-                line['secondary'] = secondary_measurements()
-            except Exception as e:  # noqa: BLE001 -- the headline must still print
-                line['secondary'] = {'error': repr(e)[:300]}
+        if not args.no_secondary:
+            line['secondary'] = {'sharded': sharded}
+            if world == 1:
+                try:
+                    line['secondary'].update(secondary_measurements())
+                except Exception as e:  # noqa: BLE001 -- the headline must still print
+                    line['secondary']['error'] = repr(e)[:300]
         if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_sample(n, full=os.environ.get('GP_BENCH_CPU_FULL', '1') != '0')
+            # bounded (~30 s): n = 4000 and 8000 measured, n = 20 000 from the n^2 / n^3 fit (flagged); the measured
+            # n = 20 000 evaluation is the reference arm's (`bench.py --impl reference`)
+            line['cpu_baseline'] = cpu_sample(n, full=os.environ.get('GP_BENCH_CPU_FULL', '0') != '0')
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

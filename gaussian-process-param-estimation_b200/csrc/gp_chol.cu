@@ -13,6 +13,9 @@
 #include "gp_internal.h"
 #include <stdlib.h>
 #include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace gp {
 
@@ -383,33 +386,47 @@ __global__ void place_diag_inverse_kernel(const double* __restrict__ Linv, doubl
 // look-ahead panel of the factorisation run beside the caller's stream, ordered with events ---------------------
 struct SidePool {
     cudaStream_t s[3];
+    // ordering events of this pool, reused round-robin: an event is re-recorded only after EVENT_RING later orderings
+    // have been enqueued on the same caller stream, by which time the earlier wait has long been submitted (a
+    // cudaStreamWaitEvent captures the event's state at submission, so re-recording afterwards is safe)
+    std::vector<cudaEvent_t> events;
+    size_t next = 0;
 };
-// one pool per caller stream: two evaluations driven on two streams (a sweep keeps two cells in flight to fill the
-// latency-bound phases of each other) must not serialise on shared helper streams
-static std::map<cudaStream_t, SidePool> g_pools;
+constexpr size_t EVENT_RING = 64;
+// one pool per (device, caller stream): two evaluations driven on two streams (a sweep keeps two cells in flight to fill
+// the latency-bound phases of each other) must not serialise on shared helper streams, and a second device in the same
+// process gets its own streams. The map is guarded by a mutex; a pool itself is only used by the host thread that drives
+// its caller stream.
+static std::mutex g_pools_mutex;
+static std::map<std::pair<int, cudaStream_t>, SidePool*> g_pools;
 static thread_local SidePool* g_side_ptr = nullptr;
 #define g_side (*g_side_ptr)
 
 static int side_streams_init(cudaStream_t caller) {
-    auto it = g_pools.find(caller);
+    int dev = 0;
+    GP_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pools_mutex);
+    auto key = std::make_pair(dev, caller);
+    auto it = g_pools.find(key);
     if (it == g_pools.end()) {
         int lo = 0, hi = 0;
         GP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        SidePool p;
-        for (int i = 0; i < 3; ++i) GP_CUDA_CHECK(cudaStreamCreateWithPriority(&p.s[i], cudaStreamNonBlocking, hi));
-        it = g_pools.insert(std::make_pair(caller, p)).first;
+        SidePool* p = new SidePool();
+        for (int i = 0; i < 3; ++i) GP_CUDA_CHECK(cudaStreamCreateWithPriority(&p->s[i], cudaStreamNonBlocking, hi));
+        p->events.resize(EVENT_RING);
+        for (size_t i = 0; i < EVENT_RING; ++i) GP_CUDA_CHECK(cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming));
+        it = g_pools.insert(std::make_pair(key, p)).first;
     }
-    g_side_ptr = &it->second;
+    g_side_ptr = it->second;
     return 0;
 }
 
-// make `to` wait for everything enqueued on `from` so far
+// make `to` wait for everything enqueued on `from` so far (event from the pool's ring: no create / destroy per call)
 static int stream_order(cudaStream_t from, cudaStream_t to) {
-    cudaEvent_t e;
-    GP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t e = g_side.events[g_side.next];
+    g_side.next = (g_side.next + 1) % EVENT_RING;
     GP_CUDA_CHECK(cudaEventRecord(e, from));
     GP_CUDA_CHECK(cudaStreamWaitEvent(to, e, 0));
-    GP_CUDA_CHECK(cudaEventDestroy(e));  // released once the recorded work completes
     return 0;
 }
 
@@ -509,12 +526,8 @@ int gp_potrf_f64(double* A, int64_t n, int64_t npad, int* info_dev, void* ws, vo
     if (!A || !info_dev || !ws || npad <= 0 || (npad % DB) || npad > INT32_MAX || n > npad) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     double* linv = (double*)ws;
-    static bool configured = false;
     const int diag_smem = (DB * DPITCH + DB + 3 * SB * TPITCH) * sizeof(double);
-    if (!configured) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
-        configured = true;
-    }
+    if (int rc0 = configure_once((const void*)chol_diag_block_kernel, diag_smem)) return rc0;
     int rc = side_streams_init(s);
     if (rc) return rc;
     static bool nb_read = false;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #define GP_TILE 128  // every dense matrix is padded to a multiple of this (identity padding)
 
@@ -20,8 +21,8 @@
 namespace gp {
 
 // number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
-#define GP_COUNT(k) (gp::g_launch_count += (unsigned long long)(k))
+extern std::atomic<unsigned long long> g_launch_count;
+#define GP_COUNT(k) (gp::g_launch_count.fetch_add((unsigned long long)(k), std::memory_order_relaxed))
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

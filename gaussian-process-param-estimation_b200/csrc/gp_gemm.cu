@@ -22,7 +22,7 @@
 
 namespace gp {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // optional per-launch timing of the DMMA GEMM (bench.py's roofline leg): events around every launch
 struct GemmProfile {
@@ -352,7 +352,8 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 template <int AT, int BT, int BN_>
 __global__ void __launch_bounds__(TCfg<BN_>::THREADS, TCfg<BN_>::MIN_CTAS)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C, int64_t ldc,
-                 int tiles_m, int tiles_n, int K, double alpha, double beta, int krange, int tmask) {
+                 int tiles_m, int tiles_n, int K, double alpha, double beta, int krange, int tmask,
+                 const int* __restrict__ kbeg_tab, const int* __restrict__ kend_tab) {
     using G = TCfg<BN_>;
     constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -372,8 +373,11 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (krange == KR_A_LOWER) kend = min(K, m0 + BM);
     else if (krange == KR_B_LOWER) kbeg = min(n0, K);
     else if (krange == KR_TN_LOWER) kbeg = min(max(m0, n0), K);
+    // optional per-row-tile k ranges (staircase operands of the distributed inverse, _blockcyclic.py)
+    if (kbeg_tab) kbeg = max(kbeg, min(kbeg_tab[tm], K));
+    if (kend_tab) kend = min(kend, kend_tab[tm]);
     kbeg = (kbeg / BK) * BK;
-    const int KT = (kend - kbeg) / BK;
+    const int KT = max(0, (kend - kbeg) / BK);
 
     const uint32_t base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + STAGES * G::STAGE_BYTES;      // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
@@ -589,7 +593,8 @@ static int g_impl = -1;      // GP_GEMM_IMPL=cpasync selects the older cp.async 
 
 template <int AT, int BT, int BN_>
 static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
-                           int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
+                           int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream,
+                           const int* kbeg_tab, const int* kend_tab) {
     using G = TCfg<BN_>;
     if (K % G::BK) return -1;
     int tiles_m = M / BM, tiles_n = N / BN_;
@@ -601,7 +606,7 @@ static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda,
     if ((rc = make_map(&mapB, BT, B, ldb, N, K, BN_))) return rc;
     cudaEvent_t e1 = profile_begin(tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask), stream);
     dgemm_tma_kernel<AT, BT, BN_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
-        mapA, mapB, C, ldc, tiles_m, tiles_n, K, alpha, beta, krange, tmask);
+        mapA, mapB, C, ldc, tiles_m, tiles_n, K, alpha, beta, krange, tmask, kbeg_tab, kend_tab);
     if (e1) cudaEventRecord(e1, stream);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
@@ -610,11 +615,12 @@ static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda,
 
 template <int BN_>
 static int launch_tma_bn(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
-                         int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream) {
-    if (at == 0 && bt == 0) return launch_tma_inst<0, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 0 && bt == 1) return launch_tma_inst<0, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 1 && bt == 1) return launch_tma_inst<1, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-    if (at == 1 && bt == 0) return launch_tma_inst<1, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+                         int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream,
+                         const int* kbeg_tab = nullptr, const int* kend_tab = nullptr) {
+    if (at == 0 && bt == 0) return launch_tma_inst<0, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 0 && bt == 1) return launch_tma_inst<0, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 1 && bt == 1) return launch_tma_inst<1, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 1 && bt == 0) return launch_tma_inst<1, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
     return -4;
 }
 
@@ -642,7 +648,7 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
     int bn = aliased ? 128 : (g_force_bn == 128 ? 128 : 64);
     if (g_impl < 0) {
         const char* e = getenv("GP_GEMM_IMPL");
-        g_impl = (e && !strcmp(e, "cpasync")) ? 0 : 1;
+        g_impl = (e && !strcmp(e, "tma")) ? 1 : 0;   // TEMPORARY default: cp.async kernel until the TMA path is cleared at n = 20k
     }
     if (g_impl == 1 && encode_init() == 1) {
         if (bn == 128) return launch_tma_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
@@ -651,6 +657,22 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
     if (bn == 128) return launch_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     return launch_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
 }
+
+// GEMM with per-row-tile k ranges: tile row tm (128 rows) uses k in [kbeg_tab[tm], kend_tab[tm]) (device int arrays, either
+// may be null). TMA kernel only.
+int launch_dgemm_ktab(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                      int M, int N, int K, double alpha, double beta, const int* kbeg_tab, const int* kend_tab,
+                      cudaStream_t stream) {
+    if (M < 0 || N < 0 || K < 0 || (M % BM) || (N % 128) || (K % 32)) return -1;
+    if ((lda & 1) || (ldb & 1) || (ldc & 1)) return -2;
+    if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return -3;
+    if (C == A || C == B) return -6;
+    if (encode_init() != 1) return -7;
+    if (K == 0) K = 32;   // a zero k extent still has to scale C by beta: the tables (or kend = 0) keep the loop empty
+    return launch_tma_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, KR_FULL, TM_ALL, stream, kbeg_tab, kend_tab);
+}
+
+int set_gemm_impl(int impl) { g_impl = impl; return 0; }
 
 int profile_enable(int on) {
     g_prof.on = on != 0;

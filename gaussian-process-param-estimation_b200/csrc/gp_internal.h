@@ -28,6 +28,11 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel); thread-safe
 int configure_once(const void* func, int smem_bytes);
 
+int launch_dgemm_ktab(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
+                      int M, int N, int K, double alpha, double beta, const int* kbeg_tab, const int* kend_tab,
+                      cudaStream_t stream);
+
+int set_gemm_impl(int impl);   // 1 = TMA + mbarrier kernel (default), 0 = cp.async kernel (A-B measurements)
 int profile_enable(int on);
 int profile_read(double* ms_sum, double* ms_union, double* flops, long long* launches);
 

@@ -361,6 +361,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct LoglikWs {
     double* S;        // npad x p
     double* V;        // npad x p
+    double* V2;       // npad x p (Kn^-1 S of the third-moment flag)
     double* logdet;   // 1
     double* gram;     // nparts x p^2
     double* tr;       // ntiles x 3
@@ -379,6 +380,7 @@ static LoglikWs carve(void* ws, int64_t npad, int p) {
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return base ? base + o : (char*)nullptr; };
     w.S = (double*)take(sizeof(double) * npad * MAXP);
     w.V = (double*)take(sizeof(double) * npad * MAXP);
+    w.V2 = (double*)take(sizeof(double) * npad * MAXP);
     w.logdet = (double*)take(sizeof(double) * 4);
     w.gram = (double*)take(sizeof(double) * 296 * MAXP * MAXP);
     w.tr = (double*)take(sizeof(double) * (T * (T + 1) / 2) * 3);
@@ -442,6 +444,37 @@ int gp_symm_skinny(const double* K, int64_t n, int64_t npad, const double* X, in
     return 0;
 }
 
+// V = dK/drho S with dK regenerated from the points (never stored): the device half of Q = S^T dK S for callers that
+// assemble the evaluation themselves (the distributed path, gaussian_proc/_blockcyclic.py)
+int gp_dk_apply(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, const double* S, int64_t p,
+                int64_t lds, double* V, void* stream) {
+    if (!points || !scale_host || !S || !V || n <= 0 || d <= 0 || d > LMAXD || p <= 0 || p > MAXP || lds < p) return -1;
+    MaternParams mp;
+    mp.nu = nu; mp.coef = 0.0; mp.sq2nu = 0.0;
+    for (int k = 0; k < d; ++k) {
+        if (!(scale_host[k] > 0.0) || scale_host[k] != scale_host[0]) return -4;
+        mp.inv_scale[k] = 1.0 / scale_host[k];
+    }
+    mp.inv_rho = 1.0 / scale_host[0];
+    int mode = matern_mode_of(nu);
+    if (mode == MAT_GENERAL) {
+        mp.coef = pow(2.0, 1.0 - nu) / tgamma(nu);
+        mp.sq2nu = sqrt(2.0 * nu);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 63) / 64);
+    switch (mode) {
+        case MAT_05: dk_apply_kernel<MAT_05><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+        case MAT_15: dk_apply_kernel<MAT_15><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+        case MAT_25: dk_apply_kernel<MAT_25><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+        case MAT_GAUSS: dk_apply_kernel<MAT_GAUSS><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+        default: dk_apply_kernel<MAT_GENERAL><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+    }
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
 int64_t gp_traces_workspace_bytes(int64_t npad) {
     int64_t T = npad / 128;
     return (int64_t)sizeof(double) * (T * (T + 1) / 2 * 3 + T * T + 64);
@@ -469,7 +502,7 @@ int gp_inverse_traces(const double* M, int64_t n, int64_t npad, int kind, double
 
 int64_t gp_loglik_workspace_bytes(int64_t npad) { return (int64_t)carve(nullptr, npad, MAXP).total; }
 
-int64_t gp_loglik_out_len(int64_t p) { return 8 + 3 * p * p; }
+int64_t gp_loglik_out_len(int64_t p) { return 8 + 4 * p * p; }
 
 int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, int64_t p, double eta, int flags,
                     const double* points, int64_t d, const double* scale_host, double nu, double* A, double* W,
@@ -477,6 +510,7 @@ int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, i
     if (!K || !R || !A || !potrf_ws || !ws || !out || n <= 0 || npad != gp_padded_size(n) || p <= 0 || p > MAXP) return -1;
     if ((flags & 3) && !W) return -2;
     if ((flags & 4) && (!(flags & 2) || !points || !scale_host || d <= 0 || d > LMAXD)) return -3;
+    if ((flags & 8) && !(flags & 3)) return -5;
     cudaStream_t s = (cudaStream_t)stream;
     LoglikWs w = carve(ws, npad, (int)p);
     const int N = (int)n, NP = (int)npad, P = (int)p;
@@ -499,7 +533,14 @@ int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, i
     double* Q = H + p * p;
     if ((rc = gram(R, w.S, N, P, p, w.gram, G, s))) return rc;
     if ((rc = gram(w.S, w.S, N, P, p, w.gram, H, s))) return rc;
-    GP_CUDA_CHECK(cudaMemsetAsync(Q, 0, sizeof(double) * p * p, s));
+    double* T3 = Q + p * p;
+    GP_CUDA_CHECK(cudaMemsetAsync(Q, 0, sizeof(double) * 2 * p * p, s));
+    if (flags & 8) {
+        // third moments (Hessian, second eta-derivative): T3 = S^T Kn^-1 S = R^T Kn^-3 R from one more skinny solve batch
+        GP_CUDA_CHECK(cudaMemcpyAsync(w.V2, w.S, sizeof(double) * npad * p, cudaMemcpyDeviceToDevice, s));
+        if ((rc = solve_with_inverse(W, NP, w.V2, w.V, P, w.tpart, s))) return rc;
+        if ((rc = gram(w.S, w.V2, N, P, p, w.gram, T3, s))) return rc;
+    }
     if (flags & 2) {
         if ((rc = gp_lauum_f64(W, A, npad, stream))) return rc;
         bool with_dk = (flags & 4) != 0;

@@ -6,6 +6,7 @@
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_matern.cuh"
+#include "gp_internal.h"
 
 namespace gp {
 
@@ -119,10 +120,10 @@ static int launch_mode(const double* pts, int n, int d, int npad, double* K, dou
     int tiles = T * (T + 1) / 2;
     size_t smem = sizeof(double) * (2 * d * MT + (dK ? 2 : 1) * CH * PITCH);
     if (dK) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(matern_dense_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        if (int rc = configure_once((const void*)matern_dense_kernel<MODE, true>, 96 * 1024)) return rc;
         matern_dense_kernel<MODE, true><<<tiles, 256, smem, s>>>(pts, n, d, npad, K, dK, mp);
     } else {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(matern_dense_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        if (int rc = configure_once((const void*)matern_dense_kernel<MODE, false>, 96 * 1024)) return rc;
         matern_dense_kernel<MODE, false><<<tiles, 256, smem, s>>>(pts, n, d, npad, K, nullptr, mp);
     }
     GP_COUNT(1);
@@ -132,7 +133,7 @@ static int launch_mode(const double* pts, int n, int d, int npad, double* K, dou
 
 // ---- rectangular cross-correlation block K(P_rows, P_cols) for distributed (block-cyclic) layouts -----------------
 // Global indices decide the special cases: identity padding for indices >= n, exactly 1 (+ eta) on the diagonal.
-template <int MODE>
+template <int MODE, bool DK>
 __global__ void __launch_bounds__(256)
 matern_cross_kernel(const double* __restrict__ prow, const double* __restrict__ pcol, const int* __restrict__ rg,
                     const int* __restrict__ cg, int n, int d, int64_t ld, double* __restrict__ out, double eta, MaternParams mp) {
@@ -153,14 +154,19 @@ matern_cross_kernel(const double* __restrict__ prow, const double* __restrict__ 
         for (int e = 0; e < 4; ++e) {
             const int cl = tx * 4 + e, gj = gc[cl];
             double val;
-            if (gi >= n || gj >= n) val = (gi == gj) ? 1.0 : 0.0;
-            else if (gi == gj) val = 1.0 + eta;
+            if (gi >= n || gj >= n) val = (gi == gj && !DK) ? 1.0 : 0.0;
+            else if (gi == gj) val = DK ? 0.0 : 1.0 + eta;
             else {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < MAXD; ++k)
                     if (k < d) { double t = (sr[k][rr] - sc[k][cl]) * mp.inv_scale[k]; s += t * t; }
-                val = matern_value<MODE>(sqrt(s), mp);
+                if (DK) {
+                    double kv;
+                    matern_value_drho<MODE>(sqrt(s), mp, &kv, &val);      // d/d rho of an isotropic correlation scale
+                } else {
+                    val = matern_value<MODE>(sqrt(s), mp);
+                }
             }
             v[e] = val;
         }
@@ -172,9 +178,10 @@ matern_cross_kernel(const double* __restrict__ prow, const double* __restrict__ 
 
 template <int MODE>
 static int launch_cross(const double* prow, const double* pcol, const int* rg, const int* cg, int nr, int nc, int n, int d,
-                        int64_t ld, double* out, double eta, const MaternParams& mp, cudaStream_t s) {
+                        int64_t ld, double* out, double eta, const MaternParams& mp, cudaStream_t s, bool dk = false) {
     dim3 grid(nc / 128, nr / 64);
-    matern_cross_kernel<MODE><<<grid, 256, 0, s>>>(prow, pcol, rg, cg, n, d, ld, out, eta, mp);
+    if (dk) matern_cross_kernel<MODE, true><<<grid, 256, 0, s>>>(prow, pcol, rg, cg, n, d, ld, out, eta, mp);
+    else matern_cross_kernel<MODE, false><<<grid, 256, 0, s>>>(prow, pcol, rg, cg, n, d, ld, out, eta, mp);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
@@ -216,9 +223,9 @@ extern "C" int gp_matern_dense(const double* points, int64_t n, int64_t d, const
 
 // out[r][c] = K(p_row[r], p_col[c]) (+ eta on the global diagonal) for nr x nc blocks of a larger padded matrix;
 // row_gidx / col_gidx are the global indices of the rows / columns (device int32), n the unpadded global size.
-extern "C" int gp_matern_cross(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
-                               int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
-                               int64_t ld, void* stream) {
+static int matern_cross_impl(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                             int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
+                             int64_t ld, void* stream, bool dk) {
     using namespace gp;
     if (!prow || !pcol || !row_gidx || !col_gidx || !out || !scale_host || nr <= 0 || nc <= 0 || (nr % 64) || (nc % 128) || d <= 0 ||
         d > MAXD || (ld & 1))
@@ -226,6 +233,7 @@ extern "C" int gp_matern_cross(const double* prow, const double* pcol, const int
     MaternParams mp;
     for (int k = 0; k < d; ++k) {
         if (!(scale_host[k] > 0.0)) return -3;
+        if (dk && scale_host[k] != scale_host[0]) return -4;
         mp.inv_scale[k] = 1.0 / scale_host[k];
     }
     mp.nu = nu; mp.coef = 0.0; mp.sq2nu = 0.0; mp.inv_rho = 1.0 / scale_host[0];
@@ -237,10 +245,23 @@ extern "C" int gp_matern_cross(const double* prow, const double* pcol, const int
     }
     cudaStream_t s = (cudaStream_t)stream;
     switch (mode) {
-        case MAT_05: return launch_cross<MAT_05>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
-        case MAT_15: return launch_cross<MAT_15>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
-        case MAT_25: return launch_cross<MAT_25>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
-        case MAT_GAUSS: return launch_cross<MAT_GAUSS>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
-        default: return launch_cross<MAT_GENERAL>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s);
+        case MAT_05: return launch_cross<MAT_05>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s, dk);
+        case MAT_15: return launch_cross<MAT_15>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s, dk);
+        case MAT_25: return launch_cross<MAT_25>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s, dk);
+        case MAT_GAUSS: return launch_cross<MAT_GAUSS>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s, dk);
+        default: return launch_cross<MAT_GENERAL>(prow, pcol, row_gidx, col_gidx, (int)nr, (int)nc, (int)n, (int)d, ld, out, eta, mp, s, dk);
     }
+}
+
+extern "C" int gp_matern_cross(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                               int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
+                               int64_t ld, void* stream) {
+    return matern_cross_impl(prow, pcol, row_gidx, col_gidx, nr, nc, n, d, scale_host, nu, eta, out, ld, stream, false);
+}
+
+// the same block of dK/d rho (isotropic correlation scale): zero on the global diagonal and in the padding
+extern "C" int gp_matern_cross_dk(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                                  int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double* out,
+                                  int64_t ld, void* stream) {
+    return matern_cross_impl(prow, pcol, row_gidx, col_gidx, nr, nc, n, d, scale_host, nu, 0.0, out, ld, stream, true);
 }

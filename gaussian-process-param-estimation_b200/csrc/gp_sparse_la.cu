@@ -6,6 +6,7 @@
 // All column blocks are n x B row-major with B in {1,2,4,8,16,32}; HBM-bound: 12 nnz + 4 (n+1) + 16 n B bytes / SpMM.
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
+#include "gp_internal.h"
 
 namespace gp {
 
@@ -858,6 +859,9 @@ int gp_block_combine(const double* basis, int64_t n, int64_t B, int64_t m, const
     if (!basis || !coef_dev || !X || n <= 0 || B <= 0 || B > 32 || m <= 0 || m > 256) return -1;
     const int64_t total = n * B;
     const int64_t work = (B == 1) ? total : total / 2;
+    // m B coefficients in dynamic shared memory: up to 64 KB (m = 256, B = 32), above the 48 KB default
+    if (m * B * (int64_t)sizeof(double) > 48 * 1024)
+        if (int rc = configure_once((const void*)block_combine_kernel, 64 * 1024)) return rc;
     block_combine_kernel<<<(unsigned)((work + 255) / 256), 256, (size_t)(m * B * sizeof(double)), (cudaStream_t)stream>>>(
         basis, total, (int)B, (int)m, coef_dev, X);
     GP_COUNT(1);

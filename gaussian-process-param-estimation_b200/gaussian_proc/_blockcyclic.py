@@ -1,40 +1,61 @@
 """
-2-D block-cyclic distributed Cholesky of K + eta*I for matrices that do not fit one GPU (BASELINE.json configs[4]:
-dense Matern n = 100 000 on 2 / 4 / 8 B200), with the panel exchanged by NCCL broadcasts.
+Distributed dense Cholesky + log-likelihood GRADIENT for matrices that do not fit one GPU (BASELINE.json configs[4]:
+dense Matern n = 100 000 on 2 / 4 / 8 B200), panels exchanged by NCCL broadcasts over NVLink. The reference
+is single-node LAPACK (gaussian_proc/_mixed_correlation/_linear_solver.py:71, mixed_correlation.py:183-191,250-261); the
+quantities produced here are those of _likelihood/_profile_likelihood.py:38-132 plus the d/d rho extension.
 
-Layout: global padded size npad = NB * nb; block (i, j) lives on process (i mod P_r, j mod P_c); each rank stores its
-blocks as one dense local matrix (local block rows x local block cols, row-major). K is generated directly in this
-layout (every rank evaluates only its own tiles, csrc/gp_matern.cu `gp_matern_cross`).
+Layout (B200-first: NVSwitch moves a 400 MB panel in about a millisecond and every GPU has 180 GB, so the factor is
+REPLICATED while the work is partitioned):
+  * block size nb, NB = ceil(n / nb) block rows / columns, identity padding to npad = NB nb;
+  * block-cyclic ownership on a 1 x P process grid (the P_r = 1 case of the 2-D layout) with boustrophedon ("snake")
+    order: block column j belongs to rank j mod P on even rounds and P - 1 - (j mod P) on odd ones, so that every pair of
+    rounds hands each rank the same amount of trailing-update work; K + eta I is generated directly in this layout;
+  * every finished panel k (the diagonal block L_kk, the block column below it and inv(L_kk)) is broadcast ONCE to all
+    ranks and KEPT: after the factorisation each rank holds the whole factor L (n^2/2 doubles, 40 GB at n = 100 000).
 
-Right-looking factorisation, per block column k:
-  1. the owner of (k, k) factors the nb x nb diagonal block and inverts its factor (gp_potrf_f64 + gp_trtri_f64),
-  2. inv(L_kk) is broadcast down process column k mod P_c; those ranks form their panel blocks L_ik = A_ik inv(L_kk)^T
-     (DMMA GEMM),
-  3. each process row's stack of panel blocks is broadcast to every rank (P_r broadcasts of (n-k nb)/P_r x nb),
-  4. every rank updates its local trailing blocks A_ij -= L_ik L_jk^T, i >= j > k (one DMMA GEMM per local block column).
-log det = 2 sum log diag(L_kk) (all-reduce); solves use the stored inv(L_kk) blocks with one small all-reduce and one
-broadcast per block step (right-hand sides are replicated).
+Factorisation (right-looking, look-ahead 1): the owner of block column k+1 applies panel k to that column first, factors
+its diagonal block (gp_potrf_f64 + gp_trtri_f64), forms the panel with one DMMA GEMM and broadcasts it on a high-priority
+side stream while every rank - the owner included - still applies panel k to its other columns on the main stream. The
+broadcast of panel k+1 therefore overlaps trailing update k; nothing on the main stream ever waits for NCCL except the
+first use of a panel.
 
-The compute primitives are injected through `ops` (GpuOps = libgpgp kernels). tests/ inject a NumPy implementation to
-exercise the distributed algorithm on CPU with the gloo backend; the product has no CPU path.
+Gradient (no further panel traffic): with L replicated, the rows of W = inv(L) are independent (W_i L = e_i^T), so block
+ROW i of W belongs to rank snake(i) and is obtained by a block back-substitution from the right made of two DMMA GEMMs
+per block column (the staircase of zeros is skipped with per-row-tile k ranges, gp_dgemm_ktab_f64). Then
+    tr Kn^-1      = ||W||_F^2                       (local sums, one all-reduce)
+    tr Kn^-1 dK   = <W^T W, dK> = sum_ranks <X_r^T X_r, dK>,  X_r = this rank's rows of W:
+                    block column by block column, X_r^T X_r[:, J] is one TN DMMA GEMM and dK/drho[:, J] is regenerated
+                    from the points (never stored), reduced at once by a weighted Frobenius inner product;
+    S = Kn^-1 [X z] by block substitution on the replicated factor (local, identical on every rank),
+    G = R^T S, H = S^T S, Q = S^T dK S (dK S regenerated on the fly) -> the host algebra of _likelihood/_fused.py.
+Flops per rank: (n^3/3 + n^3/3 + n^3/3) / P, the same n^3 as the single-GPU evaluator.
+
+The compute primitives are injected through `ops` (GpuOps = libgpgp kernels through the C ABI). tests/ inject a NumPy
+implementation to exercise the distributed algorithm on CPU with the gloo backend; the product has no CPU path.
 """
 
+import contextlib
 import ctypes
+import time
 
 import numpy
 
 from . import _device as dev
 from ._device import lib, check
 
-__all__ = ['process_grid', 'GpuOps', 'BlockCyclicCholesky']
+__all__ = ['process_grid', 'snake_owner', 'GpuOps', 'BlockCyclicCholesky']
 
 
 def process_grid(world):
-    """P_r x P_c with P_r <= P_c, as square as possible (1x2, 2x2, 2x4, ...)."""
-    pr = int(numpy.floor(numpy.sqrt(world)))
-    while world % pr:
-        pr -= 1
-    return pr, world // pr
+    """(P_r, P_c) of the block-cyclic layout: 1 x world. The factor is replicated by the panel broadcasts (every rank needs
+    every panel for the gradient phase), so a taller grid would not save traffic; the snake order balances the columns."""
+    return 1, int(world)
+
+
+def snake_owner(j, P):
+    """Owner of block index j on P ranks in boustrophedon order."""
+    r, pos = divmod(int(j), int(P))
+    return pos if r % 2 == 0 else P - 1 - pos
 
 
 def _p(t):
@@ -42,13 +63,16 @@ def _p(t):
 
 
 class GpuOps(object):
-    """Primitives on torch float64 CUDA tensors, all through the libgpgp C ABI (views: unit column stride)."""
+    """Primitives on torch float64 CUDA tensors (row-major views with unit column stride), all through the libgpgp C ABI.
+    torch owns buffers, streams and events only."""
 
     def __init__(self):
         self.torch = dev.require_cuda()
         self.device = self.torch.device('cuda', self.torch.cuda.current_device())
         self._ws = {}
+        self._rect_ws = None
 
+    # ---- buffers ------------------------------------------------------------------------------------------------
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
 
@@ -59,51 +83,109 @@ class GpuOps(object):
         t = self.torch.from_numpy(numpy.ascontiguousarray(a))
         return t.to(self.device) if dtype is None else t.to(self.device, dtype=dtype)
 
+    def int_tensor(self, values):
+        return self.torch.tensor(list(values), dtype=self.torch.int32, device=self.device)
+
     def to_host(self, t):
         return t.cpu().numpy()
 
+    # ---- streams / events ------------------------------------------------------------------------------------------
+    def new_stream(self):
+        return self.torch.cuda.Stream(priority=-1)
+
+    def use(self, stream):
+        return self.torch.cuda.stream(stream)
+
+    def event(self, stream=None, timing=False):
+        e = self.torch.cuda.Event(enable_timing=timing)
+        e.record(stream if stream is not None else self.torch.cuda.current_stream())
+        return e
+
+    def wait(self, stream, event):
+        (stream if stream is not None else self.torch.cuda.current_stream()).wait_event(event)
+
+    def elapsed_s(self, e0, e1):
+        return e0.elapsed_time(e1) * 1e-3
+
+    def synchronize(self):
+        self.torch.cuda.synchronize()
+
+    # ---- kernels ---------------------------------------------------------------------------------------------------
     def generate(self, prow, pcol, rg, cg, n, scale, nu, eta, out):
         check(lib.gp_matern_cross(_p(prow), _p(pcol), _p(rg), _p(cg), out.shape[0], out.shape[1], n, prow.shape[1],
                                   dev.host_ptr(scale), float(nu), float(eta), _p(out), out.stride(0), dev.stream_ptr()),
               'gp_matern_cross')
 
-    def potrf_inv(self, D, nvalid):
-        """D (nb x nb contiguous): lower Cholesky in place; returns inv(L) (nb x nb, zero above the diagonal)."""
+    def generate_dk(self, prow, pcol, rg, cg, n, scale, nu, out):
+        check(lib.gp_matern_cross_dk(_p(prow), _p(pcol), _p(rg), _p(cg), out.shape[0], out.shape[1], n, prow.shape[1],
+                                     dev.host_ptr(scale), float(nu), _p(out), out.stride(0), dev.stream_ptr()),
+              'gp_matern_cross_dk')
+
+    def potrf_inv(self, D, nvalid, Linv):
+        """D (nb x nb contiguous): lower Cholesky in place; Linv (nb x nb contiguous) <- inv(L), zero above the diagonal.
+        Returns a device int tensor with the LAPACK-style info (no host synchronisation)."""
         torch = self.torch
         nb = D.shape[0]
         if nb not in self._ws:
             self._ws[nb] = (torch.empty(lib.gp_potrf_workspace_bytes(nb) // 8, dtype=torch.float64, device=self.device),
-                            torch.empty(lib.gp_potri_workspace_bytes(nb) // 8 + 8, dtype=torch.float64, device=self.device),
-                            torch.zeros(1, dtype=torch.int32, device=self.device))
-        pws, tws, info = self._ws[nb]
+                            torch.empty(lib.gp_potri_workspace_bytes(nb) // 8 + 8, dtype=torch.float64, device=self.device))
+        pws, tws = self._ws[nb]
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
         s = dev.stream_ptr()
         check(lib.gp_potrf_f64(_p(D), int(nvalid), nb, _p(info), _p(pws), s), 'gp_potrf_f64')
-        W = torch.zeros((nb, nb), dtype=torch.float64, device=self.device)
-        check(lib.gp_trtri_f64(_p(D), _p(W), nb, _p(pws), _p(tws), s), 'gp_trtri_f64')
-        bad = int(info.item())
-        return W, bad
+        Linv.zero_()
+        check(lib.gp_trtri_f64(_p(D), _p(Linv), nb, _p(pws), _p(tws), s), 'gp_trtri_f64')
+        return info
 
-    def gemm_nt(self, C, A, B, alpha, beta):
-        """C = beta C + alpha A B^T on (row-stride) views."""
-        check(lib.gp_dgemm_f64(0, 0, _p(C), C.stride(0), _p(A), A.stride(0), _p(B), B.stride(0), C.shape[0], C.shape[1],
-                               A.shape[1], float(alpha), float(beta), 0, 0, dev.stream_ptr()), 'gp_dgemm_f64')
+    def gemm(self, C, A, B, alpha, beta, at=0, bt=0, kbeg=None, kend=None):
+        """C = beta C + alpha op(A) op(B); at = 0: A is the (M x K) view, at = 1: A is the (K x M) view; bt = 0: B is the
+        (N x K) view, bt = 1: B is the (K x N) view. kbeg / kend: per-128-row-tile k ranges (device int32)."""
+        M, N = C.shape
+        K = A.shape[1] if at == 0 else A.shape[0]
+        if kbeg is None and kend is None:
+            check(lib.gp_dgemm_f64(at, bt, _p(C), C.stride(0), _p(A), A.stride(0), _p(B), B.stride(0), M, N, K, float(alpha),
+                                   float(beta), 0, 0, dev.stream_ptr()), 'gp_dgemm_f64')
+        else:
+            check(lib.gp_dgemm_ktab_f64(at, bt, _p(C), C.stride(0), _p(A), A.stride(0), _p(B), B.stride(0), M, N, K,
+                                        float(alpha), float(beta), _p(kbeg) if kbeg is not None else None,
+                                        _p(kend) if kend is not None else None, dev.stream_ptr()), 'gp_dgemm_ktab_f64')
 
-    def logdet_chol(self, D):
-        out = self.empty(1)
-        check(lib.gp_logdet_from_chol(_p(D), D.shape[0], D.shape[0], _p(out), dev.stream_ptr()), 'gp_logdet_from_chol')
-        return float(out.item())
+    def logdet_chol(self, D, nvalid, out):
+        """out (device, 1 double) <- 2 sum_{i < nvalid} log D_ii for the lower factor D (row stride D.stride(0))"""
+        check(lib.gp_logdet_from_chol(_p(D), int(nvalid), D.stride(0), _p(out), dev.stream_ptr()), 'gp_logdet_from_chol')
 
-    # skinny (n x p) products of the distributed substitution: library GEMV-class calls, O(n^2 p) flop in total
-    def matmul(self, A, X):
-        return self.torch.matmul(A, X)
+    def _rect_workspace(self, M, N, p):
+        need = int(lib.gp_rect_workspace_bytes(M, N, p)) // 8 + 8
+        if self._rect_ws is None or self._rect_ws.numel() < need:
+            self._rect_ws = self.empty(need)
+        return self._rect_ws
 
-    def matmul_t(self, A, X):
-        return self.torch.matmul(A.transpose(0, 1), X)
+    def rect_apply(self, X, R, Y, alpha=1.0, beta=0.0):
+        """Y = alpha X R + beta Y  (X: M x N slab, R: N x p, p <= 16)"""
+        check(lib.gp_rect_apply(_p(X), X.shape[0], X.shape[1], X.stride(0), _p(R), R.shape[1], R.stride(0), _p(Y), Y.stride(0),
+                                float(alpha), float(beta), dev.stream_ptr()), 'gp_rect_apply')
+
+    def rect_apply_t(self, X, Y, S, alpha=1.0, beta=0.0):
+        """S = alpha X^T Y + beta S  (X: M x N slab, Y: M x p, S: N x p)"""
+        ws = self._rect_workspace(X.shape[0], X.shape[1], Y.shape[1])
+        check(lib.gp_rect_apply_t(_p(X), X.shape[0], X.shape[1], X.stride(0), _p(Y), Y.shape[1], Y.stride(0), _p(S), S.stride(0),
+                                  float(alpha), float(beta), _p(ws), dev.stream_ptr()), 'gp_rect_apply_t')
+
+    def pair_dot(self, A, B, rows_w1, w_rest, accum):
+        """accum[0] += sum_{r < rows_w1} <A_r, B_r> + w_rest sum_{r >= rows_w1} <A_r, B_r>"""
+        ws = self._rect_workspace(1, 1, 1)
+        check(lib.gp_pair_dot(_p(A), A.stride(0), _p(B), B.stride(0), A.shape[0], A.shape[1], int(rows_w1), float(w_rest),
+                              _p(accum), _p(ws), dev.stream_ptr()), 'gp_pair_dot')
+
+    def dk_apply(self, points, n, scale, nu, S, V):
+        """V = dK/drho S (dK regenerated from the points)"""
+        check(lib.gp_dk_apply(_p(points), n, points.shape[1], dev.host_ptr(scale), float(nu), _p(S), S.shape[1], S.stride(0),
+                              _p(V), dev.stream_ptr()), 'gp_dk_apply')
 
 
 class BlockCyclicCholesky(object):
 
-    def __init__(self, points, correlation_scale, nu, nb=1024, ops=None, dist=None):
+    def __init__(self, points, correlation_scale, nu, nb=512, ops=None, dist=None):
         if nb % 128:
             raise ValueError('nb should be a multiple of 128')
         if dist is None:
@@ -113,7 +195,6 @@ class BlockCyclicCholesky(object):
         self.rank = dist.get_rank() if self.distributed else 0
         self.world = dist.get_world_size() if self.distributed else 1
         self.P_r, self.P_c = process_grid(self.world)
-        self.r, self.c = divmod(self.rank, self.P_c)
         self.ops = ops if ops is not None else GpuOps()
         self.points = numpy.ascontiguousarray(points, dtype=numpy.float64)
         self.n, self.d = self.points.shape
@@ -124,25 +205,32 @@ class BlockCyclicCholesky(object):
         self.nb = int(nb)
         self.NB = (self.n + nb - 1) // nb
         self.npad = self.NB * nb
-        self.I_loc = [i for i in range(self.NB) if i % self.P_r == self.r]
-        self.J_loc = [j for j in range(self.NB) if j % self.P_c == self.c]
-        self.col_groups = None
-        if self.distributed and self.world > 1:
-            # one group per process column (for inv(L_kk)); every rank must create every group
-            self.col_groups = [dist.new_group([rr * self.P_c + cc for rr in range(self.P_r)]) for cc in range(self.P_c)]
+        P = self.world
+        self.J_loc = [j for j in range(self.NB) if snake_owner(j, P) == self.rank]     # my block columns of K / rows of W
         self.Aloc = None
-        self.Linv = {}
+        self.panels = {}         # k -> ((NB - k + 1) nb x nb): L[k nb:, k-th block column] followed by inv(L_kk)
+        self.X = None            # my block rows of W = inv(L): (len(J_loc) nb) x npad, zero right of the staircase
+        self.eta = None
+        self.stats = {}
         self.bytes_received = 0
+        self._pts_dev = None
 
     # ---- helpers -------------------------------------------------------------------------------------------------
     def _gidx(self, blocks):
         nb = self.nb
         return numpy.concatenate([numpy.arange(b * nb, (b + 1) * nb) for b in blocks]).astype(numpy.int32) \
-            if blocks else numpy.zeros(0, dtype=numpy.int32)
+            if len(blocks) else numpy.zeros(0, dtype=numpy.int32)
 
-    def _bcast(self, t, src, group=None):
+    def _padded_points(self):
+        if self._pts_dev is None:
+            pad = numpy.zeros((self.npad, self.d))
+            pad[:self.n] = self.points
+            self._pts_dev = self.ops.from_host(pad)
+        return self._pts_dev
+
+    def _bcast(self, t, src):
         if self.world > 1:
-            self.dist.broadcast(t, src=src, group=group)
+            self.dist.broadcast(t, src=src)
             if self.rank != src:
                 self.bytes_received += t.numel() * 8
 
@@ -150,169 +238,262 @@ class BlockCyclicCholesky(object):
         if self.world > 1:
             self.dist.all_reduce(t)
 
-    def rows_after(self, k, P, me):
-        """number of block indices i > k with i mod P == me"""
-        return len([i for i in range(k + 1, self.NB) if i % P == me])
+    def _nvalid(self, k):
+        return max(0, min(self.nb, self.n - k * self.nb))
 
     # ---- generation in block-cyclic layout ---------------------------------------------------------------------------
     def generate(self, eta):
-        ops, nb = self.ops, self.nb
-        rg, cg = self._gidx(self.I_loc), self._gidx(self.J_loc)
+        """Aloc (npad x len(J_loc) nb) <- my block columns of K + eta I (identity padding)."""
+        ops = self.ops
+        pts = self._padded_points()
+        cg = self._gidx(self.J_loc)
+        rg = numpy.arange(self.npad, dtype=numpy.int32)
+        self.Aloc = ops.empty((self.npad, len(cg)))
+        if len(cg):
+            ops.generate(pts, ops.from_host(self._padded_host()[cg]), ops.from_host(rg), ops.from_host(cg), self.n, self.scale,
+                         self.nu, eta, self.Aloc)
+
+    def _padded_host(self):
         pad = numpy.zeros((self.npad, self.d))
         pad[:self.n] = self.points
-        self.Aloc = ops.empty((len(rg), len(cg)))
-        if len(rg) and len(cg):
-            ops.generate(ops.from_host(pad[rg]), ops.from_host(pad[cg]), ops.from_host(rg), ops.from_host(cg), self.n,
-                         self.scale, self.nu, eta, self.Aloc)
+        return pad
 
     # ---- factorisation ---------------------------------------------------------------------------------------------
     def factor(self, eta):
-        """Generates K + eta I in place and factors it. Raises numpy.linalg.LinAlgError (on every rank) if not PD."""
+        """Generates K + eta I in place and factors it; the panels stay replicated on every rank. Raises
+        numpy.linalg.LinAlgError (on every rank) if the matrix is not positive definite."""
+        ops, nb, NB, P = self.ops, self.nb, self.NB, self.world
+        ops.synchronize()
+        t0 = time.perf_counter()
         self.generate(eta)
-        ops, nb, NB, P_r, P_c = self.ops, self.nb, self.NB, self.P_r, self.P_c
         A = self.Aloc
-        self.Linv = {}
+        self.panels, self.X = {}, None
         self.bytes_received = 0
         bad = ops.zeros(1)
-        bufs = [None] * P_r
+        infos = []
+        lcol = {j: q for q, j in enumerate(self.J_loc)}
+        side = ops.new_stream()
+        comm = []                    # (event before, event after) of every broadcast, on the side stream
+
+        def apply_panel(k, j):
+            """block column j (mine) -= panel_k rows >= j times (the j-th block of panel_k)^T"""
+            msg = self.panels[k]
+            q = lcol[j]
+            C = A[j * nb:, q * nb:(q + 1) * nb]
+            ops.gemm(C, msg[(j - k) * nb:(NB - k) * nb], msg[(j - k) * nb:(j - k + 1) * nb], -1.0, 1.0)
+
+        def prepare_panel(k):
+            """on the side stream: the owner factors the diagonal block and forms the panel; everybody joins the broadcast"""
+            owner = snake_owner(k, P)
+            msg = ops.empty(((NB - k + 1) * nb, nb))
+            if self.rank == owner:
+                q = lcol[k]
+                col = A[k * nb:, q * nb:(q + 1) * nb]
+                D = msg[:nb]
+                D.copy_(col[:nb])
+                Linv = msg[(NB - k) * nb:]
+                infos.append((k, ops.potrf_inv(D, self._nvalid(k), Linv)))
+                if NB - k > 1:
+                    ops.gemm(msg[nb:(NB - k) * nb], col[nb:], Linv, 1.0, 0.0)      # L_ik = A_ik inv(L_kk)^T
+            e0 = ops.event(timing=True) if self.world > 1 else None
+            self._bcast(msg, owner)
+            if e0 is not None:
+                comm.append((e0, ops.event(timing=True)))
+            self.panels[k] = msg
+
+        main_done = None           # event: trailing update of the previous step enqueued on the main stream
+        with ops.use(side):
+            ops.wait(side, ops.event())      # the side stream starts after the generation
+            prepare_panel(0)
+            ready = ops.event()
         for k in range(NB):
-            pr, pc = k % P_r, k % P_c
-            owner = pr * P_c + pc
-            Linv = None
-            if self.c == pc:
-                if self.rank == owner:
-                    li, lj = self.I_loc.index(k), self.J_loc.index(k)
-                    blk = A[li * nb:(li + 1) * nb, lj * nb:(lj + 1) * nb]
-                    D = blk.contiguous()
-                    nvalid = max(0, min(nb, self.n - k * nb))
-                    Linv, info = ops.potrf_inv(D, nvalid)
-                    blk.copy_(D)
-                    self.Linv[k] = (Linv, D)
-                    if info:
-                        bad += float(k * nb + info)
-                else:
-                    Linv = ops.empty((nb, nb))
-                self._bcast(Linv, owner, self.col_groups[pc] if self.col_groups else None)
-            # panel blocks below the diagonal, stacked per process row
-            for rr in range(P_r):
-                cnt = self.rows_after(k, P_r, rr)
-                if cnt == 0:
-                    bufs[rr] = None
-                    continue
-                root = rr * P_c + pc
-                buf = ops.empty((cnt * nb, nb))
-                if self.rank == root:
-                    l0 = len(self.I_loc) - cnt
-                    lj = self.J_loc.index(k)
-                    panel = A[l0 * nb:, lj * nb:(lj + 1) * nb]
-                    ops.gemm_nt(buf, panel, Linv, 1.0, 0.0)
-                    panel.copy_(buf)
-                self._bcast(buf, root)
-                bufs[rr] = buf
-            # trailing update of the local blocks (i >= j > k)
-            mine = bufs[self.r]
-            if mine is not None:
-                my_rows = [i for i in self.I_loc if i > k]
-                for lj, j in enumerate(self.J_loc):
-                    if j <= k:
-                        continue
-                    rows = [i for i in my_rows if i >= j]
-                    if not rows:
-                        continue
-                    skip = len(my_rows) - len(rows)
-                    src = bufs[j % P_r]
-                    pos = len([i for i in range(k + 1, j) if i % P_r == j % P_r])
-                    Lj = src[pos * nb:(pos + 1) * nb]
-                    l0 = len(self.I_loc) - len(rows)
-                    C = A[l0 * nb:, lj * nb:(lj + 1) * nb]
-                    ops.gemm_nt(C, mine[skip * nb:], Lj, -1.0, 1.0)
+            ops.wait(None, ready)                                   # main stream: panel k has arrived
+            if k + 1 < NB:
+                with ops.use(side):
+                    if main_done is not None:
+                        ops.wait(side, main_done)                   # column k+1 has all its updates from panels < k
+                    if (k + 1) in lcol:
+                        apply_panel(k, k + 1)
+                    prepare_panel(k + 1)
+                    ready = ops.event()
+            for j in self.J_loc:
+                if j > k + 1:
+                    apply_panel(k, j)
+            main_done = ops.event()
+        for k, info in infos:
+            bad += (info.to(bad.dtype) > 0) * float(1 + k)
         self._allreduce(bad)
-        info = float(ops.to_host(bad)[0])
-        if info != 0.0:
-            raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite (block-cyclic potrf).' % eta)
+        ops.synchronize()
+        self.stats = {'factor_s': time.perf_counter() - t0, 'bytes_received': self.bytes_received,
+                      'comm_s': sum(ops.elapsed_s(a, b) for a, b in comm) if comm else 0.0}
+        if float(ops.to_host(bad)[0]) != 0.0:
+            raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite (distributed potrf).' % eta)
+        self.Aloc = None
         self.eta = float(eta)
 
     def logdet(self):
-        s = self.ops.zeros(1)
-        for k, (Linv, D) in self.Linv.items():
-            nvalid = max(0, min(self.nb, self.n - k * self.nb))
-            if nvalid == self.nb:
-                s += self.ops.logdet_chol(D)
-            elif nvalid > 0:
-                s += 2.0 * float(numpy.sum(numpy.log(numpy.diag(self.ops.to_host(D))[:nvalid])))
-        self._allreduce(s)
-        return float(self.ops.to_host(s)[0])
+        """log det (K + eta I) = 2 sum log diag(L) from the replicated diagonal blocks (local, identical on every rank)."""
+        ops = self.ops
+        acc = ops.zeros(self.NB)
+        for k in range(self.NB):
+            nv = self._nvalid(k)
+            if nv > 0:
+                ops.logdet_chol(self.panels[k][:self.nb], nv, acc[k:k + 1])
+        return float(ops.to_host(acc).sum())
 
-    # ---- solves with replicated right-hand sides -------------------------------------------------------------------
+    # ---- solves on the replicated factor (local; identical on every rank) ----------------------------------------------
+    def solve_dev(self, Bdev):
+        """(K + eta I)^-1 B for a device block (npad x p, p <= 16), in place: block substitution with the kept panels."""
+        ops, nb, NB = self.ops, self.nb, self.NB
+        p = Bdev.shape[1]
+        t = ops.empty((nb, p))
+        for k in range(NB):                                           # L y = b
+            msg = self.panels[k]
+            Linv = msg[(NB - k) * nb:]
+            bk = Bdev[k * nb:(k + 1) * nb]
+            ops.rect_apply(Linv, bk, t)
+            bk.copy_(t)
+            if k + 1 < NB:
+                ops.rect_apply(msg[nb:(NB - k) * nb], bk, Bdev[(k + 1) * nb:], alpha=-1.0, beta=1.0)
+        for k in range(NB - 1, -1, -1):                               # L^T x = y
+            msg = self.panels[k]
+            Linv = msg[(NB - k) * nb:]
+            bk = Bdev[k * nb:(k + 1) * nb]
+            if k + 1 < NB:
+                ops.rect_apply_t(msg[nb:(NB - k) * nb], Bdev[(k + 1) * nb:], bk, alpha=-1.0, beta=1.0)
+            ops.rect_apply_t(Linv, bk, t)
+            bk.copy_(t)
+        return Bdev
+
     def solve(self, R):
         """(K + eta I)^-1 R for a host array R (n,) or (n, p); returns a host array (identical on every rank)."""
-        ops, nb, NB, P_r, P_c = self.ops, self.nb, self.NB, self.P_r, self.P_c
         R = numpy.asarray(R, dtype=numpy.float64)
         vec = (R.ndim == 1)
         R2 = R.reshape(self.n, -1)
-        p = R2.shape[1]
-        Bp = numpy.zeros((self.npad, p))
-        Bp[:self.n] = R2
-        b = ops.from_host(Bp)
-        A = self.Aloc
-        # forward: L y = b
-        acc = ops.zeros((self.npad, p))
-        y = ops.zeros((self.npad, p))
-        for k in range(NB):
-            pr, pc = k % P_r, k % P_c
-            owner = pr * P_c + pc
-            t = acc[k * nb:(k + 1) * nb].clone()
-            self._allreduce(t)
-            yk = ops.empty((nb, p))
-            if self.rank == owner:
-                yk.copy_(ops.matmul(self.Linv[k][0], b[k * nb:(k + 1) * nb] - t))
-            self._bcast(yk, owner)
-            y[k * nb:(k + 1) * nb] = yk
-            if self.c == pc:
-                rows = [i for i in self.I_loc if i > k]
-                if rows:
-                    l0 = len(self.I_loc) - len(rows)
-                    lj = self.J_loc.index(k)
-                    upd = ops.matmul(A[l0 * nb:, lj * nb:(lj + 1) * nb], yk)
-                    for q, i in enumerate(rows):
-                        acc[i * nb:(i + 1) * nb] += upd[q * nb:(q + 1) * nb]
-        # backward: L^T x = y
-        x = ops.zeros((self.npad, p))
-        for k in range(NB - 1, -1, -1):
-            pr, pc = k % P_r, k % P_c
-            owner = pr * P_c + pc
-            t = ops.zeros((nb, p))
-            if self.c == pc:
-                rows = [i for i in self.I_loc if i > k]
-                if rows:
-                    l0 = len(self.I_loc) - len(rows)
-                    lj = self.J_loc.index(k)
-                    xs = ops.empty((len(rows) * nb, p))
-                    for q, i in enumerate(rows):
-                        xs[q * nb:(q + 1) * nb] = x[i * nb:(i + 1) * nb]
-                    t = ops.matmul_t(A[l0 * nb:, lj * nb:(lj + 1) * nb], xs)
-            t = t.contiguous()
-            self._allreduce(t)
-            xk = ops.empty((nb, p))
-            if self.rank == owner:
-                xk.copy_(ops.matmul_t(self.Linv[k][0], y[k * nb:(k + 1) * nb] - t))
-            self._bcast(xk, owner)
-            x[k * nb:(k + 1) * nb] = xk
-        out = ops.to_host(x)[:self.n]
+        out = numpy.empty_like(R2)
+        for c0 in range(0, R2.shape[1], 16):
+            blk = R2[:, c0:c0 + 16]
+            Bp = numpy.zeros((self.npad, blk.shape[1]))
+            Bp[:self.n] = blk
+            out[:, c0:c0 + 16] = self.ops.to_host(self.solve_dev(self.ops.from_host(Bp)))[:self.n]
         return out[:, 0] if vec else out
 
-    # ---- profile log-likelihood at (sigma_hat(eta), eta) from the distributed factor ------------------------------------
+    # ---- rows of inv(L) ----------------------------------------------------------------------------------------------
+    def inverse_rows(self):
+        """X <- my block rows of W = inv(L) (block back-substitution from the right on the replicated factor)."""
+        if self.X is not None:
+            return self.X
+        ops, nb, NB = self.ops, self.nb, self.NB
+        I = self.J_loc
+        nq = len(I)
+        X = ops.zeros((max(nq, 1) * nb, self.npad))
+        T = ops.empty((max(nq, 1) * nb, nb))
+        tiles = nb // 128
+        for k in range(NB - 1, -1, -1):
+            msg = self.panels[k]
+            Linv = msg[(NB - k) * nb:]
+            q0 = next((q for q, i in enumerate(I) if i >= k), nq)        # first local row with i_q >= k
+            if q0 < nq and I[q0] == k:
+                X[q0 * nb:(q0 + 1) * nb, k * nb:(k + 1) * nb].copy_(Linv)
+                q0 += 1
+            if q0 >= nq:
+                continue
+            rows = slice(q0 * nb, nq * nb)
+            # T = X[rows, columns > k] L[rows > k, k]; row block q only has columns <= i_q
+            kend = ops.int_tensor([(I[q] - k) * nb for q in range(q0, nq) for _ in range(tiles)])
+            ops.gemm(T[rows], X[rows, (k + 1) * nb:], msg[nb:(NB - k) * nb], 1.0, 0.0, at=0, bt=1, kend=kend)
+            ops.gemm(X[rows, k * nb:(k + 1) * nb], T[rows], Linv, -1.0, 0.0, at=0, bt=1)
+        self.X = X
+        return X
+
+    def inverse_traces(self, with_dk=True):
+        """(tr Kn^-1, tr Kn^-1 dK/drho) - all-reduced, identical on every rank."""
+        ops, nb, NB, npad = self.ops, self.nb, self.NB, self.npad
+        X = self.inverse_rows()
+        I = self.J_loc
+        nq = len(I)
+        acc = ops.zeros(2)
+        if nq:
+            ops.pair_dot(X[:nq * nb], X[:nq * nb], nq * nb, 1.0, acc[0:1])
+        if with_dk and nq:
+            pts = self._padded_points()
+            host = self._padded_host()
+            C = ops.empty((npad, nb))
+            D = ops.empty((npad, nb))
+            tiles = nb // 128
+            for j in range(NB):
+                q0 = next((q for q, i in enumerate(I) if i >= j), nq)
+                if q0 >= nq:
+                    break
+                rows = slice(q0 * nb, nq * nb)
+                M = npad - j * nb
+                # C[J', J] = sum over my rows i >= j' of W[i, J']^T W[i, J]   (J' >= J): TN product with a staircase k start
+                kbeg = ops.int_tensor([(next((q for q in range(q0, nq) if I[q] >= jp), nq) - q0) * nb
+                                       for jp in range(j, NB) for _ in range(tiles)])
+                ops.gemm(C[:M], X[rows, j * nb:], X[rows, j * nb:(j + 1) * nb], 1.0, 0.0, at=1, bt=1, kbeg=kbeg)
+                cg = self._gidx([j])
+                rg = numpy.arange(j * nb, npad, dtype=numpy.int32)
+                ops.generate_dk(pts[j * nb:], ops.from_host(host[cg]), ops.from_host(rg), ops.from_host(cg), self.n, self.scale,
+                                self.nu, D[:M])
+                ops.pair_dot(C[:M], D[:M], nb, 2.0, acc[1:2])          # the diagonal block once, the blocks below twice
+        self._allreduce(acc)
+        out = ops.to_host(acc)
+        # the identity padding block of L inverts to itself: its npad - n unit entries are not part of tr Kn^-1
+        return float(out[0]) - (npad - self.n), float(out[1])
+
+    # ---- likelihood ----------------------------------------------------------------------------------------------------
+    def _fused_out(self, z, X, with_gradient):
+        """out[] in the layout of gp_loglik_dense (include/gpgp.h) for the host algebra of _likelihood/_fused.py"""
+        ops = self.ops
+        n, m = X.shape
+        p = m + 1
+        R = numpy.zeros((self.npad, p))
+        R[:n, :m] = X
+        R[:n, m] = z
+        Rd = ops.from_host(R)
+        ops.synchronize()
+        t0 = time.perf_counter()
+        S = self.solve_dev(Rd.clone())
+        Sh, Rh = ops.to_host(S), R
+        out = numpy.zeros(8 + 4 * p * p)
+        out[0] = self.logdet()
+        out[8:8 + p * p] = (Rh.T @ Sh).ravel()
+        out[8 + p * p:8 + 2 * p * p] = (Sh.T @ Sh).ravel()
+        if with_gradient:
+            V = ops.zeros((self.npad, p))
+            ops.dk_apply(ops.from_host(self.points), n, self.scale, self.nu, S, V)
+            out[8 + 2 * p * p:8 + 3 * p * p] = (Sh.T @ ops.to_host(V)).ravel()
+        ops.synchronize()
+        self.stats['solve_s'] = time.perf_counter() - t0
+        if with_gradient:
+            t0 = time.perf_counter()
+            out[1], out[3] = self.inverse_traces(with_dk=True)
+            ops.synchronize()
+            self.stats['traces_s'] = time.perf_counter() - t0
+        return out
+
     def profile_log_likelihood(self, z, X, eta):
         """l^(sigma_hat, eta) exactly as ProfileLikelihood.log_likelihood (reference _profile_likelihood.py:38-85)
         evaluated at sigma_hat^2 = z^T M z / (n - m); returns (l^, sigma_hat)."""
+        from ._likelihood._fused import FusedQuantities
         self.factor(eta)
         n, m = X.shape
-        R = numpy.c_[X, z]
-        S = self.solve(R)
-        G = R.T @ S
-        B = G[:m, :m]
-        beta = numpy.linalg.solve(B, G[:m, m])
-        zMz = G[m, m] - G[:m, m] @ beta
-        sigma2 = zMz / (n - m)
-        lp = -0.5 * (n - m) * numpy.log(sigma2) - 0.5 * self.logdet() - 0.5 * numpy.log(numpy.linalg.det(B)) - 0.5 * (n - m)
+        q = FusedQuantities(self._fused_out(z, X, False), n, m, float(eta), 0)
+        sigma2 = q.zMz / (n - m)
+        lp = -0.5 * (n - m) * numpy.log(sigma2) - 0.5 * q.logdet_Kn - 0.5 * numpy.log(numpy.linalg.det(q.B)) - 0.5 * (n - m)
         return float(lp), float(numpy.sqrt(sigma2))
+
+    def profile_log_likelihood_and_gradient(self, z, X, eta):
+        """(l^, d l^/d eta, d l^/d rho) at one (rho, eta) - the unit of BASELINE.json's metric - for n beyond one GPU
+        (reference formulas: _profile_likelihood.py:38-132; d/d rho: SURVEY 8a A10)."""
+        from ._likelihood._fused import FusedQuantities
+        from ._likelihood._profile_likelihood import ProfileLikelihood
+        self.factor(eta)
+        n, m = X.shape
+        q = FusedQuantities(self._fused_out(z, X, True), n, m, float(eta), 7)
+        return ProfileLikelihood._gradient_from(q, X.shape, True)
+
+
+@contextlib.contextmanager
+def _null():
+    yield

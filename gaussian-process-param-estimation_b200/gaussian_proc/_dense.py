@@ -16,11 +16,12 @@ import numpy
 from . import _device as dev
 from ._device import lib, check
 
-__all__ = ['DeviceCorrelation', 'DenseEngine', 'EigenEngine', 'FLAG_TRACEINV', 'FLAG_INVERSE', 'FLAG_DRHO']
+__all__ = ['DeviceCorrelation', 'DenseEngine', 'EigenEngine', 'FLAG_TRACEINV', 'FLAG_INVERSE', 'FLAG_DRHO', 'FLAG_CUBIC']
 
 FLAG_TRACEINV = 1
 FLAG_INVERSE = 2
 FLAG_DRHO = 4
+FLAG_CUBIC = 8      # third moments T3 = R^T Kn^-3 R (Hessian, second eta-derivative)
 MAX_RHS = 16
 
 
@@ -250,9 +251,8 @@ class EigenEngine(object):
         self._kernel_id = None
 
     def _projected_rhs(self, R_dev):
-        key = R_dev.data_ptr()
-        if self._a is None or self._a[0] != key:
-            self._a = (key, dev.torch.matmul(self.V.t(), R_dev[:self.n]))
+        if self._a is None or self._a[0] is not R_dev:      # the tensor itself is kept: its address cannot be reused
+            self._a = (R_dev, dev.torch.matmul(self.V.t(), R_dev[:self.n]))
         return self._a[1]
 
     def _projected_dK(self):
@@ -308,4 +308,6 @@ class EigenEngine(object):
             C, Cdiag = self._projected_dK()
             out[3] = (Cdiag * d).sum()
             out[8 + 2 * p * p:8 + 3 * p * p] = torch.matmul(da.t(), torch.matmul(C, da)).reshape(-1)
+        if flags & FLAG_CUBIC:
+            out[8 + 3 * p * p:8 + 4 * p * p] = torch.matmul(da.t(), da * d[:, None]).reshape(-1)
         return out

@@ -67,6 +67,14 @@ SIGNATURES = {
     'gp_cg_solve': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_dgemm_f64': (_int, [_int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _int, _int,
                             _vp]),
+    'gp_dgemm_ktab_f64': (_int, [_int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _vp, _vp, _vp]),
+    'gp_gemm_set_impl': (_int, [_int]),
+    'gp_matern_cross_dk': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _vp, _i64, _vp]),
+    'gp_rect_apply': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _f64, _f64, _vp]),
+    'gp_rect_workspace_bytes': (_i64, [_i64, _i64, _i64]),
+    'gp_rect_apply_t': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _f64, _f64, _vp, _vp]),
+    'gp_pair_dot': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
+    'gp_dk_apply': (_int, [_vp, _i64, _i64, _vp, _f64, _vp, _i64, _i64, _vp, _vp]),
     'gp_shift_copy': (_int, [_vp, _i64, _i64, _f64, _vp, _vp]),
     'gp_potrf_workspace_bytes': (_i64, [_i64]),
     'gp_potrf_f64': (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
@@ -146,11 +154,9 @@ def host_ptr(a):
 
 
 def host_key(a):
-    """Cheap identity + content fingerprint of a host array used as a cache key for its device copy: object id, shape
-    and 16 sampled entries (an in-place edit of the array between two evaluations is then very likely to be noticed)."""
-    arr = numpy.asarray(a)
-    flat = arr.reshape(-1)
-    if flat.size == 0:
-        return (id(a), arr.shape)
-    idx = numpy.linspace(0, flat.size - 1, num=min(16, flat.size)).astype(numpy.int64)
-    return (id(a), arr.shape, tuple(float(v) for v in flat[idx]))
+    """Content fingerprint of a host array used as the cache key of its device copy (and of Krylov runs started from
+    it): shape, dtype and a BLAKE2b digest of ALL bytes - O(n p), negligible next to an evaluation - so that any in-place
+    edit between two evaluations is noticed (the reference re-reads z and X on every call)."""
+    import hashlib
+    arr = numpy.ascontiguousarray(a)
+    return (arr.shape, arr.dtype.str, hashlib.blake2b(arr.view(numpy.uint8).reshape(-1), digest_size=16).digest())

@@ -13,7 +13,7 @@ formulas follow without touching n-sized data again (M = Kn^-1 - Kn^-1 X (X^T Kn
 import numpy
 
 from .. import _device as dev
-from .._dense import FLAG_TRACEINV, FLAG_INVERSE, FLAG_DRHO
+from .._dense import FLAG_TRACEINV, FLAG_INVERSE, FLAG_DRHO, FLAG_CUBIC
 
 __all__ = ['FusedQuantities', 'evaluate', 'evaluate_async', 'finish']
 
@@ -43,6 +43,24 @@ class FusedQuantities(object):
         self.zMdKMz = float(self.c @ Q @ self.c)
         self.trace_M = self.trace_Kninv - float(numpy.trace(self.Binv @ H[:m, :m]))
         self.trace_MdK = self.trace_Kninv_dK - float(numpy.trace(self.Binv @ Q[:m, :m]))
+        # third moments (flag CUBIC): T3 = R^T Kn^-3 R. With u = M z = S c:  M u = Kn^-1 u - S_X B^-1 (S_X^T u), hence
+        #   z^T M^3 z = c^T T3 c - (H_x c)^T B^-1 (H_x c),   tr M^2 = tr Kn^-2 - 2 tr(B^-1 T3_xx) + tr((B^-1 H_xx)^2)
+        self.zM3z = self.trace_M2 = None
+        if out.shape[0] >= 8 + 4 * p * p and (flags == -1 or (flags >= 0 and (flags & FLAG_CUBIC))):
+            T3 = out[8 + 3 * p * p:8 + 4 * p * p].reshape(p, p)
+            self.T3 = T3
+            hx = H[:m, :] @ self.c
+            self.zM3z = float(self.c @ T3 @ self.c - hx @ self.Binv @ hx)
+            BH = self.Binv @ H[:m, :m]
+            self.trace_M2 = self.trace_Kninv2 - 2.0 * float(numpy.trace(self.Binv @ T3[:m, :m])) + float(numpy.trace(BH @ BH))
+
+    def moments(self):
+        """(t, s): t[k] = tr M^k (k = 1, 2), s[k] = z^T M^k z (k = 1, 2, 3) of the projected precision
+        M = Kn^-1 - Kn^-1 X B^-1 X^T Kn^-1 at this eta (index 0 unused) - what every derivative up to second order is
+        made of (_direct_likelihood.py:163-270, _profile_likelihood.py:138-192)."""
+        if self.zM3z is None:
+            raise ValueError('third moments were not requested (cubic=True)')
+        return (None, self.trace_M, self.trace_M2), (None, self.zMz, self.zM2z, self.zM3z)
 
     def set_trace_Kninv(self, value):
         """tr Kn^-1 supplied from outside (the interpolated trace of a MixedCorrelation(interpolate=True))"""
@@ -62,14 +80,14 @@ def _rhs_device(K_mixed, X, z):
     return Rd
 
 
-def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
+def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False, cubic=False):
     """Enqueues one fused evaluation on torch's current stream and returns a handle without synchronising; several
     evaluations on different streams / operators can be in flight (see sweep.py). Complete it with finish()."""
     n, m = X.shape
     if K_mixed.sparse:
         # sparse K: batched CG solves + skinny Gram matrices + the engine's stochastic traces (synchronous)
-        out = K_mixed.engine.fused(float(eta), X, z, traceinv=traceinv or inverse, drho=drho)
-        return (out, n, m, float(eta), -1, None)
+        out = K_mixed.engine.fused(float(eta), X, z, traceinv=traceinv or inverse or cubic, drho=drho, cubic=cubic)
+        return (out, n, m, float(eta), -1 if cubic else -2, None)
     flags = 0
     if traceinv:
         flags |= FLAG_TRACEINV
@@ -77,6 +95,8 @@ def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False
         flags |= FLAG_INVERSE
     if drho:
         flags |= FLAG_DRHO
+    if cubic:
+        flags |= FLAG_CUBIC | FLAG_INVERSE         # tr Kn^-2 comes with the explicit inverse
     Rd = _rhs_device(K_mixed, X, z)
     if getattr(K_mixed, 'imate_method', None) == 'eigenvalue':
         # one eigendecomposition per matrix, O(n^2 p) per eta (the reference's default method, likelihood.py:41)
@@ -100,12 +120,12 @@ def finish(handle):
     return q
 
 
-def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False):
+def evaluate(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False, cubic=False):
     """Runs the fused evaluator once; raises numpy.linalg.LinAlgError if K + eta I is not positive definite.
     With MixedCorrelation(interpolate=True) the trace of the inverse is the interpolated one
     (mixed_correlation.py:167-170) and the evaluation skips the inverse it would otherwise need for it."""
-    if traceinv and getattr(K_mixed, 'interpolate', False) and not (inverse or drho):
+    if traceinv and getattr(K_mixed, 'interpolate', False) and not (inverse or drho or cubic):
         q = finish(evaluate_async(z, X, K_mixed, eta, traceinv=False))
         q.set_trace_Kninv(K_mixed.traceinv(eta))
         return q
-    return finish(evaluate_async(z, X, K_mixed, eta, traceinv=traceinv, inverse=inverse, drho=drho))
+    return finish(evaluate_async(z, X, K_mixed, eta, traceinv=traceinv, inverse=inverse, drho=drho, cubic=cubic))

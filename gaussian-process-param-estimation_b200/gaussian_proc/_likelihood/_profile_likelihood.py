@@ -70,22 +70,12 @@ class ProfileLikelihood(object):
     # ---- second derivative, valid at the stationary point only (:138-192) --------------------------
     @staticmethod
     def log_likelihood_der2_eta(z, X, K_mixed, eta):
-        Y = K_mixed.solve(eta, X)
-        V = K_mixed.solve(eta, Y)
-        w = K_mixed.solve(eta, z)
+        """d2 l^/d eta2 at a root of d l^/d eta, from the moments t_k = tr M^k, s_k = z^T M^k z of ONE fused evaluation:
+        (n - m) / (2 s_1) * ((t_2 / (n - m) + (t_1 / (n - m))^2) s_1 - 2 s_3)."""
         n, m = X.shape
-        Binv = numpy.linalg.inv(numpy.matmul(X.T, Y))
-        Mz = w - numpy.matmul(Y, numpy.matmul(Binv, numpy.matmul(Y.T, z)))
-        A = numpy.matmul(Binv, numpy.matmul(Y.T, Y))
-        trace_M = K_mixed.traceinv(eta) - numpy.trace(A)
-        trace_C = numpy.trace(numpy.matmul(Binv, numpy.matmul(Y.T, V)))
-        trace_M2 = K_mixed.traceinv(eta, exponent=2) - 2.0 * trace_C + numpy.trace(numpy.matmul(A, A))
-        v = K_mixed.solve(eta, Mz)
-        MMz = v - numpy.matmul(Y, numpy.matmul(Binv, numpy.matmul(Y.T, Mz)))
-        zMz = numpy.dot(z, Mz)
-        zM3z = numpy.dot(Mz, MMz)
-        sigma02 = zMz / (n - m)
-        return (0.5 / sigma02) * ((trace_M2 / (n - m) + (trace_M / (n - m)) ** 2) * zMz - 2.0 * zM3z)
+        t, s = _fused.evaluate(z, X, K_mixed, eta, traceinv=True, cubic=True).moments()
+        nm = float(n - m)
+        return 0.5 * nm / s[1] * ((t[2] / nm + (t[1] / nm) ** 2) * s[1] - 2.0 * s[3])
 
     # ---- Nelder-Mead over (sigma, eta) (:198-238) --------------------------------------------------------------
     @staticmethod
@@ -115,10 +105,22 @@ class ProfileLikelihood(object):
             return numpy.sqrt(numpy.dot(z, z - v) / (n - m))
 
         print('Find root of log likelihood derivative ...')
-        if getattr(K_mixed, 'sparse', False):
-            # the root find asks many eta of this operator: keep the Krylov run of [X z] from the first one on
-            if 'eager_rhs_basis' not in K_mixed.imate_options:
-                K_mixed.engine.opt['eager_rhs_basis'] = True
+        tune = getattr(K_mixed, 'sparse', False) and 'eager_rhs_basis' not in K_mixed.imate_options
+        if tune:
+            # the root find asks many eta of this operator: keep the Krylov run of [X z] from the first one on - for the
+            # duration of this call only (the caller's operator gets its own setting back)
+            saved = K_mixed.engine.opt.get('eager_rhs_basis', False)
+            K_mixed.engine.opt['eager_rhs_basis'] = True
+        try:
+            return ProfileLikelihood._find_der1_zeros(z, X, K_mixed, interval_eta, tol, max_iterations, num_bracket_trials,
+                                                      find_optimal_sigma, find_optimal_sigma0)
+        finally:
+            if tune:
+                K_mixed.engine.opt['eager_rhs_basis'] = saved
+
+    @staticmethod
+    def _find_der1_zeros(z, X, K_mixed, interval_eta, tol, max_iterations, num_bracket_trials, find_optimal_sigma,
+                         find_optimal_sigma0):
         f = partial(ProfileLikelihood.log_likelihood_der1_eta, z, X, K_mixed)
         bracket = [numpy.log10(interval_eta[0]), numpy.log10(interval_eta[1])]
         bracket_found, bracket, bracket_values = find_interval_with_sign_change(f, bracket, num_bracket_trials, args=(), )
@@ -132,23 +134,19 @@ class ProfileLikelihood(object):
             sigma0 = numpy.sqrt(eta) * sigma
             success = True
         else:
-            # no sign change: decide between eta -> 0 and eta -> inf from the curvature at eta = 0 (:352-405)
-            dlp_left, dlp_right = bracket_values[0], bracket_values[1]
-            d2lp_zero = ProfileLikelihood.log_likelihood_der2_eta(z, X, K_mixed, 0.0)
-            print('dL/deta   at eta = %0.2e:\t %0.2f' % (bracket[0], dlp_left))
-            print('dL/deta   at eta = %0.2e:\t %0.16f' % (bracket[1], dlp_right))
-            print('d2L/deta2 at eta = 0.0:\t %0.2f' % d2lp_zero)
-            if (dlp_left > 0) and (dlp_right > 0):
-                eta = 0.0 if d2lp_zero > 0 else numpy.inf
-            elif (dlp_left < 0) and (dlp_right < 0):
-                eta = 0.0 if d2lp_zero < 0 else numpy.inf
-            else:
+            # No sign change on the interval (:352-405): d l^/d eta keeps one sign, so the maximiser sits at an end of
+            # [0, inf). The curvature at eta = 0 tells which: the same sign as the slope means the slope does not turn
+            # around towards zero -> eta = 0, otherwise the extremum is at infinity.
+            slopes = numpy.sign([bracket_values[0], bracket_values[1]])
+            if slopes[0] != slopes[1] or slopes[0] == 0:
                 raise ValueError('eta must be zero or inf at this point.')
-            if eta == 0:
-                sigma0 = 0
-                sigma = find_optimal_sigma(eta)
+            curvature = ProfileLikelihood.log_likelihood_der2_eta(z, X, K_mixed, 0.0)
+            for label, where, value in (('dL/deta  ', bracket[0], bracket_values[0]), ('dL/deta  ', bracket[1], bracket_values[1])):
+                print('%s at eta = %0.2e:\t %0.6g' % (label, where, value))
+            print('d2L/deta2 at eta = 0:\t %0.6g' % curvature)
+            if numpy.sign(curvature) == slopes[0]:
+                eta, sigma0, sigma = 0.0, 0, find_optimal_sigma(0.0)
             else:
-                sigma = 0
-                sigma0 = find_optimal_sigma0()
+                eta, sigma, sigma0 = numpy.inf, 0, find_optimal_sigma0()
             success = True
         return {'sigma': sigma, 'sigma0': sigma0, 'eta': eta, 'success': success}

@@ -47,7 +47,13 @@ class MixedCorrelation(object):
             if imate_method not in _SPARSE_METHODS:
                 raise ValueError('For a sparse K, existing methods are "slq" and "hutchinson".')
             self.sparse = True
-            self.engine = SparseEngine(K, imate_method, self.imate_options)
+            # imate_options['probe_split']=True: the probes of every stochastic estimate are split over the ranks of the
+            # initialised torch.distributed group; the estimates are then identical on every rank
+            probe_range = self.imate_options.pop('probe_range', None)
+            if self.imate_options.pop('probe_split', False):
+                from .._distributed import rank_world
+                probe_range = rank_world()
+            self.engine = SparseEngine(K, imate_method, self.imate_options, probe_range=probe_range)
             self.K = self.engine.K
         else:
             if imate_method not in _DENSE_METHODS:

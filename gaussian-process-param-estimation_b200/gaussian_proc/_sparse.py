@@ -511,8 +511,19 @@ class SparseEngine(object):
         samples, first = (numpy.empty((0, ncols)), 0) if state is None else state
         atol = o['error_atol'] if o['error_atol'] is not None else 0.0
 
+        failure = []      # a breakdown on THIS rank (indefinite K + eta I: non-positive Ritz value / CG breakdown)
+
+        def reduce_or_raise():
+            """all-reduce of the running sums together with a 'some rank failed' flag: a local breakdown must not leave
+            the other ranks blocked in the collective - every rank raises after it."""
+            N, mean, sd, failed = self._reduce(samples, bool(failure))
+            if failed:
+                raise failure[0] if failure else numpy.linalg.LinAlgError(
+                    'K + eta*I is not positive definite (breakdown reported by another rank of the probe split).')
+            return N, mean, sd
+
         def converged():
-            N, mean, sd = self._reduce(samples)
+            N, mean, sd = reduce_or_raise()
             if N < lo:
                 return False
             half = zc * sd / numpy.sqrt(N)
@@ -525,27 +536,35 @@ class SparseEngine(object):
             my0 = first + rank * per
             my1 = min(first + nb, my0 + per)
             for (f, w) in self._chunks(my0, max(0, my1 - my0), B):
-                samples = numpy.vstack([samples, sample_fn(f, w)])
+                if failure:
+                    break
+                try:
+                    samples = numpy.vstack([samples, sample_fn(f, w)])
+                except numpy.linalg.LinAlgError as exc:
+                    if world == 1:
+                        raise
+                    failure.append(exc)
             first += nb
             done = converged()
-        N, mean, sd = self._reduce(samples)
+        N, mean, sd = reduce_or_raise()
         half = zc * sd / numpy.sqrt(max(N, 1))
         return mean, half, int(N), (samples, first)
 
-    def _reduce(self, samples):
-        """(N, mean, unbiased std) over all ranks: all-reduce of (count, sum, sum of squares) per quantity."""
-        cnt = numpy.array([samples.shape[0]], dtype=float)
+    def _reduce(self, samples, failed=False):
+        """(N, mean, unbiased std, any rank failed) over all ranks: all-reduce of (count, failure flag, sum, sum of
+        squares) per quantity."""
+        cnt = numpy.array([samples.shape[0], 1.0 if failed else 0.0], dtype=float)
         s1 = samples.sum(axis=0)
         s2 = (samples ** 2).sum(axis=0)
         if self.probe_range is not None and self.probe_range[1] > 1:
             from ._distributed import allreduce_sum
             packed = allreduce_sum(numpy.concatenate([cnt, s1, s2]))
             k = s1.size
-            cnt, s1, s2 = packed[:1], packed[1:1 + k], packed[1 + k:]
+            cnt, s1, s2 = packed[:2], packed[2:2 + k], packed[2 + k:]
         N = cnt[0]
         mean = s1 / max(N, 1)
         var = numpy.maximum(s2 - N * mean ** 2, 0.0) / max(N - 1, 1)
-        return N, mean, numpy.sqrt(var)
+        return N, mean, numpy.sqrt(var), bool(cnt[1] > 0)
 
     def _slq(self, eta):
         """SLQ estimates [logdet, tr Kn^-1, tr Kn^-2] at eta (cached). When the matrix carries dK/drho the same Lanczos
@@ -719,7 +738,7 @@ class SparseEngine(object):
         self._rhs_cache = (key, Rop, X, z)
         return Rop
 
-    def fused(self, eta, X, z, traceinv=True, drho=True):
+    def fused(self, eta, X, z, traceinv=True, drho=True, cubic=False):
         """Everything log-likelihood + gradient need at one eta, in the layout of the dense evaluator's out[]
         (csrc/gp_loglik.cu): [logdet Kn, tr Kn^-1, tr Kn^-2, tr(Kn^-1 dK/drho), info, -, -, -, G, H, Q] with R = [X z],
         S = Kn^-1 R (batched CG, the reference's tol 1e-6), G = R^T S, H = S^T S, Q = S^T dK S; the traces are the
@@ -731,7 +750,7 @@ class SparseEngine(object):
         if bool(self.opt.get('overlap', True)) and (self.method == 'slq' or drho):
             self.prefetch_slq(eta)
         S = self.solve_rhs_block(eta, Rd, (dev.host_key(X), dev.host_key(z)), refs=(X, z))
-        out = numpy.zeros(8 + 3 * p * p)
+        out = numpy.zeros(8 + 4 * p * p)
         out[8:8 + p * p] = self.gram(Rd, S)[:p, :p].ravel()
         out[8 + p * p:8 + 2 * p * p] = self.gram(S, S)[:p, :p].ravel()
         if drho:
@@ -739,6 +758,10 @@ class SparseEngine(object):
                 raise ValueError('d/d(correlation_scale) needs a DeviceCSR generated with with_derivative=True')
             D = self.spmm(0.0, S, derivative=True)
             out[8 + 2 * p * p:8 + 3 * p * p] = self.gram(S, D)[:p, :p].ravel()
+        if cubic:
+            # third moments T3 = S^T Kn^-1 S (Hessian / second eta-derivative): one more batched CG on S
+            V2 = self.solve_dev(eta, S.clone())
+            out[8 + 3 * p * p:8 + 4 * p * p] = self.gram(S, V2)[:p, :p].ravel()
         out[0] = self.logdet(eta)
         if traceinv or drho:
             out[1] = self.traceinv(eta)

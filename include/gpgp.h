@@ -59,6 +59,28 @@ int gp_matern_dense(const double* points, int64_t n, int64_t d, const double* sc
 int gp_matern_cross(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
                     int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double eta, double* out,
                     int64_t ld, void* stream);
+/* the same block of dK/d rho (isotropic correlation scale; zero on the global diagonal and in the padding) */
+int gp_matern_cross_dk(const double* prow, const double* pcol, const int* row_gidx, const int* col_gidx, int64_t nr,
+                       int64_t nc, int64_t n, int64_t d, const double* scale_host, double nu, double* out, int64_t ld,
+                       void* stream);
+
+/* ---- helpers of the distributed dense path (gaussian_proc/_blockcyclic.py; replaces what a ScaLAPACK-style build of the
+ * reference's dposv / inverse would provide; the reference itself is single-node, _linear_solver.py:71) ---------------- */
+/* Y (M x p) = alpha X (M x N, ldx) R (N x p) + beta Y: skinny product with a rectangular slab, p <= 16 */
+int gp_rect_apply(const double* X, int64_t M, int64_t N, int64_t ldx, const double* R, int64_t p, int64_t ldr, double* Y,
+                  int64_t ldy, double alpha, double beta, void* stream);
+/* S (N x p) = alpha X^T Y + beta S; ws: gp_rect_workspace_bytes(M, N, p) bytes; fixed-order two-stage reduction */
+int64_t gp_rect_workspace_bytes(int64_t M, int64_t N, int64_t p);
+int gp_rect_apply_t(const double* X, int64_t M, int64_t N, int64_t ldx, const double* Y, int64_t p, int64_t ldy, double* S,
+                    int64_t lds, double alpha, double beta, void* ws, void* stream);
+/* accum_dev[0] += sum_{r < rows_w1} <A_r, B_r> + w_rest * sum_{r >= rows_w1} <A_r, B_r> over `cols` columns
+ * (ws: gp_rect_workspace_bytes(1, 1, 1) bytes suffice) */
+int gp_pair_dot(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t rows, int64_t cols, int64_t rows_w1,
+                double w_rest, double* accum_dev, void* ws, void* stream);
+/* V (n x p, lds) = dK/drho S with dK/drho regenerated from the points (isotropic scale), rows >= n of V zero up to the
+ * padded size */
+int gp_dk_apply(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, const double* S, int64_t p,
+                int64_t lds, double* V, void* stream);
 
 /* tau = matern(kernel_radius(density), nu): host-only, bit-follows _estimate_kernel_threshold
  * (_generate_sparse_correlation.pyx:294-413, with the missing `dimension` argument of :390 supplied).
@@ -99,6 +121,14 @@ int gp_csr_sort_rows(int64_t n, const int* indptr_dev, int* indices_dev, double*
 int gp_dgemm_f64(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                  int64_t ldb, int64_t M, int64_t N, int64_t K, double alpha, double beta, int krange, int tmask,
                  void* stream);
+/* The same product with per-row-tile k ranges: output rows [128 t, 128 t + 128) use k in [kbeg_tab[t], kend_tab[t])
+ * (DEVICE int arrays of M / 128 entries, either may be NULL): the staircase operands of the distributed inverse
+ * (gaussian_proc/_blockcyclic.py). C must not alias an operand. */
+int gp_dgemm_ktab_f64(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                      int64_t ldb, int64_t M, int64_t N, int64_t K, double alpha, double beta, const int* kbeg_tab,
+                      const int* kend_tab, void* stream);
+/* developer switch for A-B measurements: 1 = TMA + mbarrier GEMM kernel (default), 0 = the cp.async kernel */
+int gp_gemm_set_impl(int impl);
 
 /* A (npad x npad, lower triangle referenced) := K + eta*I on the first n diagonal entries (padding diagonal
  * stays exactly 1); replaces `Kn = K + eta*I` of mixed_correlation.py:184,251,296. */
@@ -210,12 +240,15 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
  * flags  : bit0 (1) tr Kn^-1 via ||inv(L)||_F^2       (enough for d/d eta)
  *          bit1 (2) full inverse: tr Kn^-1, tr Kn^-2  (needed for d/d rho and the Hessian traces)
  *          bit2 (4) d/d rho reductions, needs bit1 and points/d/scale_host/nu (dK/drho is re-evaluated on the fly)
+ *          bit3 (8) third moments T3 = R^T Kn^-3 R from one more skinny solve batch (Hessian _direct_likelihood.py:163-270,
+ *                   second eta-derivative _profile_likelihood.py:138-192); needs bit0 or bit1
  * Output : out (DEVICE, gp_loglik_out_len(p) doubles):
  *          out[0] logdet(K + eta I)   out[1] tr Kn^-1   out[2] tr Kn^-2   out[3] tr(Kn^-1 dK/drho)
  *          out[4] potrf info (0 = ok) out[5..7] reserved
  *          out[8 ..]            G = R^T Kn^-1 R        (p x p)
  *          out[8 + p^2 ..]      H = R^T Kn^-2 R        (p x p)
  *          out[8 + 2 p^2 ..]    Q = (Kn^-1 R)^T dK/drho (Kn^-1 R)   (p x p; zero unless bit2)
+ *          out[8 + 3 p^2 ..]    T3 = R^T Kn^-3 R       (p x p; zero unless bit3)
  * The remaining (m+1)x(m+1) algebra is host-side (gaussian_proc/_likelihood/_fused.py).
  * ------------------------------------------------------------------------------------------------------- */
 int64_t gp_loglik_workspace_bytes(int64_t npad);

@@ -40,7 +40,7 @@ def test_no_gpu_calls_are_pure():
     assert dev.padded_size(1) == 128 and dev.padded_size(128) == 128 and dev.padded_size(129) == 256
     assert dev.padded_size(20000) == 20096 and dev.padded_size(0) == 0
     assert dev.lib.gp_potrf_workspace_bytes(256) == 2 * 128 * 128 * 8
-    assert dev.lib.gp_loglik_out_len(7) == 8 + 3 * 49
+    assert dev.lib.gp_loglik_out_len(7) == 8 + 4 * 49          # G, H, Q, T3
     assert dev.lib.gp_launch_count() == 0
 
 

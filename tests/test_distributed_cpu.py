@@ -47,6 +47,17 @@ def _worker(rank, world, port, out):
     eng.opt = dict(DEFAULTS, min_num_samples=10, max_num_samples=24, batch=4, error_rtol=1e-9)
     eng.probe_range = (rank, world)
     res['est'] = eng._run_estimator(_fake_samples, 2)[:3]
+
+    # a breakdown on ONE rank (indefinite K + eta I) must raise on EVERY rank after the collective, not deadlock
+    def breaking(first, width):
+        if rank == 1:
+            raise numpy.linalg.LinAlgError('non-positive Ritz value')
+        return _fake_samples(first, width)
+    try:
+        eng._run_estimator(breaking, 2)
+        res['breakdown'] = 'no error'
+    except numpy.linalg.LinAlgError as exc:
+        res['breakdown'] = 'raised: ' + str(exc)[:40]
     dist.barrier()
     dist.destroy_process_group()
     out[rank] = res
@@ -76,6 +87,7 @@ def test_two_rank_gloo_matches_single_process():
     mean2, half2, n2, _ = eng._run_estimator(_fake_samples, 2, state=state)
     assert n2 == n1 and numpy.array_equal(mean2, mean1)
     for r in range(world):
+        assert out[r]['breakdown'].startswith('raised'), out[r]['breakdown']
         mean, half, n = out[r]['est']
         assert n == n1 == 24
         assert numpy.allclose(mean, mean1, rtol=0, atol=1e-12) and numpy.allclose(half, half1, rtol=0, atol=1e-12)

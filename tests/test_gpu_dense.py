@@ -256,7 +256,90 @@ def test_full_size_n20k_properties(gp):
     lp0 = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta * (1 - h), with_rho=False)[0]
     _, deta, drho = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
     assert abs((lp1 - lp0) / (2 * h * eta) - deta) <= 1e-5 * abs(deta)
-    assert numpy.isfinite(drho)
+    # (d) d l^/d rho against a Richardson-extrapolated central difference of l^ over REGENERATED K(rho +- h):
+    # truncation O(h^4), round-off ~ eps |l^| / h; tolerance 1e-6 relative
+    del Km
+    rho, hr = 0.1, 1e-3
+
+    def lp_at(r):
+        Kr = MixedCorrelation(gp.generate_correlation(pts, r, 2.5, device=True))
+        return ProfileLikelihood.log_likelihood_and_gradient(z, X, Kr, eta, with_rho=False)[0]
+    d1 = (lp_at(rho + hr) - lp_at(rho - hr)) / (2 * hr)
+    d2 = (lp_at(rho + hr / 2) - lp_at(rho - hr / 2)) / hr
+    fd = (4 * d2 - d1) / 3
+    assert abs(fd - drho) <= 1e-6 * abs(drho), (fd, drho)
+
+
+def _oracle_cell(pts, z, X, rho, nu, eta):
+    """[l^, d l^/d eta, d l^/d rho] of one cell from the CPU oracle (reference formulas, one dposv per solve)."""
+    from oracle import likelihood as L, matern
+    Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, rho, nu), 'cholesky')
+    dK = matern.matern_derivative_rho(pts, rho, nu)
+    sig = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, eta)
+    return [L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [sig, eta]),
+            L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(eta)),
+            L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dK, eta)]
+
+
+@pytest.mark.parametrize('rho,eta', [(0.1, 0.1), (0.1, 1.0), (0.2, 1e-2)])
+def test_config2_n8k_cells_match_oracle(gp, rho, eta):
+    """BASELINE configs[2] cell size (n = 8000, nu = 2.5): l^, d l^/d eta, d l^/d rho of three (rho, eta) cells against
+    the CPU oracle, 1e-9 relative (eta >= 1e-2)."""
+    from oracle import data_utilities as du
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    n = 8000
+    numpy.random.seed(0)
+    pts = numpy.random.rand(n, 2)
+    z, X = du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2)
+    Km = MixedCorrelation(gp.generate_correlation(pts, rho, 2.5, device=True))
+    got = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, eta)
+    ref = _oracle_cell(pts, z, X, rho, 2.5, eta)
+    for g_, r_ in zip(got, ref):
+        assert abs(g_ - r_) <= RTOL * max(abs(r_), 1.0), (got, ref)
+
+
+def test_n12k_cell_matches_oracle(gp):
+    """One oracle comparison above n = 12 000 (same generator of synthetic inputs as configs[1]): 1e-9 relative."""
+    from oracle import data_utilities as du
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    n = 12500                                  # not a multiple of 128: the identity padding is exercised too
+    numpy.random.seed(0)
+    pts = numpy.random.rand(n, 2)
+    z, X = du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2)
+    Km = MixedCorrelation(gp.generate_correlation(pts, 0.1, 2.5, device=True))
+    got = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1)
+    ref = _oracle_cell(pts, z, X, 0.1, 2.5, 0.1)
+    for g_, r_ in zip(got, ref):
+        assert abs(g_ - r_) <= RTOL * max(abs(r_), 1.0), (got, ref)
+
+
+@pytest.mark.parametrize('rows', [(0, 16), (16, 31), (31, 46), (46, 61)])
+def test_golden_pickle_whole_grid_on_gpu(gp, golden_pickles, rows):
+    """ALL 61 x 60 cells of the reference's shipped answer sheet data/OptimalCovariance_WithoutPrior.pickle
+    (examples/FindOptimalCovarianceParameters.py:632-702: n = 900 grid points, general-nu Matern, profile likelihood at
+    its eta root) through the GPU path, 1e-9 relative."""
+    from oracle import data_utilities as du
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    import contextlib
+    import io
+    pts = du.generate_points(30, 2, grid=True)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    worst = 0.0
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(rows[0], rows[1]):
+            for j in range(60):
+                rho, nu = golden_pickles['rho'][i], golden_pickles['nu'][j]
+                Km = MixedCorrelation(gp.generate_correlation(pts, rho, nu, device=True))
+                res = ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Km, [1e-3, 1e3])
+                lp = ProfileLikelihood.log_likelihood(z, X, Km, False, [res['sigma'], res['eta']])
+                ref = golden_pickles['Lp_noprior'][i, j]
+                worst = max(worst, abs(lp - ref) / abs(ref))
+                assert abs(lp - ref) <= 1e-9 * abs(ref), (i, j, lp, ref)
+    assert worst <= 1e-9
 
 
 # ------------------------------------------------------------ configs[0]: ~1k points, nu = 1.5, full MLE drivers
@@ -307,21 +390,34 @@ def test_grid_sweep_matches_oracle(gp):
 
 
 def test_block_cyclic_single_rank_matches_dense_engine(gp):
-    """The 2-D block-cyclic Cholesky on a 1x1 grid (the multi-rank algorithm itself is covered on CPU/gloo in
-    tests/test_blockcyclic_cpu.py and on 2/4 GPUs by tools/gpu_check_blockcyclic.py): GPU ops through the C ABI."""
+    """The distributed Cholesky + gradient on ONE rank (the multi-rank algorithm itself is covered on CPU/gloo in
+    tests/test_blockcyclic_cpu.py and on 2-8 GPUs by bench.py --gpus N / tools/gpu_check_blockcyclic.py): GPU ops through
+    the C ABI - look-ahead streams, replicated panels, rows of inv(L) with staircase k ranges, regenerated dK panels."""
     from oracle import data_utilities as du, likelihood as L, matern
     from gaussian_proc._blockcyclic import BlockCyclicCholesky
     numpy.random.seed(0)
     pts = numpy.random.rand(1000, 2)
     z = du.generate_data(pts, 0.2)
     X = du.generate_basis_functions(pts, 2)
-    bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=256)
-    lp, sig = bc.profile_log_likelihood(z, X, 0.3)
-    Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, 0.1, 2.5), 'cholesky')
+    Kh = matern.generate_dense_correlation(pts, 0.1, 2.5)
+    Ko = L.MixedCorrelation(Kh, 'cholesky')
+    dK = matern.matern_derivative_rho(pts, 0.1, 2.5)
     s0 = L.ProfileLikelihood.find_optimal_sigma(z, X, Ko, 0.3)
-    assert abs(lp - L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [s0, 0.3])) <= RTOL * abs(lp)
-    assert abs(bc.logdet() - Ko.logdet(0.3)) <= RTOL * abs(Ko.logdet(0.3))
-    assert rel(bc.solve(numpy.c_[X, z]), Ko.solve(0.3, numpy.c_[X, z])) <= RTOL
+    ref = [L.ProfileLikelihood.log_likelihood(z, X, Ko, False, [s0, 0.3]),
+           L.ProfileLikelihood.log_likelihood_der1_eta(z, X, Ko, numpy.log10(0.3)),
+           L.ProfileLikelihood.log_likelihood_der1_rho(z, X, Ko, dK, 0.3)]
+    Kinv = numpy.linalg.inv(Kh + 0.3 * numpy.eye(1000))
+    for nb in (128, 256):
+        bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
+        lp, sig = bc.profile_log_likelihood(z, X, 0.3)
+        assert abs(lp - ref[0]) <= RTOL * abs(lp) and abs(sig - s0) <= RTOL * s0
+        assert abs(bc.logdet() - Ko.logdet(0.3)) <= RTOL * abs(Ko.logdet(0.3))
+        assert rel(bc.solve(numpy.c_[X, z]), Ko.solve(0.3, numpy.c_[X, z])) <= RTOL
+        t1, t2 = bc.inverse_traces()
+        assert abs(t1 - numpy.trace(Kinv)) <= RTOL * numpy.trace(Kinv)
+        assert abs(t2 - numpy.sum(Kinv * dK)) <= RTOL * abs(numpy.sum(Kinv * dK))
+        got = bc.profile_log_likelihood_and_gradient(z, X, 0.3)
+        assert rel(got, ref) <= RTOL
     with pytest.raises(numpy.linalg.LinAlgError):
         bc.factor(-2.0)
 
@@ -399,3 +495,55 @@ def test_eigen_engine_matches_cholesky_engine(gp):
     Ge = likelihood_grid(pts, z, X, 2.5, rhos, etas, method='eigenvalue')
     Gc = likelihood_grid(pts, z, X, 2.5, rhos, etas)
     assert rel(Ge, Gc) <= 1e-9
+
+
+def test_in_place_edit_of_z_is_noticed(gp, problem):
+    """The device copy of [X z] is cached by CONTENT (full digest): an in-place edit of a single entry of z between two
+    evaluations must give the numbers of a fresh evaluation (the reference re-reads z on every call)."""
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import ProfileLikelihood
+    pts, z, X = problem
+    z = z.copy()
+    K = gp.generate_correlation(pts, 0.1, 1.5, device=True)
+    Km = MixedCorrelation(K)
+    a = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.5)
+    z[137] += 0.5                                   # not one of any "sampled" positions
+    b = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.5)
+    fresh = ProfileLikelihood.log_likelihood_and_gradient(z.copy(), X, MixedCorrelation(K), 0.5)
+    assert b != a
+    assert rel(b, fresh) <= 1e-13
+
+
+def test_hessian_one_factorisation_and_sigma_space_optimiser(gp):
+    """f-3: l + jacobian + hessian cost one fused evaluation each (no generic solves), der2_eta matches the explicit
+    formula, and with chain_rule=True (derivatives in the optimiser's own variables) trust-exact ends with success: True
+    at the oracle's maximum."""
+    from oracle import data_utilities as du, likelihood as L, matern
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    from gaussian_proc._likelihood import DirectLikelihood, ProfileLikelihood
+    numpy.random.seed(0)
+    pts = numpy.random.rand(600, 2)
+    z, X = du.generate_data(pts, 0.2), du.generate_basis_functions(pts, 2)
+    n, m = X.shape
+    Kd = gp.generate_correlation(pts, 0.1, 1.5, device=True)
+    Km = MixedCorrelation(Kd)
+    Kh = matern.generate_dense_correlation(pts, 0.1, 1.5)
+    Ko = L.MixedCorrelation(Kh, 'cholesky')
+    h = [0.25, 0.15]
+    calls = []
+    orig = Km.solve
+    Km.solve = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    H = DirectLikelihood.log_likelihood_hessian(z, X, Km, False, h)
+    assert not calls                                          # nothing goes through the generic per-call solves
+    assert rel(H, L.DirectLikelihood.log_likelihood_hessian(z, X, Ko, False, h)) <= 1e-8
+    eta = 0.3
+    Kinv = numpy.linalg.inv(Kh + eta * numpy.eye(n))
+    Y = Kinv @ X
+    M = Kinv - Y @ numpy.linalg.inv(X.T @ Y) @ Y.T
+    Mz = M @ z
+    ref = 0.5 * (n - m) / (z @ Mz) * ((numpy.sum(M * M) / (n - m) + (numpy.trace(M) / (n - m)) ** 2) * (z @ Mz) - 2 * Mz @ M @ Mz)
+    assert rel(ProfileLikelihood.log_likelihood_der2_eta(z, X, Km, eta), ref) <= 1e-8
+    res = DirectLikelihood.maximize_log_likelihood(z, X, Km, chain_rule=True)
+    assert res['success']
+    root = L.ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Ko, [1e-4, 1e3])
+    assert abs(res['eta'] - root['eta']) <= 2e-2 * root['eta'] and abs(res['sigma'] - root['sigma']) <= 1e-2 * root['sigma']

@@ -50,15 +50,90 @@ def _simulate_device_out(K, dK, X, z, eta):
     Kinv = numpy.linalg.inv(Kn)
     R = numpy.c_[X, z]
     S = Kinv @ R
-    out = numpy.zeros(8 + 3 * p * p)
+    out = numpy.zeros(8 + 4 * p * p)
     out[0] = numpy.linalg.slogdet(Kn)[1]
     out[1] = numpy.trace(Kinv)
     out[2] = numpy.sum(Kinv * Kinv)
     out[3] = numpy.sum(Kinv * dK)
     out[8:8 + p * p] = (R.T @ S).ravel()
     out[8 + p * p:8 + 2 * p * p] = (S.T @ S).ravel()
-    out[8 + 2 * p * p:] = (S.T @ dK @ S).ravel()
+    out[8 + 2 * p * p:8 + 3 * p * p] = (S.T @ dK @ S).ravel()
+    out[8 + 3 * p * p:] = (S.T @ Kinv @ S).ravel()
     return out
+
+
+class _HostOperator(object):
+    """Duck-typed K_mixed for host-only tests of the likelihood algebra: the fused evaluator is simulated in NumPy."""
+    sparse = False
+    interpolate = False
+
+    def __init__(self, K, dK):
+        self.K, self.dK = K, dK
+
+    def dot(self, eta, x, exponent=1):
+        return self.K @ x + eta * x
+
+    def trace(self, eta, exponent=1):
+        A = self.K + eta * numpy.eye(self.K.shape[0])
+        return numpy.trace(A) if exponent == 1 else numpy.sum(A * A)
+
+
+def test_second_derivatives_from_moments(monkeypatch):
+    """Hessian (variance space = the reference's numbers, and sigma space with chain_rule=True), the second
+    eta-derivative and the sigma -> 0 limit, all assembled from the moments of one fused evaluation."""
+    from gaussian_proc._likelihood import _fused, DirectLikelihood, ProfileLikelihood
+    numpy.random.seed(5)
+    pts = numpy.random.rand(120, 2)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    n, m = X.shape
+    K = matern.generate_dense_correlation(pts, 0.1, 1.5)
+    dK = matern.matern_derivative_rho(pts, 0.1, 1.5)
+    op = _HostOperator(K, dK)
+    Ko = L.MixedCorrelation(K, 'cholesky')
+
+    def fake_evaluate(z_, X_, K_mixed, eta, traceinv=False, inverse=False, drho=False, cubic=False):
+        return _fused.FusedQuantities(_simulate_device_out(K_mixed.K, K_mixed.dK, X_, z_, eta), n, m, eta, 15)
+    monkeypatch.setattr(_fused, 'evaluate', fake_evaluate)
+    for h in ([0.3, 0.2], [0.7, 0.1], [0.2, 0.5]):
+        ref = L.DirectLikelihood.log_likelihood_hessian(z, X, Ko, False, h)
+        got = DirectLikelihood.log_likelihood_hessian(z, X, op, False, h)
+        assert numpy.max(numpy.abs(got - ref)) <= 1e-8 * numpy.max(numpy.abs(ref))
+        assert (DirectLikelihood.log_likelihood_hessian(z, X, op, True, h) == -got).all()
+        # sigma-space Hessian = finite difference of the sigma-space gradient of the oracle's l
+        gs = lambda x: L.DirectLikelihood.log_likelihood_jacobian(z, X, Ko, False, list(x)) * 2.0 * numpy.asarray(x)  # noqa: E731
+        e = 1e-5
+        fd = numpy.array([(gs([h[0] + e, h[1]]) - gs([h[0] - e, h[1]])) / (2 * e),
+                          (gs([h[0], h[1] + e]) - gs([h[0], h[1] - e])) / (2 * e)])
+        hs = DirectLikelihood.log_likelihood_hessian(z, X, op, False, h, chain_rule=True)
+        assert numpy.max(numpy.abs(hs - fd)) <= 2e-6 * numpy.max(numpy.abs(fd))
+    # second eta-derivative: the reference formula (:183) written with the explicit projected precision
+    eta = 0.4
+    Kinv = numpy.linalg.inv(K + eta * numpy.eye(n))
+    Y = Kinv @ X
+    M = Kinv - Y @ numpy.linalg.inv(X.T @ Y) @ Y.T
+    Mz = M @ z
+    zMz, zM3z = z @ Mz, Mz @ (M @ Mz)
+    ref = (0.5 / (zMz / (n - m))) * ((numpy.sum(M * M) / (n - m) + (numpy.trace(M) / (n - m)) ** 2) * zMz - 2.0 * zM3z)
+    got = ProfileLikelihood.log_likelihood_der2_eta(z, X, op, eta)
+    assert abs(got - ref) <= 1e-9 * abs(ref)
+    # sigma -> 0: the closed-form limit against finite differences of l(a, b), Sigma = a K + b I, around a = 0
+    def ell(a, b):
+        Sg = a * K + b * numpy.eye(n)
+        Si = numpy.linalg.inv(Sg)
+        Bm = X.T @ Si @ X
+        Pz = Si @ z - Si @ X @ numpy.linalg.solve(Bm, X.T @ (Si @ z))
+        return -0.5 * (n - m) * numpy.log(2 * numpy.pi) - 0.5 * numpy.linalg.slogdet(Sg)[1] \
+            - 0.5 * numpy.linalg.slogdet(Bm)[1] - 0.5 * z @ Pz
+    b0, e = 0.09, 2e-4
+    g0, h0 = DirectLikelihood._degenerate_derivatives(z, X, op, numpy.sqrt(b0))
+    fd_g = numpy.array([(ell(e, b0) - ell(-e, b0)) / (2 * e), (ell(0.0, b0 + e) - ell(0.0, b0 - e)) / (2 * e)])
+    fd_h = numpy.array([[(ell(e, b0) - 2 * ell(0.0, b0) + ell(-e, b0)) / e ** 2,
+                         (ell(e, b0 + e) - ell(e, b0 - e) - ell(-e, b0 + e) + ell(-e, b0 - e)) / (4 * e * e)],
+                        [0.0, (ell(0.0, b0 + e) - 2 * ell(0.0, b0) + ell(0.0, b0 - e)) / e ** 2]])
+    fd_h[1, 0] = fd_h[0, 1]
+    assert numpy.max(numpy.abs(g0 - fd_g)) <= 1e-5 * numpy.max(numpy.abs(g0))
+    assert numpy.max(numpy.abs(h0 - fd_h)) <= 1e-3 * numpy.max(numpy.abs(h0))
 
 
 def test_fused_algebra_reproduces_reference_formulas():
@@ -239,6 +314,9 @@ def test_sparse_engine_host_helpers():
     a = numpy.arange(100.0)
     k1 = dev.host_key(a)
     assert dev.host_key(a) == k1
-    a[0] = -1.0                        # an in-place edit of a sampled entry changes the key
-    assert dev.host_key(a) != k1
-    assert dev.host_key(numpy.zeros((0, 3)))[1] == (0, 3)
+    for pos in (0, 37, 99):            # an in-place edit of ANY entry changes the key (full-content digest)
+        b = a.copy()
+        b[pos] = -1.0
+        assert dev.host_key(b) != k1
+    assert dev.host_key(a.copy()) == k1            # same content, another object: same device copy can be reused
+    assert dev.host_key(numpy.zeros((0, 3)))[0] == (0, 3)

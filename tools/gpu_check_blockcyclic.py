@@ -26,14 +26,16 @@ n = 6000
 pts, z, X = bench.make_inputs(n)
 bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=512)
 out['grid'] = [bc.P_r, bc.P_c]
-lp, sig = bc.profile_log_likelihood(z, X, 0.1)
+grad = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
+lp = grad[0]
 ld = bc.logdet()
 sol = bc.solve(z)
 Km = MixedCorrelation(generate_correlation(pts, 0.1, 2.5, device=True))
-ref_lp = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1, with_rho=False)[0]
+ref_grad = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1)
+ref_lp = ref_grad[0]
 ref_ld = Km.logdet(0.1)
 ref_sol = Km.solve(0.1, z)
-out['check'] = {'lp_rel': abs(lp - ref_lp) / abs(ref_lp), 'logdet_rel': abs(ld - ref_ld) / abs(ref_ld),
+out['check'] = {'grad_rel': [abs(a - b) / abs(b) for a, b in zip(grad, ref_grad)], 'lp_rel': abs(lp - ref_lp) / abs(ref_lp), 'logdet_rel': abs(ld - ref_ld) / abs(ref_ld),
                 'solve_rel': float(numpy.max(numpy.abs(sol - ref_sol)) / numpy.max(numpy.abs(ref_sol)))}
 del Km, bc
 torch.cuda.empty_cache()
@@ -43,20 +45,19 @@ nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 numpy.random.seed(0)
 pts = numpy.random.rand(nbig, 2)
 bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
+pts, z, X = bench.make_inputs(nbig)
 for rep in range(2):
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
-    bc.generate(0.1)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    bc.factor(0.1)
+    g = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
-    t2 = time.perf_counter()
-out['big'] = {'n': nbig, 'nb': nb, 't_generate_s': t1 - t0, 't_generate_factor_s': t2 - t1,
-              'potrf_tflops_total': (nbig ** 3 / 3.0) / (t2 - t1) * 1e-12, 'bytes_received_per_rank': bc.bytes_received,
-              'logdet': bc.logdet()}
+    t1 = time.perf_counter()
+st = dict(bc.stats)
+out['big'] = {'n': nbig, 'nb': nb, 't_total_s': t1 - t0, 'loglik_grad': [float(v) for v in g], 'stats': st,
+              'potrf_tflops_total': (nbig ** 3 / 3.0) / st['factor_s'] * 1e-12,
+              'total_tflops_per_gpu': float(nbig) ** 3 / (t1 - t0) / world * 1e-12}
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
