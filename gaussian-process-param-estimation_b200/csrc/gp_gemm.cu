@@ -294,7 +294,7 @@ struct TCfg {
     static constexpr int CONSUMER_WARPS = (BM / WM) * WARPS_N;
     static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;            // + the TMA producer warp
     static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN_ * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;   // tiles + barriers + alignment slack
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2048;   // tiles + 1 KB alignment slack + barriers (whole KB)
     static constexpr int MIN_CTAS = (BN_ == 128) ? 1 : 2;
 };
 
@@ -306,6 +306,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// arrive with a data dependence on `value` that the assembler cannot fold away: both predicated copies arrive once
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t value) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %1, 0x7ff7a5c3;\n"
+        "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "@!q mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar), "r"(value) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -456,6 +466,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int s = kt % STAGES;
         mbar_wait(bars + 8 * s, (kt / STAGES) & 1);
         const uint32_t sa = base + s * G::STAGE_BYTES, sb = sa + G::A_BYTES;
+        uint32_t dep = 0;        // data dependence of the release on every fragment load of this slab (see mbar_arrive_after)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             double a[MI], b[NI];
@@ -470,12 +481,23 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 b[j] = lds_f64(sb + o);
             }
 #pragma unroll
+            for (int i = 0; i < MI; ++i) dep ^= (uint32_t)__double2hiint(a[i]);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dep ^= (uint32_t)__double2hiint(b[j]);
+#pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+        // Release of the stage. The arrive must not be ISSUED before every fragment load of this warp has RETURNED its
+        // data: the hardware does not order an outstanding LDS before a later SYNCS.ARRIVE of the same warp, and the
+        // assembler is free to hoist the arrive right behind the last LDS issue (measured: with the load / store unit
+        // busy - two CTAs per SM, C read-modify-write epilogues - the producer's next TMA write then overtook pending
+        // loads and single fragment rows were read from the wrong slab). The arrive is therefore predicated on a value
+        // computed from ALL loaded registers of the slab (it is skipped only for one exact bit pattern that is then
+        // replaced), a data dependence the assembler cannot remove.
+        dep = __reduce_xor_sync(0xffffffffu, dep);
+        if (lane == 0) mbar_arrive_after(bars + 8 * (STAGES + s), dep);
     }
 
     // epilogue (identical to the cp.async variant)
@@ -648,7 +670,7 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
     int bn = aliased ? 128 : (g_force_bn == 128 ? 128 : 64);
     if (g_impl < 0) {
         const char* e = getenv("GP_GEMM_IMPL");
-        g_impl = (e && !strcmp(e, "tma")) ? 1 : 0;   // TEMPORARY default: cp.async kernel until the TMA path is cleared at n = 20k
+        g_impl = (e && !strcmp(e, "cpasync")) ? 0 : 1;
     }
     if (g_impl == 1 && encode_init() == 1) {
         if (bn == 128) return launch_tma_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);

@@ -88,15 +88,18 @@ trace_tiles_kernel(const double* __restrict__ Ainv, int n, int npad, const doubl
             } else {
                 t2 += 2.0 * a * a;
                 if (WITH_DK) {
-                    double s = 0.0;
+                    double s = 0.0, ud = 0.0;
 #pragma unroll
                     for (int k = 0; k < LMAXD; ++k)
                         if (k < d) {
                             double t = (pr[k][r] - pc[k][2 * tx + e]) * mp.inv_scale[k];
                             s += t * t;
+                            if (k == mp.ddim) ud = t * t;
                         }
                     double val, dval;
                     matern_value_drho<MODE>(sqrt(s), mp, &val, &dval);
+                    // d/d scale[ddim]: the isotropic g(x) / rho becomes g(x) u_ddim^2 / (x^2 scale[ddim])
+                    if (mp.ddim >= 0) dval = (s > 0.0) ? dval * (ud / s) * mp.inv_scale[mp.ddim] : 0.0;
                     t3 += 2.0 * a * dval;
                 }
             }
@@ -167,15 +170,17 @@ dk_apply_kernel(const double* __restrict__ pts, int n, int d, MaternParams mp, c
                 int jj = t * 4 + part;
                 int gj = j0 + jj;
                 if (gj >= n || gj == gi) continue;
-                double s = 0.0;
+                double s = 0.0, ud = 0.0;
 #pragma unroll
                 for (int k = 0; k < LMAXD; ++k)
                     if (k < d) {
                         double u = (pi[k] - pcs[k][jj]) * mp.inv_scale[k];
                         s += u * u;
+                        if (k == mp.ddim) ud = u * u;
                     }
                 double val, dval;
                 matern_value_drho<MODE>(sqrt(s), mp, &val, &dval);
+                if (mp.ddim >= 0) dval = (s > 0.0) ? dval * (ud / s) * mp.inv_scale[mp.ddim] : 0.0;
 #pragma unroll
                 for (int c = 0; c < MAXP; ++c)
                     if (c < p) acc[c] += dval * ss[jj * SSP + c];
@@ -353,6 +358,7 @@ finalize_out_kernel(double* out, const double* logdet, const double* tr_parts, i
         out[2] = t2;
         out[3] = t3;
         out[4] = (double)(*info);
+        out[5] = out[6] = out[7] = 0.0;      // reserved
     }
 }
 
@@ -496,6 +502,52 @@ int gp_inverse_traces(const double* M, int64_t n, int64_t npad, int kind, double
     else trace_tiles_kernel<MAT_05, false><<<tiles, 256, 0, s>>>(M, (int)n, (int)npad, nullptr, 0, mp, tr);
     finalize_out_kernel<<<1, 256, 0, s>>>(out_dev, misc, tr, tiles, frob, T * T, (const int*)(misc + 2), kind == 0 ? 1 : 2);
     GP_COUNT(2);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void sum_trace3_kernel(const double* __restrict__ tr, int tiles, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < tiles; i += blockDim.x) s += tr[(int64_t)i * 3 + 2];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// Anisotropic gradient: after gp_loglik_dense(flags & 2) on the same (Ainv = A, ws), out_dim[0] = tr(Kn^-1 dK/d scale[dim])
+// and out_dim[1 .. p^2] = S^T (dK/d scale[dim]) S, with dK regenerated from the points (reference kernel:
+// generate_correlation/_kernels.pyx:107-136, one scale per dimension).
+int gp_loglik_dense_dscale(const double* Ainv, int64_t n, int64_t npad, int64_t p, const double* points, int64_t d,
+                           const double* scale_host, double nu, int64_t dim, void* ws, double* out_dim, void* stream) {
+    if (!Ainv || !points || !scale_host || !ws || !out_dim || n <= 0 || npad != gp_padded_size(n) || p <= 0 || p > MAXP ||
+        d <= 0 || d > LMAXD || dim < 0 || dim >= d)
+        return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    LoglikWs w = carve(ws, npad, (int)p);
+    MaternParams mp;
+    mp.nu = nu; mp.coef = 0.0; mp.sq2nu = 0.0; mp.inv_rho = 1.0; mp.ddim = (int)dim;
+    for (int k = 0; k < d; ++k) {
+        if (!(scale_host[k] > 0.0)) return -4;
+        mp.inv_scale[k] = 1.0 / scale_host[k];
+    }
+    int mode = matern_mode_of(nu);
+    if (mode == MAT_GENERAL) {
+        mp.coef = pow(2.0, 1.0 - nu) / tgamma(nu);
+        mp.sq2nu = sqrt(2.0 * nu);
+    }
+    const int N = (int)n, NP = (int)npad, P = (int)p;
+    int rc;
+    switch (mode) {
+        case MAT_05: rc = grad_reductions<MAT_05>(Ainv, N, NP, points, (int)d, mp, true, w, P, out_dim + 1, s); break;
+        case MAT_15: rc = grad_reductions<MAT_15>(Ainv, N, NP, points, (int)d, mp, true, w, P, out_dim + 1, s); break;
+        case MAT_25: rc = grad_reductions<MAT_25>(Ainv, N, NP, points, (int)d, mp, true, w, P, out_dim + 1, s); break;
+        case MAT_GAUSS: rc = grad_reductions<MAT_GAUSS>(Ainv, N, NP, points, (int)d, mp, true, w, P, out_dim + 1, s); break;
+        default: rc = grad_reductions<MAT_GENERAL>(Ainv, N, NP, points, (int)d, mp, true, w, P, out_dim + 1, s); break;
+    }
+    if (rc) return rc;
+    int T = NP / 128;
+    sum_trace3_kernel<<<1, 256, 0, s>>>(w.tr, T * (T + 1) / 2, out_dim);
+    GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;
 }

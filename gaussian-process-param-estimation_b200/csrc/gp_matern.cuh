@@ -100,6 +100,7 @@ struct MaternParams {
     double sq2nu;   // sqrt(2 nu)
     double inv_rho; // 1 / rho for dK/drho (isotropic)
     double inv_scale[8]; // 1 / correlation_scale[k]
+    int ddim = -1;       // >= 0: derivative with respect to correlation_scale[ddim] alone (anisotropic gradient; inv_rho = 1)
 };
 
 // correlation value only; x is the scaled distance (>= 0). x == 0 -> exactly 1 (_kernels.pyx:73-74).

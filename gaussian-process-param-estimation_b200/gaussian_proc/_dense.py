@@ -90,6 +90,7 @@ class DenseEngine(object):
         self._have_W = False
         self._have_Ainv = False
         self.launch_count = 0
+        self.last_dscale = None  # per-dimension gradient pieces of the last fused call (anisotropic correlation_scale)
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _need_W(self):
@@ -208,20 +209,30 @@ class DenseEngine(object):
         W = self._need_W() if (flags & 3) else None
         pts = scale = None
         d, nu = 0, 0.0
+        aniso = False
         if flags & FLAG_DRHO:
             if not K.has_kernel():
                 raise ValueError('d/d(correlation_scale) needs a correlation generated by generate_correlation('
                                  '..., device=True) or MixedCorrelation.set_kernel(points, correlation_scale, nu).')
-            if not K.isotropic():
-                raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
             pts, scale, d, nu = K.points, K.correlation_scale, K.points.shape[1], float(K.nu)
+            aniso = not K.isotropic()
         self.invalidate()  # A / W are overwritten
-        rc = lib.gp_loglik_dense(_p(K.data), self.n, self.npad, _p(R_dev), p, float(eta), int(flags),
-                                 _p(pts) if pts is not None else None, d,
-                                 dev.host_ptr(scale) if scale is not None else None, nu,
+        kflags = int(flags) & ~FLAG_DRHO if aniso else int(flags)
+        rc = lib.gp_loglik_dense(_p(K.data), self.n, self.npad, _p(R_dev), p, float(eta), kflags,
+                                 _p(pts) if (pts is not None and not aniso) else None, d if not aniso else 0,
+                                 dev.host_ptr(scale) if (scale is not None and not aniso) else None, nu,
                                  _p(self.A), _p(W) if W is not None else None, _p(self.potrf_ws), _p(self.ws), _p(out),
                                  dev.stream_ptr())
         check(rc, 'gp_loglik_dense')
+        self.last_dscale = None
+        if aniso:
+            # one correlation scale per dimension (the reference kernel, _kernels.pyx:107-136): d/d scale[k] for every k
+            # from the SAME factorisation - tr(Kn^-1 dK_k) and Q_k = S^T dK_k S, dK_k regenerated from the points
+            ds = torch.empty((d, 1 + p * p), dtype=torch.float64, device='cuda')
+            for k in range(d):
+                check(lib.gp_loglik_dense_dscale(_p(self.A), self.n, self.npad, p, _p(pts), d, dev.host_ptr(scale), nu, k,
+                                                 _p(self.ws), _p(ds[k]), dev.stream_ptr()), 'gp_loglik_dense_dscale')
+            self.last_dscale = ds
         return out
 
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     'gp_traces_workspace_bytes': (_i64, [_i64]),
     'gp_inverse_traces': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
     'gp_symm_skinny': (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    'gp_loglik_dense_dscale': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _f64, _i64, _vp, _vp, _vp]),
     'gp_loglik_workspace_bytes': (_i64, [_i64]),
     'gp_loglik_out_len': (_i64, [_i64]),
     'gp_loglik_dense': (_int, [_vp, _i64, _i64, _vp, _i64, _f64, _int, _vp, _i64, _vp, _f64, _vp, _vp, _vp, _vp, _vp,

@@ -86,7 +86,9 @@ class DirectLikelihood(object):
         trace_KM = (n - m) / sigma ** 2 - eta * trace_M
         jac = numpy.array([-0.5 * trace_KM + 0.5 * q.zMKMz / sigma ** 4, -0.5 * trace_M + 0.5 * q.zM2z / sigma ** 4])
         drho = None
-        if with_rho:
+        if with_rho and q.trace_MdK_dims is not None:
+            drho = -0.5 * q.trace_MdK_dims + 0.5 * q.zMdKMz_dims / sigma ** 2      # one entry per correlation_scale[k]
+        elif with_rho:
             drho = -0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sigma ** 2
         return lp, jac, drho
 

@@ -21,7 +21,7 @@ __all__ = ['FusedQuantities', 'evaluate', 'evaluate_async', 'finish']
 class FusedQuantities(object):
     """Unpacked result of one fused evaluation at a given eta (all host floats / small arrays)."""
 
-    def __init__(self, out, n, m, eta, flags):
+    def __init__(self, out, n, m, eta, flags, dscale=None):
         p = m + 1
         self.n, self.m, self.eta, self.flags = n, m, eta, flags
         self.logdet_Kn = float(out[0])
@@ -43,6 +43,11 @@ class FusedQuantities(object):
         self.zMdKMz = float(self.c @ Q @ self.c)
         self.trace_M = self.trace_Kninv - float(numpy.trace(self.Binv @ H[:m, :m]))
         self.trace_MdK = self.trace_Kninv_dK - float(numpy.trace(self.Binv @ Q[:m, :m]))
+        # anisotropic correlation scale: per-dimension tr(M dK_k) and z^T M dK_k M z (rows of `dscale`: [trace, Q_k])
+        self.trace_MdK_dims = self.zMdKMz_dims = None
+        if dscale is not None:
+            self.trace_MdK_dims = numpy.array([row[0] - numpy.trace(self.Binv @ row[1:].reshape(p, p)[:m, :m]) for row in dscale])
+            self.zMdKMz_dims = numpy.array([self.c @ row[1:].reshape(p, p) @ self.c for row in dscale])
         # third moments (flag CUBIC): T3 = R^T Kn^-3 R. With u = M z = S c:  M u = Kn^-1 u - S_X B^-1 (S_X^T u), hence
         #   z^T M^3 z = c^T T3 c - (H_x c)^T B^-1 (H_x c),   tr M^2 = tr Kn^-2 - 2 tr(B^-1 T3_xx) + tr((B^-1 H_xx)^2)
         self.zM3z = self.trace_M2 = None
@@ -87,7 +92,7 @@ def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False
     if K_mixed.sparse:
         # sparse K: batched CG solves + skinny Gram matrices + the engine's stochastic traces (synchronous)
         out = K_mixed.engine.fused(float(eta), X, z, traceinv=traceinv or inverse or cubic, drho=drho, cubic=cubic)
-        return (out, n, m, float(eta), -1 if cubic else -2, None)
+        return (out, n, m, float(eta), -1 if cubic else -2, None, None)
     flags = 0
     if traceinv:
         flags |= FLAG_TRACEINV
@@ -98,22 +103,24 @@ def evaluate_async(z, X, K_mixed, eta, traceinv=False, inverse=False, drho=False
     if cubic:
         flags |= FLAG_CUBIC | FLAG_INVERSE         # tr Kn^-2 comes with the explicit inverse
     Rd = _rhs_device(K_mixed, X, z)
+    dscale = None
     if getattr(K_mixed, 'imate_method', None) == 'eigenvalue':
         # one eigendecomposition per matrix, O(n^2 p) per eta (the reference's default method, likelihood.py:41)
         out = K_mixed.eigen_engine().fused(float(eta), Rd, m + 1, flags)
     else:
         out = K_mixed.engine.fused(float(eta), Rd, m + 1, flags)
-    return (out, n, m, float(eta), flags, dev.torch.cuda.current_stream())
+        dscale = K_mixed.engine.last_dscale
+    return (out, n, m, float(eta), flags, dev.torch.cuda.current_stream(), dscale)
 
 
 def finish(handle):
     """Waits for the evaluation's stream, reads out[] back (one small D2H) and does the host algebra; raises
     numpy.linalg.LinAlgError if K + eta I was not positive definite."""
-    out, n, m, eta, flags, stream = handle
+    out, n, m, eta, flags, stream, dscale = handle
     if stream is None:
         return FusedQuantities(out, n, m, eta, flags)      # sparse engine: already complete, breakdowns raised there
     stream.synchronize()
-    q = FusedQuantities(out.cpu().numpy(), n, m, eta, flags)
+    q = FusedQuantities(out.cpu().numpy(), n, m, eta, flags, None if dscale is None else dscale.cpu().numpy())
     if q.info != 0:
         raise numpy.linalg.LinAlgError(
             '%d-th leading minor of K + eta*I (eta=%g) is not positive definite.' % (q.info, eta))

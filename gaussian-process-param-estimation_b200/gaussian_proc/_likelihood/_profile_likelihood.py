@@ -64,7 +64,11 @@ class ProfileLikelihood(object):
         lp = -0.5 * (n - m) * numpy.log(sigma2) - 0.5 * q.logdet_Kn - 0.5 * numpy.log(numpy.linalg.det(q.B)) \
             - 0.5 * (n - m)
         deta = -0.5 * (q.trace_M - q.zM2z / sigma2)
-        drho = (-0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sigma2) if with_rho else None
+        if with_rho and q.trace_MdK_dims is not None:
+            # anisotropic correlation_scale: the gradient with respect to every scale[k] (array of length d)
+            drho = -0.5 * q.trace_MdK_dims + 0.5 * q.zMdKMz_dims / sigma2
+        else:
+            drho = (-0.5 * q.trace_MdK + 0.5 * q.zMdKMz / sigma2) if with_rho else None
         return lp, deta, drho
 
     # ---- second derivative, valid at the stationary point only (:138-192) --------------------------

@@ -11,7 +11,7 @@ import numpy
 
 from . import _distributed as gpd
 
-__all__ = ['likelihood_grid']
+__all__ = ['likelihood_grid', 'profile_likelihood_surface']
 
 
 class _GpuRowEvaluator(object):
@@ -105,34 +105,161 @@ class _GpuSparseRowEvaluator(object):
         return numpy.array([ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta) for eta in etas])
 
 
+class _Checkpoint(object):
+    """Restartable sweeps: every finished row (one correlation matrix, all its cells) is written to
+    `<dir>/row_<key>.npy` by the rank that computed it (write to a temporary name, then rename: a killed job never leaves
+    a torn file). A later call with the same directory - any number of ranks - loads the finished rows and computes only
+    the missing ones. The directory must be visible to every rank (one node: any local path)."""
+
+    def __init__(self, directory, signature):
+        import os
+        self.dir = directory
+        self.os = os
+        if directory is not None:
+            os.makedirs(directory, exist_ok=True)
+            sig = os.path.join(directory, 'signature.txt')
+            if os.path.exists(sig):
+                if open(sig).read() != signature:
+                    raise ValueError('checkpoint directory %s belongs to a different sweep' % directory)
+            else:
+                tmp = sig + '.%d.tmp' % os.getpid()
+                open(tmp, 'w').write(signature)
+                os.replace(tmp, sig)
+
+    def _path(self, key):
+        return self.os.path.join(self.dir, 'row_%s.npy' % key)
+
+    def load(self, key):
+        if self.dir is None or not self.os.path.exists(self._path(key)):
+            return None
+        return numpy.load(self._path(key))
+
+    def save(self, key, row):
+        if self.dir is None:
+            return
+        tmp = self._path(key) + '.%d.tmp.npy' % self.os.getpid()
+        numpy.save(tmp, numpy.asarray(row))
+        self.os.replace(tmp, self._path(key))
+
+
+def _signature(tag, *arrays):
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    h.update(tag.encode())
+    for a in arrays:
+        h.update(numpy.ascontiguousarray(numpy.asarray(a, dtype=float)).tobytes())
+    return h.hexdigest()
+
+
 def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, sparse=False, density=1e-3,
-                    imate_options=None, method='cholesky'):
+                    imate_options=None, method='cholesky', checkpoint=None):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
     on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
     `concurrency` cells in flight per GPU (dense), or, with ``sparse``, the stochastic evaluator on the kernel-threshold
     correlation of the given ``density`` (``imate_options``: estimator settings, see _sparse.DEFAULTS).
-    ``method='eigenvalue'`` (dense): one eigendecomposition per rho instead of one Cholesky per cell."""
+    ``method='eigenvalue'`` (dense): one eigendecomposition per rho instead of one Cholesky per cell.
+    ``nu`` may be a sequence: the smoothness becomes a third sweep axis (the legacy (rho, nu) workload,
+    examples/FindOptimalCovarianceParameters.py:665-690) and the result has shape (len(nu), len(rhos), len(etas), 3); the
+    (nu, rho) rows are what the ranks share out.
+    ``checkpoint``: a directory; finished rows are kept there and a restarted sweep computes only the missing ones."""
     rhos = numpy.asarray(rhos, dtype=float)
     etas = numpy.asarray(etas, dtype=float)
+    nus = numpy.atleast_1d(numpy.asarray(nu, dtype=float))
+    rows_all = [(a, i) for a in range(len(nus)) for i in range(len(rhos))]           # one correlation matrix per row
     rank, world = gpd.rank_world()
-    begin, end = gpd.partition_cells(len(rhos), world, rank)
-    if evaluate is not None:
-        rows = None
-    elif sparse:
-        rows = _GpuSparseRowEvaluator(points, z, X, nu, density, imate_options)
-    elif method == 'eigenvalue':
-        rows = _GpuEigenRowEvaluator(points, z, X, nu)
-    else:
-        rows = _GpuRowEvaluator(points, z, X, nu, concurrency)
-    local = numpy.empty(((end - begin) * len(etas), 5))
+    ck = _Checkpoint(checkpoint, _signature('grid|%s|%s|%g' % (method, sparse, density), nus, rhos, etas,
+                                            numpy.asarray(points).shape if points is not None else [0]))
+    done = {}
+    if checkpoint is not None:
+        for (a, i) in rows_all:
+            row = ck.load('%d_%d' % (a, i))
+            if row is not None and row.shape == (len(etas), 3):
+                done[(a, i)] = row
+    todo = [r for r in rows_all if r not in done]
+    begin, end = gpd.partition_cells(len(todo), world, rank)
+    evaluators = {}
+
+    def evaluator(a):
+        if a not in evaluators:
+            if sparse:
+                evaluators[a] = _GpuSparseRowEvaluator(points, z, X, nus[a], density, imate_options)
+            elif method == 'eigenvalue':
+                evaluators[a] = _GpuEigenRowEvaluator(points, z, X, nus[a])
+            else:
+                evaluators[a] = _GpuRowEvaluator(points, z, X, nus[a], concurrency)
+        return evaluators[a]
+
+    local = numpy.empty(((end - begin) * len(etas), 6))
     k = 0
-    for i in range(begin, end):
-        vals = rows.row(rhos[i], etas) if rows is not None else [evaluate(rhos[i], eta) for eta in etas]
+    for (a, i) in todo[begin:end]:
+        if evaluate is not None:
+            vals = numpy.array([evaluate(rhos[i], eta) if len(nus) == 1 and numpy.ndim(nu) == 0 else evaluate(nus[a], rhos[i], eta)
+                                for eta in etas], dtype=float)
+        else:
+            vals = numpy.asarray(evaluator(a).row(rhos[i], etas), dtype=float)
+        ck.save('%d_%d' % (a, i), vals)
         for j in range(len(etas)):
-            local[k, :2] = (i, j)
-            local[k, 2:] = vals[j]
+            local[k, :3] = (a, i, j)
+            local[k, 3:] = vals[j]
             k += 1
     gathered = gpd.allgather_rows(local)
-    out = numpy.full((len(rhos), len(etas), 3), numpy.nan)
-    out[gathered[:, 0].astype(int), gathered[:, 1].astype(int)] = gathered[:, 2:]
-    return out
+    out = numpy.full((len(nus), len(rhos), len(etas), 3), numpy.nan)
+    for (a, i), row in done.items():
+        out[a, i] = row
+    if gathered.shape[0]:
+        out[gathered[:, 0].astype(int), gathered[:, 1].astype(int), gathered[:, 2].astype(int)] = gathered[:, 3:]
+    return out[0] if numpy.ndim(nu) == 0 else out
+
+
+def profile_likelihood_surface(points, z, X, rhos, nus, interval_eta=(1e-3, 1e3), checkpoint=None, evaluate=None):
+    """The reference's legacy sweep (examples/FindOptimalCovarianceParameters.py:632-702, a multiprocessing.Pool over the
+    61 x 60 (rho, nu) grid of data/OptimalCovariance_WithoutPrior.pickle): for every (rho, nu) the profile likelihood
+    maximised over eta by the root of d l^/d eta (ProfileLikelihood.find_log_likelihood_der1_zeros), i.e.
+    Lp[i, j] = l^(sigma_hat, eta_hat; rho_i, nu_j). The (rho, nu) cells are shared out over the ranks (no data-path
+    collective, one all-gather of the results); returns (Lp, eta_hat), each (len(rhos), len(nus)), identical on every rank.
+    ``checkpoint``: restartable, one file per rho row."""
+    import contextlib
+    import io
+    rhos = numpy.asarray(rhos, dtype=float)
+    nus = numpy.asarray(nus, dtype=float)
+    rank, world = gpd.rank_world()
+    ck = _Checkpoint(checkpoint, _signature('surface', rhos, nus, interval_eta))
+    done = {}
+    if checkpoint is not None:
+        for i in range(len(rhos)):
+            row = ck.load(str(i))
+            if row is not None and row.shape == (len(nus), 2):
+                done[i] = row
+    todo = [i for i in range(len(rhos)) if i not in done]
+    begin, end = gpd.partition_cells(len(todo), world, rank)
+
+    def cell(rho, nu_):
+        if evaluate is not None:
+            return evaluate(rho, nu_)
+        from .generate_correlation.generate_correlation import generate_dense_correlation
+        from ._mixed_correlation import MixedCorrelation
+        from ._likelihood import ProfileLikelihood
+        K = generate_dense_correlation(numpy.ascontiguousarray(points, dtype=float), numpy.repeat(float(rho), points.shape[1]),
+                                       float(nu_))
+        Km = MixedCorrelation(K)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = ProfileLikelihood.find_log_likelihood_der1_zeros(z, X, Km, list(interval_eta))
+        return ProfileLikelihood.log_likelihood(z, X, Km, False, [res['sigma'], res['eta']]), res['eta']
+
+    local = numpy.empty(((end - begin) * len(nus), 4))
+    k = 0
+    for i in todo[begin:end]:
+        row = numpy.array([cell(rhos[i], nu_) for nu_ in nus], dtype=float)
+        ck.save(str(i), row)
+        for j in range(len(nus)):
+            local[k] = (i, j, row[j, 0], row[j, 1])
+            k += 1
+    gathered = gpd.allgather_rows(local)
+    Lp = numpy.full((len(rhos), len(nus)), numpy.nan)
+    eta_hat = numpy.full((len(rhos), len(nus)), numpy.nan)
+    for i, row in done.items():
+        Lp[i], eta_hat[i] = row[:, 0], row[:, 1]
+    if gathered.shape[0]:
+        ii, jj = gathered[:, 0].astype(int), gathered[:, 1].astype(int)
+        Lp[ii, jj], eta_hat[ii, jj] = gathered[:, 2], gathered[:, 3]
+    return Lp, eta_hat

@@ -256,6 +256,11 @@ int64_t gp_loglik_out_len(int64_t p);
 int gp_loglik_dense(const double* K, int64_t n, int64_t npad, const double* R, int64_t p, double eta, int flags,
                     const double* points, int64_t d, const double* scale_host, double nu, double* A, double* W,
                     void* potrf_ws, void* ws, double* out, void* stream);
+/* Anisotropic gradient (one correlation scale per dimension, generate_correlation/_kernels.pyx:107-136): called after
+ * gp_loglik_dense(flags & 2) with the same A (= Kn^-1, lower) and ws. out_dim (DEVICE, 1 + p^2 doubles):
+ * out_dim[0] = tr(Kn^-1 dK/d scale[dim]), out_dim[1..] = S^T (dK/d scale[dim]) S. */
+int gp_loglik_dense_dscale(const double* Ainv, int64_t n, int64_t npad, int64_t p, const double* points, int64_t d,
+                           const double* scale_host, double nu, int64_t dim, void* ws, double* out_dim, void* stream);
 
 #ifdef __cplusplus
 }

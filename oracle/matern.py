@@ -111,6 +111,32 @@ def matern_derivative_rho(points, rho, nu):
     return dK
 
 
+def matern_derivative_scale(points, scale, nu, k):
+    """dK/d(scale[k]) for one correlation scale per dimension (extension of the reference kernel, _kernels.pyx:107-136:
+    x = sqrt(sum_j ((p_j - q_j) / scale_j)^2)). With g(x) = -x K'(x) (so that the isotropic derivative is g(x) / rho):
+    dK/d scale_k = g(x) u_k^2 / (x^2 scale_k), u_k = (p_k - q_k) / scale_k. Pinned by finite differences of the pinned
+    generator (tests/test_oracle_golden.py)."""
+    scale = numpy.asarray(scale, dtype=float)
+    x = scaled_distance_matrix(points, scale)
+    u = (points[:, None, k] - points[None, :, k]) / scale[k]
+    if nu == 0.5:
+        g = x * numpy.exp(-x)
+    elif nu == 1.5:
+        g = 3.0 * x ** 2 * numpy.exp(-numpy.sqrt(3.0) * x)
+    elif nu == 2.5:
+        g = 5.0 * x ** 2 / 3.0 * (1.0 + numpy.sqrt(5.0) * x) * numpy.exp(-numpy.sqrt(5.0) * x)
+    elif nu >= 100:
+        g = x ** 2 * numpy.exp(-0.5 * x ** 2)
+    else:
+        y = numpy.sqrt(2.0 * nu) * x
+        with numpy.errstate(invalid='ignore', over='ignore'):
+            g = (2.0 ** (1.0 - nu)) / scipy.special.gamma(nu) * (y ** (nu + 1.0)) * scipy.special.kv(nu - 1.0, y)
+    with numpy.errstate(invalid='ignore', divide='ignore'):
+        dK = g * u ** 2 / (x ** 2 * scale[k])
+    dK[x == 0] = 0.0
+    return dK
+
+
 # ---- sparse ------------------------------------------------------------------------------------------------
 
 def gamma_function(dimension):

@@ -146,6 +146,29 @@ def test_drho_extension_pinned_by_finite_differences(golden_likelihood):
             assert rel(an, fd) <= 2e-7, (nu, an, fd)
 
 
+def test_anisotropic_scale_derivative_pinned_by_finite_differences():
+    """EXTENSION (anisotropic d/d correlation_scale[k]): the analytic per-dimension derivative equals Richardson finite
+    differences of the pinned generator, and the per-dimension derivatives of an isotropic scale sum to d/d rho."""
+    numpy.random.seed(8)
+    pts = numpy.random.rand(60, 2)
+    scale = numpy.array([0.12, 0.2])
+    for nu in (0.5, 1.5, 2.5, 200.0, 3.3):
+        for k in (0, 1):
+            def Kof(h):
+                s2 = scale.copy()
+                s2[k] += h
+                return matern.generate_dense_correlation(pts, s2, nu)
+            h = 1e-4
+            d1 = (Kof(h) - Kof(-h)) / (2 * h)
+            d2 = (Kof(h / 2) - Kof(-h / 2)) / h
+            fd = (4 * d2 - d1) / 3
+            an = matern.matern_derivative_scale(pts, scale, nu, k)
+            assert numpy.max(numpy.abs(an - fd)) <= 2e-8 * max(numpy.max(numpy.abs(an)), 1.0), (nu, k)
+        iso = numpy.array([0.15, 0.15])
+        tot = matern.matern_derivative_scale(pts, iso, nu, 0) + matern.matern_derivative_scale(pts, iso, nu, 1)
+        assert numpy.max(numpy.abs(tot - matern.matern_derivative_rho(pts, 0.15, nu))) <= 1e-12 * numpy.max(numpy.abs(tot))
+
+
 # ---- (A) shipped pickles -------------------------------------------------------------------------------------
 def test_golden_pickle_cells(golden_pickles):
     pts = du.generate_points(30, 2, grid=True)
