@@ -238,87 +238,94 @@ class DenseEngine(object):
 
 class EigenEngine(object):
     """``imate_method='eigenvalue'`` -- the method the reference's Likelihood hard-codes (likelihood.py:41,
-    mixed_correlation.py:76-79,127-136,172-181,239-248): ONE symmetric eigendecomposition K = V diag(lam) V^T per
-    correlation matrix, after which EVERY eta costs O(n^2 p) instead of a factorisation:
+    mixed_correlation.py:76-79,127-136,172-181,239-248) -- on this library's own kernels (csrc/gp_eig.cu), no cuSOLVER /
+    cuBLAS call:
 
-        a = V^T [X z]  (once)          d_k = 1 / (lam_k + eta)
-        logdet = sum log(lam + eta)    tr Kn^-1 = sum d       tr Kn^-2 = sum d^2
-        G = R^T Kn^-1 R = a^T diag(d) a                       H = S^T S = a^T diag(d^2) a
-        C = V^T dK V  (once, two n^3 GEMMs)   tr(Kn^-1 dK) = sum C_kk d_k   Q = S^T dK S = (d a)^T C (d a)
+        K = Q T Q^T         gp_sytrd_f64: Householder tridiagonalisation, the rank-2 update fused into the next
+                            matrix-vector product (one read + write of the trailing matrix per column, HBM-bound)
+        lam = eig(T)        gp_stebz_f64: bisection on Sturm counts, one thread per eigenvalue   (= K_eigenvalues of the
+                            reference, mixed_correlation.py:78-79)
+        logdet, tr Kn^-1, tr Kn^-2 at any eta: O(n) reductions over lam + eta (gp_eig_reduce)
+        a = Q^T [X z]       gp_ormtr_skinny (once per [X z])
+        y = (T + eta I)^-1 a   gp_tridiag_solve, O(n p) per eta;  G = a^T y, H = y^T y, T3 = y^T (T + eta I)^-1 y
 
-    (turns an eta sweep / root find at fixed rho from one Cholesky per cell into one eigensolve per rho.)
-    The eigensolver is the cuSOLVER LIBRARY routine behind torch.linalg.eigh (0.46 s at n = 8000 on B200); the two n^3
-    products run on this package's DMMA GEMM; the skinny O(n^2 p) products are library GEMV-class calls. Same out[]
-    layout as DenseEngine.fused / gp_loglik_dense."""
+    so that after ONE reduction per correlation matrix every eta of a sweep row or of a root find costs O(n p) for
+    l^ and d l^/d eta. The d/d rho pieces (tr Kn^-1 dK, S^T dK S; an extension the reference does not have) cannot be had
+    from the spectrum of K alone: cells that ask for them take the Cholesky evaluator for those two numbers.
+    Same out[] layout as DenseEngine.fused / gp_loglik_dense."""
 
     def __init__(self, K):
         torch = dev.require_cuda()
         self.K = K
         self.n, self.npad = K.n, K.npad
-        self.lam, self.V = torch.linalg.eigh(K.data[:K.n, :K.n])
+        n = self.n
+        f64 = torch.float64
+        ldw = n + (n & 1)
+        self.ldw = ldw
+        self.Q = torch.empty((n, ldw), dtype=f64, device='cuda')        # work copy -> Householder vectors (rows)
+        self.Q[:, :n].copy_(K.data[:n, :n])
+        self.d = torch.empty(n, dtype=f64, device='cuda')
+        self.e = torch.zeros(n, dtype=f64, device='cuda')
+        self.tau = torch.zeros(n, dtype=f64, device='cuda')
+        self.lam = torch.empty(n, dtype=f64, device='cuda')
+        ws = torch.empty(lib.gp_sytrd_workspace_bytes(n) // 8 + 16, dtype=f64, device='cuda')
+        s = dev.stream_ptr()
+        check(lib.gp_sytrd_f64(_p(self.Q), n, ldw, _p(self.d), _p(self.e), _p(self.tau), _p(ws), s), 'gp_sytrd_f64')
+        check(lib.gp_stebz_f64(_p(self.d), _p(self.e), n, _p(self.lam), _p(ws), s), 'gp_stebz_f64')
+        self._piv = torch.empty(n, dtype=f64, device='cuda')
+        self._red = torch.zeros(8, dtype=f64, device='cuda')
         self._a = None
-        self._C = None
-        self._Cdiag = None
-        self._kernel_id = None
+        self._gram_ws = torch.empty(lib.gp_gram_workspace_bytes(16) // 8, dtype=f64, device='cuda')
+        self._chol = None            # Cholesky evaluator for the d/d rho pieces
 
-    def _projected_rhs(self, R_dev):
-        if self._a is None or self._a[0] is not R_dev:      # the tensor itself is kept: its address cannot be reused
-            self._a = (R_dev, dev.torch.matmul(self.V.t(), R_dev[:self.n]))
+    # ---- O(n) reductions over the spectrum --------------------------------------------------------------------
+    def reductions(self, eta):
+        """(logdet Kn, tr Kn^-1, tr Kn^-2, number of eigenvalues with lam + eta <= 0) as host floats"""
+        check(lib.gp_eig_reduce(_p(self.lam), self.n, float(eta), _p(self._red), dev.stream_ptr()), 'gp_eig_reduce')
+        r = self._red.cpu().numpy()
+        return float(r[0]), float(r[1]), float(r[2]), int(r[3])
+
+    def _projected_rhs(self, R_dev, p):
+        """a = Q^T R (n x p), cached while the same device block is passed"""
+        if self._a is None or self._a[0] is not R_dev or self._a[1].shape[1] != p:
+            a = R_dev[:self.n, :p].contiguous()
+            check(lib.gp_ormtr_skinny(_p(self.Q), self.n, self.ldw, _p(self.tau), 1, _p(a), p, p, dev.stream_ptr()),
+                  'gp_ormtr_skinny')
+            self._a = (R_dev, a)
         return self._a[1]
 
-    def _projected_dK(self):
-        """C = V^T dK V (n x n); dK is generated into a padded buffer, the products run on gp_dgemm_f64."""
-        torch = dev.torch
-        K = self.K
-        if not K.has_kernel():
-            raise ValueError('d/d(correlation_scale) needs a correlation generated by generate_correlation('
-                             '..., device=True) or MixedCorrelation.set_kernel(points, correlation_scale, nu).')
-        if not K.isotropic():
-            raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
-        kid = (K.points.data_ptr(), tuple(K.correlation_scale.tolist()), float(K.nu))
-        if self._C is not None and self._kernel_id == kid:
-            return self._C, self._Cdiag
-        n, npad = self.n, self.npad
-        f64 = torch.float64
-        T1 = torch.empty((npad, npad), dtype=f64, device='cuda')
-        dK = torch.empty((npad, npad), dtype=f64, device='cuda')
-        s = dev.stream_ptr()
-        check(lib.gp_matern_dense(_p(K.points), n, K.points.shape[1], dev.host_ptr(K.correlation_scale), float(K.nu),
-                                  _p(T1), npad, _p(dK), s), 'gp_matern_dense')          # T1 <- K (discarded), dK <- dK/drho
-        Vp = torch.zeros((npad, npad), dtype=f64, device='cuda')
-        Vp[:n, :n].copy_(self.V)
-        # T1 = dK V          (A = dK stored [m][k], B = V stored [k][n])
-        check(lib.gp_dgemm_f64(0, 1, _p(T1), npad, _p(dK), npad, _p(Vp), npad, npad, npad, npad, 1.0, 0.0, 0, 0, s),
-              'gp_dgemm_f64')
-        # C = V^T T1         (A = V stored [k][m], B = T1 stored [k][n]); written over dK
-        check(lib.gp_dgemm_f64(1, 1, _p(dK), npad, _p(Vp), npad, _p(T1), npad, npad, npad, npad, 1.0, 0.0, 0, 0, s),
-              'gp_dgemm_f64')
-        self._C = dK[:n, :n]
-        self._Cdiag = torch.diagonal(self._C).clone()
-        self._kernel_id = kid
-        return self._C, self._Cdiag
+    def _gram(self, X, Y, out_view, p):
+        check(lib.gp_gram_skinny(_p(X), _p(Y), self.n, p, _p(out_view), _p(self._gram_ws), dev.stream_ptr()), 'gp_gram_skinny')
 
     def fused(self, eta, R_dev, p, flags):
-        """Returns out[] (device tensor, layout of gp_loglik_dense); info = 1 when K + eta I is not positive definite."""
+        """Returns out[] (device tensor, layout of gp_loglik_dense); out[4] = 1 when K + eta I is not positive definite."""
         torch = dev.torch
+        n = self.n
         out = torch.zeros(int(lib.gp_loglik_out_len(p)), dtype=torch.float64, device='cuda')
-        sh = self.lam + float(eta)
-        bad = bool((sh <= 0).any().item())
-        if bad:
-            out[4] = 1.0
-            return out
-        d = 1.0 / sh
-        a = self._projected_rhs(R_dev)[:, :p]
-        da = a * d[:, None]
-        out[0] = sh.log().sum()
-        out[1] = d.sum()
-        out[2] = (d * d).sum()
-        out[8:8 + p * p] = torch.matmul(a.t(), da).reshape(-1)
-        out[8 + p * p:8 + 2 * p * p] = torch.matmul(da.t(), da).reshape(-1)
-        if flags & FLAG_DRHO:
-            C, Cdiag = self._projected_dK()
-            out[3] = (Cdiag * d).sum()
-            out[8 + 2 * p * p:8 + 3 * p * p] = torch.matmul(da.t(), torch.matmul(C, da)).reshape(-1)
+        s = dev.stream_ptr()
+        a = self._projected_rhs(R_dev, p)
+        y = torch.empty_like(a)
+        info = torch.zeros(2, dtype=torch.float64, device='cuda')
+        check(lib.gp_tridiag_solve(_p(self.d), _p(self.e), n, float(eta), _p(a), p, p, _p(y), p, _p(self._piv), _p(info), s),
+              'gp_tridiag_solve')
+        check(lib.gp_eig_reduce(_p(self.lam), n, float(eta), _p(out), s), 'gp_eig_reduce')     # out[0..2], out[3] = #bad
+        out[4] = ((out[3] > 0) | (info[1] > 0)).to(torch.float64)
+        out[3] = 0.0
+        self._gram(a, y, out[8:8 + p * p], p)
+        self._gram(y, y, out[8 + p * p:8 + 2 * p * p], p)
         if flags & FLAG_CUBIC:
-            out[8 + 3 * p * p:8 + 4 * p * p] = torch.matmul(da.t(), da * d[:, None]).reshape(-1)
+            y2 = torch.empty_like(a)
+            check(lib.gp_tridiag_solve(_p(self.d), _p(self.e), n, float(eta), _p(y), p, p, _p(y2), p, _p(self._piv), _p(info), s),
+                  'gp_tridiag_solve')
+            self._gram(y, y2, out[8 + 3 * p * p:8 + 4 * p * p], p)
+        if flags & FLAG_DRHO:
+            # not a function of the spectrum of K: one Cholesky evaluation supplies tr(Kn^-1 dK) and Q = S^T dK S
+            if self._chol is None:
+                self._chol = DenseEngine(self.K)
+            oc = self._chol.fused(eta, R_dev, p, FLAG_TRACEINV | FLAG_INVERSE | FLAG_DRHO)
+            if self._chol.last_dscale is not None:
+                raise ValueError("imate_method='eigenvalue': d/d(correlation_scale) per dimension is available on the "
+                                 "Cholesky method only.")
+            out[3] = oc[3]
+            out[8 + 2 * p * p:8 + 3 * p * p] = oc[8 + 2 * p * p:8 + 3 * p * p]
         return out

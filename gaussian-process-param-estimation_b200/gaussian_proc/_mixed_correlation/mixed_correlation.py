@@ -22,11 +22,10 @@ class MixedCorrelation(object):
     Same constructor and methods as the reference class (mixed_correlation.py:34-35). Differences, all documented
     in DESIGN.md: ``imate_method`` 'cholesky' (dense) and 'slq' / 'hutchinson' (sparse) are implemented natively;
     'eigenvalue' (the method the reference's Likelihood hard-codes, likelihood.py:41) computes all eigenvalues of K once
-    in __init__ like mixed_correlation.py:76-79 -- here with the cuSOLVER symmetric eigensolver behind
-    torch.linalg.eigvalsh, a LIBRARY call (own kernel: next) -- after which logdet / traceinv / trace are
-    O(n) reductions over lambda + eta; ``solve`` uses the native Cholesky engine, and the fused likelihood evaluation
-    (log-likelihood + gradient) runs on the full eigendecomposition (_dense.EigenEngine): one eigensolve per matrix,
-    O(n^2 p) per eta.
+    in __init__ like mixed_correlation.py:76-79 -- with this library's own Householder tridiagonalisation + bisection
+    (csrc/gp_eig.cu, no cuSOLVER) -- after which logdet / traceinv / trace are O(n) reductions over lambda + eta;
+    ``solve`` uses the native Cholesky engine, and the fused likelihood evaluation runs on the tridiagonal form
+    (_dense.EigenEngine): one reduction per matrix, O(n p) per eta for l^ and d l^/d eta.
     ``interpolate=True``: tr (K + eta I)^-1 is interpolated in eta from evaluations at ``interpolant_points``
     (_interpolate_traceinv.py, the role of imate.InterpolateTraceInv; rational polynomial scheme, parity unpinned).
     """
@@ -65,7 +64,7 @@ class MixedCorrelation(object):
             self.K_eigenvalues = None
             self._eigen = None
             if imate_method == 'eigenvalue':
-                # ONE symmetric eigensolve (values and vectors: the vectors cost ~10 % more than the values alone)
+                # ONE tridiagonalisation + all eigenvalues (the reference's eigh(K, eigvals_only=True), :78-79)
                 from .._dense import EigenEngine
                 self._eigen = EigenEngine(K)
                 self.K_eigenvalues = self._eigen.lam
@@ -120,16 +119,18 @@ class MixedCorrelation(object):
 
     def _traceinv_direct(self, eta, exponent=1):
         if not self.sparse and self.imate_method == 'eigenvalue':
-            return float(((self.K_eigenvalues + eta) ** (-exponent)).sum().item())     # :172-181
+            if exponent in (1, 2):
+                return self._eigen.reductions(eta)[exponent]                              # :172-181
+            return float(((self.K_eigenvalues + eta) ** (-exponent)).sum().item())
         return self.engine.traceinv(eta, exponent)
 
     def logdet(self, eta, exponent=1):
         """mixed_correlation.py:221-274; logdet(Kn^p) = p logdet(Kn)."""
         if not self.sparse and self.imate_method == 'eigenvalue':
-            lam = self.K_eigenvalues + eta                                                # :239-248
-            if not bool((lam > 0).all().item()):
+            logdet, _, _, bad = self._eigen.reductions(eta)                               # :239-248
+            if bad:
                 raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite.' % eta)
-            return exponent * float(lam.log().sum().item())
+            return exponent * logdet
         return exponent * self.engine.logdet(eta)
 
     def solve(self, eta, Y):

@@ -64,15 +64,16 @@ class _GpuRowEvaluator(object):
 
 
 class _GpuEigenRowEvaluator(object):
-    """All eta cells of one rho through ONE eigendecomposition of K(rho) (imate_method='eigenvalue', the reference's
-    default, likelihood.py:41; _dense.EigenEngine): every cell after the eigensolve is O(n^2 p). Pays off for long eta
-    rows (about 30 cells at n = 8000); the eigensolver itself is the cuSOLVER library routine."""
+    """All eta cells of one rho through ONE tridiagonalisation of K(rho) (imate_method='eigenvalue', the reference's
+    default, likelihood.py:41; _dense.EigenEngine, csrc/gp_eig.cu): every cell after it is O(n p) for l^ and d l^/d eta.
+    Pays off for long eta rows / root finds. d l^/d rho is not a function of the spectrum: with ``with_rho`` those cells
+    add one Cholesky evaluation each (then the plain Cholesky rows are the faster choice)."""
 
-    def __init__(self, points, z, X, nu):
+    def __init__(self, points, z, X, nu, with_rho=True):
         from . import _device as dev
         dev.require_cuda()
         self.points = numpy.ascontiguousarray(points, dtype=float)
-        self.z, self.X, self.nu = z, X, float(nu)
+        self.z, self.X, self.nu, self.with_rho = z, X, float(nu), bool(with_rho)
 
     def row(self, rho, etas):
         from .generate_correlation.generate_correlation import generate_dense_correlation
@@ -80,7 +81,8 @@ class _GpuEigenRowEvaluator(object):
         from ._likelihood import ProfileLikelihood
         K = generate_dense_correlation(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu)
         Km = MixedCorrelation(K, imate_method='eigenvalue')
-        return numpy.array([ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta) for eta in etas])
+        rows = [ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta, with_rho=self.with_rho) for eta in etas]
+        return numpy.array([[r[0], r[1], numpy.nan if r[2] is None else r[2]] for r in rows], dtype=float)
 
 
 class _GpuSparseRowEvaluator(object):
@@ -151,13 +153,23 @@ def _signature(tag, *arrays):
     return h.hexdigest()
 
 
+def _frozen(a):
+    """a read-only copy: its device copy is then keyed once instead of being re-fingerprinted for every cell"""
+    if a is None:
+        return None
+    b = numpy.array(a, dtype=float, copy=True)
+    b.setflags(write=False)
+    return b
+
+
 def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, sparse=False, density=1e-3,
-                    imate_options=None, method='cholesky', checkpoint=None):
+                    imate_options=None, method='cholesky', checkpoint=None, with_rho=True):
     """Returns an array (len(rhos), len(etas), 3) with [l^(sigma_hat, eta), d l^/d eta, d l^/d rho] per cell, identical
     on every rank. `evaluate(rho, eta)` may be injected (tests); by default it is the fused GPU evaluator with
     `concurrency` cells in flight per GPU (dense), or, with ``sparse``, the stochastic evaluator on the kernel-threshold
     correlation of the given ``density`` (``imate_options``: estimator settings, see _sparse.DEFAULTS).
-    ``method='eigenvalue'`` (dense): one eigendecomposition per rho instead of one Cholesky per cell.
+    ``method='eigenvalue'`` (dense): one tridiagonalisation per rho instead of one Cholesky per cell (``with_rho=False``
+    skips d l^/d rho, NaN in the result, which the spectrum alone cannot give).
     ``nu`` may be a sequence: the smoothness becomes a third sweep axis (the legacy (rho, nu) workload,
     examples/FindOptimalCovarianceParameters.py:665-690) and the result has shape (len(nu), len(rhos), len(etas), 3); the
     (nu, rho) rows are what the ranks share out.
@@ -165,6 +177,7 @@ def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, 
     rhos = numpy.asarray(rhos, dtype=float)
     etas = numpy.asarray(etas, dtype=float)
     nus = numpy.atleast_1d(numpy.asarray(nu, dtype=float))
+    z, X = _frozen(z), _frozen(X)
     rows_all = [(a, i) for a in range(len(nus)) for i in range(len(rhos))]           # one correlation matrix per row
     rank, world = gpd.rank_world()
     ck = _Checkpoint(checkpoint, _signature('grid|%s|%s|%g' % (method, sparse, density), nus, rhos, etas,
@@ -184,7 +197,7 @@ def likelihood_grid(points, z, X, nu, rhos, etas, evaluate=None, concurrency=4, 
             if sparse:
                 evaluators[a] = _GpuSparseRowEvaluator(points, z, X, nus[a], density, imate_options)
             elif method == 'eigenvalue':
-                evaluators[a] = _GpuEigenRowEvaluator(points, z, X, nus[a])
+                evaluators[a] = _GpuEigenRowEvaluator(points, z, X, nus[a], with_rho)
             else:
                 evaluators[a] = _GpuRowEvaluator(points, z, X, nus[a], concurrency)
         return evaluators[a]
@@ -222,6 +235,7 @@ def profile_likelihood_surface(points, z, X, rhos, nus, interval_eta=(1e-3, 1e3)
     import io
     rhos = numpy.asarray(rhos, dtype=float)
     nus = numpy.asarray(nus, dtype=float)
+    z, X = _frozen(z), _frozen(X)
     rank, world = gpd.rank_world()
     ck = _Checkpoint(checkpoint, _signature('surface', rhos, nus, interval_eta))
     done = {}

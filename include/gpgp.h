@@ -230,6 +230,26 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Symmetric eigenvalue path (imate_method = 'eigenvalue', the reference's default: _likelihood/likelihood.py:41,
+ * _mixed_correlation/mixed_correlation.py:76-79 -> scipy.linalg.eigh(K, eigvals_only=True); :127-136,172-181,239-248 reduce
+ * over lam + eta). csrc/gp_eig.cu.
+ * ------------------------------------------------------------------------------------------------------- */
+/* K = Q T Q^T. A (n x n, lda even, BOTH triangles valid) is overwritten: row k right of the diagonal keeps Householder
+ * vector k (v[k+1] = 1). d (n), e (n; n-1 used), tau (n) on the device. ws: gp_sytrd_workspace_bytes(n). */
+int64_t gp_sytrd_workspace_bytes(int64_t n);
+int gp_sytrd_f64(double* A, int64_t n, int64_t lda, double* d, double* e, double* tau, void* ws, void* stream);
+/* all eigenvalues (ascending) of the tridiagonal (d, e) by bisection; ws: (n + 8) doubles; synchronises the stream once */
+int gp_stebz_f64(const double* d, const double* e, int64_t n, double* lam, void* ws, void* stream);
+/* R (n x p, p <= 16) <- Q^T R (trans != 0) or Q R (trans == 0), Q from gp_sytrd_f64 */
+int gp_ormtr_skinny(const double* A, int64_t n, int64_t lda, const double* tau, int trans, double* R, int64_t p, int64_t ldr,
+                    void* stream);
+/* Y <- (T + eta I)^-1 B (n x p); out (device, 2): log det (T + eta I), number of non-positive pivots; ws: n doubles */
+int gp_tridiag_solve(const double* d, const double* e, int64_t n, double eta, const double* B, int64_t p, int64_t ldb, double* Y,
+                     int64_t ldy, void* ws, double* out, void* stream);
+/* out (device, 4): sum log(lam + eta), sum (lam + eta)^-1, sum (lam + eta)^-2, count of lam + eta <= 0 */
+int gp_eig_reduce(const double* lam, int64_t n, double eta, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Fused log-likelihood (+ gradient ingredients) evaluation at one (rho, eta)
  * (reference: _likelihood/_direct_likelihood.py:31-157 log_likelihood + log_likelihood_jacobian,
  *  _likelihood/_profile_likelihood.py:38-132 log_likelihood + log_likelihood_der1_eta; the d/drho terms are the

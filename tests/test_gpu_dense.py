@@ -436,7 +436,11 @@ def test_eigenvalue_method_matches_reference_vectors(gp, golden_likelihood):
         assert rel(Km.logdet(eta), g['c1_eigenvalue_logdet'][i]) <= RTOL
         assert rel(Km.traceinv(eta), g['c1_eigenvalue_traceinv'][i]) <= (1e-8 if t < 0 else RTOL)
         assert rel(Km.traceinv(eta, exponent=2), g['c1_eigenvalue_traceinv2'][i]) <= (1e-7 if t < 0 else RTOL)
-    assert rel(Km.trace(0.5, exponent=3), numpy.sum((numpy.linalg.eigvalsh(K.to_numpy()) + 0.5) ** 3)) <= 1e-10
+    lam_ref = numpy.linalg.eigvalsh(K.to_numpy())
+    assert rel(Km.trace(0.5, exponent=3), numpy.sum((lam_ref + 0.5) ** 3)) <= 1e-10
+    # the spectrum itself (own tridiagonalisation + bisection) against LAPACK: absolute accuracy ~ eps ||K||
+    lam = Km.K_eigenvalues.cpu().numpy()
+    assert numpy.max(numpy.abs(numpy.sort(lam) - lam_ref)) <= 1e-12 * lam_ref[-1]
     h = list(g['hyper_direct'][0])
     lk = Likelihood(X, K, likelihood_method='direct', imate_method='eigenvalue')
     assert rel(lk.likelihood(z, h), g['c1_eigenvalue_direct_ll'][0]) <= RTOL
@@ -495,6 +499,17 @@ def test_eigen_engine_matches_cholesky_engine(gp):
     Ge = likelihood_grid(pts, z, X, 2.5, rhos, etas, method='eigenvalue')
     Gc = likelihood_grid(pts, z, X, 2.5, rhos, etas)
     assert rel(Ge, Gc) <= 1e-9
+    Gn = likelihood_grid(pts, z, X, 2.5, rhos, etas, method='eigenvalue', with_rho=False)      # spectrum only: no d/d rho
+    assert rel(Gn[:, :, :2], Gc[:, :, :2]) <= 1e-9 and numpy.isnan(Gn[:, :, 2]).all()
+    # odd size (leading dimension padding of the work copy) and tiny sizes
+    for nn in (3, 4, 131):
+        numpy.random.seed(nn)
+        A = numpy.random.rand(nn, nn)
+        A = A @ A.T + numpy.eye(nn)
+        Kn = MixedCorrelation(A, imate_method='eigenvalue')
+        ref = numpy.linalg.eigvalsh(A)
+        assert numpy.max(numpy.abs(numpy.sort(Kn.K_eigenvalues.cpu().numpy()) - ref)) <= 1e-12 * ref[-1]
+        assert rel(Kn.logdet(0.3), numpy.sum(numpy.log(ref + 0.3))) <= 1e-11
 
 
 def test_in_place_edit_of_z_is_noticed(gp, problem):
