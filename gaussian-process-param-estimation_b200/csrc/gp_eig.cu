@@ -114,6 +114,7 @@ sytd_pass_kernel(double* __restrict__ A, int n, int64_t lda, int k, int first, c
         }
         ++j;
     }
+#pragma unroll 4
     for (int jj = j + 2 * lane; jj < n; jj += 64) {
         if (jj + 1 < n) {
             double2 a = *reinterpret_cast<const double2*>(row + jj);
@@ -217,39 +218,79 @@ ormtr_skinny_kernel(const double* __restrict__ A, int n, int64_t lda, const doub
     }
 }
 
-// ---- (T + eta I) Y = B, p right-hand sides, one warp: lane c < p owns column c; the pivots are shared ------------------------
-__global__ void __launch_bounds__(32)
+// ---- (T + eta I) Y = B, p right-hand sides ------------------------------------------------------------------------------
+// One CTA. The recurrences are sequential in i, so the only way to make them fast is to keep every operand of the inner
+// loop in shared memory: the CTA stages chunks of TCH rows (d, e, the right-hand sides) cooperatively, warp 0 runs the
+// recurrence on the chunk (lane c < p owns column c, the pivots are recomputed by every lane), and the chunk is written back
+// cooperatively. log det (T + eta I) = sum log |delta_i| is summed in parallel from the stored pivots afterwards.
+constexpr int TCH = 256;
+__global__ void __launch_bounds__(256)
 tridiag_solve_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, double eta, const double* __restrict__ B,
                      int p, int64_t ldb, double* __restrict__ Y, int64_t ldy, double* __restrict__ piv, double* __restrict__ out) {
-    const int c = threadIdx.x;
-    // forward: delta_i = d_i + eta - e_{i-1}^2 / delta_{i-1};  y_i = b_i - (e_{i-1} / delta_{i-1}) y_{i-1}
-    double delta = d[0] + eta;
-    double y = (c < p) ? B[c] : 0.0;
-    double logdet = log(fabs(delta));
-    int neg = (delta <= 0.0);
-    if (c == 0) piv[0] = delta;
-    if (c < p) Y[c] = y;
-    for (int i = 1; i < n; ++i) {
-        const double l = e[i - 1] / delta;
-        delta = d[i] + eta - l * e[i - 1];
-        y = ((c < p) ? B[(int64_t)i * ldb + c] : 0.0) - l * y;
-        logdet += log(fabs(delta));
-        neg += (delta <= 0.0);
-        if (c == 0) piv[i] = delta;
-        if (c < p) Y[(int64_t)i * ldy + c] = y;
+    __shared__ double sd[TCH], se[TCH], sp[TCH];
+    __shared__ double sy[TCH * EP];
+    __shared__ double red[40];
+    __shared__ double carry[EP + 2];          // [0..p): last y / x of the previous chunk, [EP]: last pivot, [EP + 1]: e before the chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- forward: delta_i = d_i + eta - e_{i-1}^2 / delta_{i-1};  y_i = b_i - (e_{i-1} / delta_{i-1}) y_{i-1}
+    for (int c0 = 0; c0 < n; c0 += TCH) {
+        const int cnt = min(TCH, n - c0);
+        for (int r = tid; r < cnt; r += 256) {
+            sd[r] = d[c0 + r] + eta;
+            se[r] = (c0 + r > 0) ? e[c0 + r - 1] : 0.0;       // the off-diagonal entry ABOVE row c0 + r
+        }
+        for (int idx = tid; idx < cnt * p; idx += 256) sy[(idx / p) * EP + idx % p] = B[(int64_t)(c0 + idx / p) * ldb + idx % p];
+        __syncthreads();
+        if (warp == 0) {
+            double delta = (c0 > 0) ? carry[EP] : 1.0;
+            double y = (c0 > 0 && lane < p) ? carry[lane] : 0.0;
+            for (int r = 0; r < cnt; ++r) {
+                const double l = se[r] / delta;                // zero for the very first row
+                delta = sd[r] - l * se[r];
+                y = ((lane < p) ? sy[r * EP + lane] : 0.0) - l * y;
+                if (lane == 0) sp[r] = delta;
+                if (lane < p) sy[r * EP + lane] = y;
+            }
+            if (lane < p) carry[lane] = y;
+            if (lane == 0) carry[EP] = delta;
+        }
+        __syncthreads();
+        for (int r = tid; r < cnt; r += 256) piv[c0 + r] = sp[r];
+        for (int idx = tid; idx < cnt * p; idx += 256) Y[(int64_t)(c0 + idx / p) * ldy + idx % p] = sy[(idx / p) * EP + idx % p];
+        __syncthreads();
     }
-    // backward: x_i = y_i / delta_i - (e_i / delta_i) x_{i+1}
-    double x = 0.0;
-    for (int i = n - 1; i >= 0; --i) {
+    // ---- backward: x_i = (y_i - e_i x_{i+1}) / delta_i
+    const int nchunks = (n + TCH - 1) / TCH;
+    for (int ch = nchunks - 1; ch >= 0; --ch) {
+        const int c0 = ch * TCH, cnt = min(TCH, n - c0);
+        for (int r = tid; r < cnt; r += 256) {
+            sp[r] = piv[c0 + r];
+            se[r] = (c0 + r + 1 < n) ? e[c0 + r] : 0.0;         // the off-diagonal entry BELOW row c0 + r
+        }
+        for (int idx = tid; idx < cnt * p; idx += 256) sy[(idx / p) * EP + idx % p] = Y[(int64_t)(c0 + idx / p) * ldy + idx % p];
+        __syncthreads();
+        if (warp == 0) {
+            double x = (ch < nchunks - 1 && lane < p) ? carry[lane] : 0.0;
+            for (int r = cnt - 1; r >= 0; --r) {
+                x = (((lane < p) ? sy[r * EP + lane] : 0.0) - se[r] * x) / sp[r];
+                if (lane < p) sy[r * EP + lane] = x;
+            }
+            if (lane < p) carry[lane] = x;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < cnt * p; idx += 256) Y[(int64_t)(c0 + idx / p) * ldy + idx % p] = sy[(idx / p) * EP + idx % p];
+        __syncthreads();
+    }
+    // ---- log det and the number of non-positive pivots
+    double ld = 0.0, neg = 0.0;
+    for (int i = tid; i < n; i += 256) {
         const double dl = piv[i];
-        const double yi = (c < p) ? Y[(int64_t)i * ldy + c] : 0.0;
-        x = (yi - ((i + 1 < n) ? e[i] * x : 0.0)) / dl;
-        if (c < p) Y[(int64_t)i * ldy + c] = x;
+        ld += log(fabs(dl));
+        neg += (dl <= 0.0) ? 1.0 : 0.0;
     }
-    if (c == 0) {
-        out[0] = logdet;
-        out[1] = (double)neg;       // > 0: T + eta I is not positive definite
-    }
+    ld = block_sum_all(ld, red);
+    neg = block_sum_all(neg, red);
+    if (tid == 0) { out[0] = ld; out[1] = neg; }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -375,7 +416,7 @@ int gp_ormtr_skinny(const double* A, int64_t n, int64_t lda, const double* tau, 
 int gp_tridiag_solve(const double* d, const double* e, int64_t n, double eta, const double* B, int64_t p, int64_t ldb, double* Y,
                      int64_t ldy, void* ws, double* out, void* stream) {
     if (!d || !e || !B || !Y || !ws || !out || n <= 0 || p <= 0 || p > EP || ldb < p || ldy < p) return -1;
-    tridiag_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, e, (int)n, eta, B, (int)p, ldb, Y, ldy, (double*)ws, out);
+    tridiag_solve_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d, e, (int)n, eta, B, (int)p, ldb, Y, ldy, (double*)ws, out);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;

@@ -214,6 +214,7 @@ class BlockCyclicCholesky(object):
         self.stats = {}
         self.bytes_received = 0
         self._pts_dev = None
+        self._Abuf = self._Lflat = self._Xbuf = self._Tbuf = None
 
     # ---- helpers -------------------------------------------------------------------------------------------------
     def _gidx(self, blocks):
@@ -248,7 +249,9 @@ class BlockCyclicCholesky(object):
         pts = self._padded_points()
         cg = self._gidx(self.J_loc)
         rg = numpy.arange(self.npad, dtype=numpy.int32)
-        self.Aloc = ops.empty((self.npad, len(cg)))
+        if self._Abuf is None:
+            self._Abuf = ops.empty((self.npad, len(cg)))      # kept across factorisations (no allocator traffic per call)
+        self.Aloc = self._Abuf
         if len(cg):
             ops.generate(pts, ops.from_host(self._padded_host()[cg]), ops.from_host(rg), ops.from_host(cg), self.n, self.scale,
                          self.nu, eta, self.Aloc)
@@ -273,6 +276,12 @@ class BlockCyclicCholesky(object):
         infos = []
         lcol = {j: q for q, j in enumerate(self.J_loc)}
         side = ops.new_stream()
+        # ONE buffer for the whole replicated factor (panel k: (NB - k + 1) nb rows), allocated once: a per-panel
+        # allocation inside the loop would go through cudaMalloc - a device-wide synchronisation - and stall the look-ahead
+        offs = numpy.concatenate([[0], numpy.cumsum([(NB - k + 1) * nb for k in range(NB)])])
+        if self._Lflat is None:
+            self._Lflat = ops.empty((int(offs[-1]), nb))
+        Lflat = self._Lflat
         comm = []                    # (event before, event after) of every broadcast, on the side stream
 
         def apply_panel(k, j):
@@ -285,7 +294,7 @@ class BlockCyclicCholesky(object):
         def prepare_panel(k):
             """on the side stream: the owner factors the diagonal block and forms the panel; everybody joins the broadcast"""
             owner = snake_owner(k, P)
-            msg = ops.empty(((NB - k + 1) * nb, nb))
+            msg = Lflat[int(offs[k]):int(offs[k + 1])]
             if self.rank == owner:
                 q = lcol[k]
                 col = A[k * nb:, q * nb:(q + 1) * nb]
@@ -302,8 +311,9 @@ class BlockCyclicCholesky(object):
             self.panels[k] = msg
 
         main_done = None           # event: trailing update of the previous step enqueued on the main stream
+        generated = ops.event()      # recorded on the MAIN stream (before the side stream becomes current)
         with ops.use(side):
-            ops.wait(side, ops.event())      # the side stream starts after the generation
+            ops.wait(side, generated)        # the side stream starts after the generation
             prepare_panel(0)
             ready = ops.event()
         for k in range(NB):
@@ -321,14 +331,17 @@ class BlockCyclicCholesky(object):
                     apply_panel(k, j)
             main_done = ops.event()
         for k, info in infos:
-            bad += (info.to(bad.dtype) > 0) * float(1 + k)
+            bad += (info.to(bad.dtype) > 0) * float(1 + k) * 1e-6 + (info.to(bad.dtype) > 0)    # count + sum of (1 + block index) / 1e6
         self._allreduce(bad)
         ops.synchronize()
         self.stats = {'factor_s': time.perf_counter() - t0, 'bytes_received': self.bytes_received,
                       'comm_s': sum(ops.elapsed_s(a, b) for a, b in comm) if comm else 0.0}
-        if float(ops.to_host(bad)[0]) != 0.0:
-            raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite (distributed potrf).' % eta)
-        self.Aloc = None
+        nbad = float(ops.to_host(bad)[0])
+        if nbad != 0.0:
+            raise numpy.linalg.LinAlgError('K + eta*I (eta=%g) is not positive definite (distributed potrf: %d diagonal blocks '
+                                           'with a non-positive pivot, mean block index %.1f of %d).'
+                                           % (eta, int(nbad), (nbad - int(nbad)) * 1e6 / max(int(nbad), 1) - 1, NB))
+        self.Aloc = None                 # (the buffer itself stays in self._Abuf for the next factorisation)
         self.eta = float(eta)
 
     def logdet(self):
@@ -386,8 +399,18 @@ class BlockCyclicCholesky(object):
         ops, nb, NB = self.ops, self.nb, self.NB
         I = self.J_loc
         nq = len(I)
-        X = ops.zeros((max(nq, 1) * nb, self.npad))
-        T = ops.empty((max(nq, 1) * nb, nb))
+        if self._Tbuf is None:
+            self._Tbuf = ops.empty((max(nq, 1) * nb, nb))
+        if nq and self._Abuf is not None:
+            # my block columns of K are dead once the factor sits in the panels: the rows of W take over that storage
+            # (npad x nq nb and nq nb x npad have the same number of entries)
+            X = self._Abuf.reshape(-1)[:nq * nb * self.npad].view(nq * nb, self.npad)
+        else:
+            if self._Xbuf is None:
+                self._Xbuf = ops.empty((max(nq, 1) * nb, self.npad))
+            X = self._Xbuf
+        T = self._Tbuf
+        X.zero_()
         tiles = nb // 128
         for k in range(NB - 1, -1, -1):
             msg = self.panels[k]

@@ -288,7 +288,7 @@ class EigenEngine(object):
     def _projected_rhs(self, R_dev, p):
         """a = Q^T R (n x p), cached while the same device block is passed"""
         if self._a is None or self._a[0] is not R_dev or self._a[1].shape[1] != p:
-            a = R_dev[:self.n, :p].contiguous()
+            a = R_dev[:self.n, :p].clone(memory_format=dev.torch.contiguous_format)     # a COPY: ormtr works in place
             check(lib.gp_ormtr_skinny(_p(self.Q), self.n, self.ldw, _p(self.tau), 1, _p(a), p, p, dev.stream_ptr()),
                   'gp_ormtr_skinny')
             self._a = (R_dev, a)

@@ -332,7 +332,7 @@ class SparseEngine(object):
         o = self.opt
         B, hi = int(o['batch']), int(o['max_num_samples'])
         rank, world = self.probe_range if self.probe_range is not None else (0, 1)
-        nb = min(B * world, hi)
+        nb = min(B, hi)
         per = (nb + world - 1) // world
         my0 = rank * per
         chunks = self._chunks(my0, max(0, min(nb, my0 + per) - my0), B)
@@ -531,7 +531,7 @@ class SparseEngine(object):
 
         done = (first > 0) and converged()
         while first < hi and not done:
-            nb = min(B * world, hi - first)
+            nb = min(B, hi - first)          # the round size does not depend on the rank count: same samples, same stopping decision
             per = (nb + world - 1) // world
             my0 = first + rank * per
             my1 = min(first + nb, my0 + per)

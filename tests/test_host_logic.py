@@ -306,8 +306,8 @@ def test_sparse_engine_host_helpers():
     eng.opt = dict(DEFAULTS, max_num_samples=50, batch=16)
     eng.probe_range = None
     assert eng._first_chunk() == (0, 16)
-    eng.probe_range = (1, 2)          # second of two ranks: the round of 32 probes is cut into 16 + 16
-    assert eng._first_chunk() == (16, 16)
+    eng.probe_range = (1, 2)          # second of two ranks: the round of 16 probes is cut into 8 + 8
+    assert eng._first_chunk() == (8, 8)
     eng.opt = dict(DEFAULTS, max_num_samples=10, batch=16)
     eng.probe_range = (1, 4)          # 10 probes over 4 ranks: 3 each, rank 1 takes ids 3, 4, 5 -> first chunk (3, 2)
     assert eng._first_chunk() == (3, 2)

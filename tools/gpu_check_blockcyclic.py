@@ -1,5 +1,5 @@
-"""Developer check (multi-GPU, run under torchrun): 2-D block-cyclic Cholesky vs the single-GPU dense engine, then a
-timed large-n factorisation.  torchrun --nproc-per-node N tools/gpu_check_blockcyclic.py [n_big] [nb]"""
+"""Developer check (multi-GPU, run under torchrun): distributed Cholesky + gradient vs the single-GPU dense engine, then a
+timed large-n evaluation.  torchrun --nproc-per-node N tools/gpu_check_blockcyclic.py [n_big] [nb] [n_check ...]"""
 import json, os, sys, time
 import numpy
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'gaussian-process-param-estimation_b200'))
@@ -20,45 +20,56 @@ from gaussian_proc import generate_correlation
 from gaussian_proc._mixed_correlation import MixedCorrelation
 from gaussian_proc._likelihood import ProfileLikelihood
 
-out = {'world': world}
-# ---- correctness at n = 6000 against the single-GPU path ------------------------------------------------------
-n = 6000
-pts, z, X = bench.make_inputs(n)
-bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=512)
-out['grid'] = [bc.P_r, bc.P_c]
-grad = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
-lp = grad[0]
-ld = bc.logdet()
-sol = bc.solve(z)
-Km = MixedCorrelation(generate_correlation(pts, 0.1, 2.5, device=True))
-ref_grad = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1)
-ref_lp = ref_grad[0]
-ref_ld = Km.logdet(0.1)
-ref_sol = Km.solve(0.1, z)
-out['check'] = {'grad_rel': [abs(a - b) / abs(b) for a, b in zip(grad, ref_grad)], 'lp_rel': abs(lp - ref_lp) / abs(ref_lp), 'logdet_rel': abs(ld - ref_ld) / abs(ref_ld),
-                'solve_rel': float(numpy.max(numpy.abs(sol - ref_sol)) / numpy.max(numpy.abs(ref_sol)))}
-del Km, bc
-torch.cuda.empty_cache()
-# ---- timing ------------------------------------------------------------------------------------------------------
 nbig = int(sys.argv[1]) if len(sys.argv) > 1 else 40960
-nb = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-numpy.random.seed(0)
-pts = numpy.random.rand(nbig, 2)
-bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
-pts, z, X = bench.make_inputs(nbig)
-for rep in range(2):
-    torch.cuda.synchronize()
-    if world > 1: dist.barrier()
-    t0 = time.perf_counter()
-    g = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
-    torch.cuda.synchronize()
-    if world > 1: dist.barrier()
-    t1 = time.perf_counter()
-st = dict(bc.stats)
-out['big'] = {'n': nbig, 'nb': nb, 't_total_s': t1 - t0, 'loglik_grad': [float(v) for v in g], 'stats': st,
-              'potrf_tflops_total': (nbig ** 3 / 3.0) / st['factor_s'] * 1e-12,
-              'total_tflops_per_gpu': float(nbig) ** 3 / (t1 - t0) / world * 1e-12}
-if rank == 0:
-    print(json.dumps(out))
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+checks = [int(a) for a in sys.argv[3:]] or [6000]
+
+
+def say(obj):
+    if rank == 0:
+        print(json.dumps(obj), flush=True)
+
+
+# ---- correctness against the single-GPU path ----------------------------------------------------------------------
+for n in checks:
+    pts, z, X = bench.make_inputs(n)
+    out = {'world': world, 'check_n': n, 'nb': nb}
+    try:
+        bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
+        grad = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
+        ld = bc.logdet()
+        sol = bc.solve(z)
+        Km = MixedCorrelation(generate_correlation(pts, 0.1, 2.5, device=True))
+        ref_grad = ProfileLikelihood.log_likelihood_and_gradient(z, X, Km, 0.1)
+        ref_ld = Km.logdet(0.1)
+        ref_sol = Km.solve(0.1, z)
+        out.update({'grad_rel': [abs(a - b) / abs(b) for a, b in zip(grad, ref_grad)], 'logdet_rel': abs(ld - ref_ld) / abs(ref_ld),
+                    'solve_rel': float(numpy.max(numpy.abs(sol - ref_sol)) / numpy.max(numpy.abs(ref_sol))), 'stats': dict(bc.stats)})
+        del Km, bc
+    except Exception as exc:  # noqa: BLE001
+        out['error'] = repr(exc)[:300]
+    torch.cuda.empty_cache()
+    say(out)
+# ---- timing ------------------------------------------------------------------------------------------------------
+if nbig > 0:
+    pts, z, X = bench.make_inputs(nbig)
+    bc = BlockCyclicCholesky(pts, 0.1, 2.5, nb=nb)
+    for rep in range(2):
+        out = {'world': world, 'n': nbig, 'nb': nb, 'rep': rep}
+        try:
+            torch.cuda.synchronize()
+            if world > 1: dist.barrier()
+            t0 = time.perf_counter()
+            g = bc.profile_log_likelihood_and_gradient(z, X, 0.1)
+            torch.cuda.synchronize()
+            if world > 1: dist.barrier()
+            t1 = time.perf_counter()
+            st = dict(bc.stats)
+            out.update({'t_total_s': t1 - t0, 'loglik_grad': [float(v) for v in g], 'stats': st,
+                        'potrf_tflops_total': (nbig ** 3 / 3.0) / st['factor_s'] * 1e-12,
+                        'total_tflops_per_gpu': float(nbig) ** 3 / (t1 - t0) / world * 1e-12})
+        except Exception as exc:  # noqa: BLE001
+            out['error'] = repr(exc)[:300]
+        say(out)
 if world > 1:
     dist.destroy_process_group()
