@@ -554,7 +554,7 @@ def blockcyclic_measurement(n, world, rank):
            'scaling': 'strong', 'seconds_total': ms * 1e-3, 'loglik_grad': [float(v) for v in res],
            'seconds_generate_factor': st.get('factor_s'), 'factor_tflops_total': fl_factor / st['factor_s'] * 1e-12 if st.get('factor_s') else None,
            'factor_tflops_per_gpu': fl_factor / st['factor_s'] / world * 1e-12 if st.get('factor_s') else None,
-           'seconds_inverse_and_traces': st.get('traces_s'), 'seconds_solves': st.get('solve_s'),
+           'seconds_inverse_rows': st.get('inverse_rows_s'), 'seconds_traces': st.get('traces_s'), 'seconds_solves': st.get('solve_s'),
            'total_tflops_per_gpu': float(n) ** 3 / (ms * 1e-3) / world * 1e-12,
            'bytes_received_per_rank': st.get('bytes_received'), 'nccl_seconds_on_comm_stream': st.get('comm_s'),
            'nccl_fraction_of_factor_time': (st['comm_s'] / st['factor_s']) if st.get('comm_s') is not None and st.get('factor_s') else None,

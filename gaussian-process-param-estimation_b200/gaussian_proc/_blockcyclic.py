@@ -391,6 +391,21 @@ class BlockCyclicCholesky(object):
             out[:, c0:c0 + 16] = self.ops.to_host(self.solve_dev(self.ops.from_host(Bp)))[:self.n]
         return out[:, 0] if vec else out
 
+    def solve_with_rows(self, Rdev):
+        """(K + eta I)^-1 R = W^T (W R) from the rows of W = inv(L) this rank holds: two passes over the local slab and one
+        all-reduce of the (npad x p) result - instead of 2 NB latency-bound substitution steps on the replicated panels."""
+        ops, nb = self.ops, self.nb
+        X = self.inverse_rows()
+        nq = len(self.J_loc)
+        p = Rdev.shape[1]
+        S = ops.zeros((self.npad, p))
+        if nq:
+            Y = ops.empty((nq * nb, p))
+            ops.rect_apply(X[:nq * nb], Rdev, Y)
+            ops.rect_apply_t(X[:nq * nb], Y, S)
+        self._allreduce(S)
+        return S
+
     # ---- rows of inv(L) ----------------------------------------------------------------------------------------------
     def inverse_rows(self):
         """X <- my block rows of W = inv(L) (block back-substitution from the right on the replicated factor)."""
@@ -475,8 +490,13 @@ class BlockCyclicCholesky(object):
         R[:n, m] = z
         Rd = ops.from_host(R)
         ops.synchronize()
+        if with_gradient:
+            t0 = time.perf_counter()
+            self.inverse_rows()
+            ops.synchronize()
+            self.stats['inverse_rows_s'] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        S = self.solve_dev(Rd.clone())
+        S = self.solve_with_rows(Rd) if with_gradient else self.solve_dev(Rd.clone())
         Sh, Rh = ops.to_host(S), R
         out = numpy.zeros(8 + 4 * p * p)
         out[0] = self.logdet()
