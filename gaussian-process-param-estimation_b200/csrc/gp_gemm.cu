@@ -285,13 +285,14 @@ dgemm_dmma_kernel(double* C, int64_t ldc, const double* A, int64_t lda, const do
 // permutation for A and B, so the product is unchanged - which makes the 8-byte fragment loads of both layouts
 // bank-conflict free (each half-warp covers 16 distinct 8-byte bank groups).
 // =====================================================================================================================
-template <int BN_>
+template <int BN_, int WM_>
 struct TCfg {
     static constexpr int BN = BN_;
     static constexpr int BK = 16;
     static constexpr int STAGES = (BN_ == 128) ? 6 : 4;
     static constexpr int WARPS_N = BN_ / WN;
-    static constexpr int CONSUMER_WARPS = (BM / WM) * WARPS_N;
+    static constexpr int WM = WM_, MI = WM_ / 8;         // warp tile WM x 32: 64 (2 warps / SM sub-partition at two CTAs per SM) or 32 (4)
+    static constexpr int CONSUMER_WARPS = (BM / WM_) * WARPS_N;
     static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;            // + the TMA producer warp
     static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN_ * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 2048;   // tiles + 1 KB alignment slack + barriers (whole KB)
@@ -359,13 +360,13 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
-template <int AT, int BT, int BN_>
-__global__ void __launch_bounds__(TCfg<BN_>::THREADS, TCfg<BN_>::MIN_CTAS)
+template <int AT, int BT, int BN_, int WM_>
+__global__ void __launch_bounds__(TCfg<BN_, WM_>::THREADS, TCfg<BN_, WM_>::MIN_CTAS)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* C, int64_t ldc,
                  int tiles_m, int tiles_n, int K, double alpha, double beta, int krange, int tmask,
                  const int* __restrict__ kbeg_tab, const int* __restrict__ kend_tab) {
-    using G = TCfg<BN_>;
-    constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES;
+    using G = TCfg<BN_, WM_>;
+    constexpr int BN = G::BN, BK = G::BK, STAGES = G::STAGES, WM = G::WM, MI = G::MI;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     int bid = blockIdx.x;
@@ -613,21 +614,21 @@ static int launch_inst(double* C, int64_t ldc, const double* A, int64_t lda, con
 
 static int g_impl = -1;      // GP_GEMM_IMPL=cpasync selects the older cp.async kernel (A-B measurements); default: TMA
 
-template <int AT, int BT, int BN_>
+template <int AT, int BT, int BN_, int WM_>
 static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                            int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream,
                            const int* kbeg_tab, const int* kend_tab) {
-    using G = TCfg<BN_>;
+    using G = TCfg<BN_, WM_>;
     if (K % G::BK) return -1;
     int tiles_m = M / BM, tiles_n = N / BN_;
     if (tiles_m == 0 || tiles_n == 0) return 0;
-    int rc = configure_once((const void*)dgemm_tma_kernel<AT, BT, BN_>, G::SMEM);
+    int rc = configure_once((const void*)dgemm_tma_kernel<AT, BT, BN_, WM_>, G::SMEM);
     if (rc) return rc;
     CUtensorMap mapA, mapB;
     if ((rc = make_map(&mapA, AT, A, lda, M, K, BM))) return rc;
     if ((rc = make_map(&mapB, BT, B, ldb, N, K, BN_))) return rc;
     cudaEvent_t e1 = profile_begin(tile_flops(tiles_m, tiles_n, BN_, K, krange, tmask), stream);
-    dgemm_tma_kernel<AT, BT, BN_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
+    dgemm_tma_kernel<AT, BT, BN_, WM_><<<tiles_m * tiles_n, G::THREADS, G::SMEM, stream>>>(
         mapA, mapB, C, ldc, tiles_m, tiles_n, K, alpha, beta, krange, tmask, kbeg_tab, kend_tab);
     if (e1) cudaEventRecord(e1, stream);
     GP_COUNT(1);
@@ -635,14 +636,14 @@ static int launch_tma_inst(double* C, int64_t ldc, const double* A, int64_t lda,
     return 0;
 }
 
-template <int BN_>
+template <int BN_, int WM_>
 static int launch_tma_bn(int at, int bt, double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb,
                          int M, int N, int K, double alpha, double beta, int krange, int tmask, cudaStream_t stream,
                          const int* kbeg_tab = nullptr, const int* kend_tab = nullptr) {
-    if (at == 0 && bt == 0) return launch_tma_inst<0, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
-    if (at == 0 && bt == 1) return launch_tma_inst<0, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
-    if (at == 1 && bt == 1) return launch_tma_inst<1, 1, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
-    if (at == 1 && bt == 0) return launch_tma_inst<1, 0, BN_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 0 && bt == 0) return launch_tma_inst<0, 0, BN_, WM_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 0 && bt == 1) return launch_tma_inst<0, 1, BN_, WM_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 1 && bt == 1) return launch_tma_inst<1, 1, BN_, WM_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
+    if (at == 1 && bt == 0) return launch_tma_inst<1, 0, BN_, WM_>(C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream, kbeg_tab, kend_tab);
     return -4;
 }
 
@@ -673,8 +674,11 @@ int launch_dgemm(int at, int bt, double* C, int64_t ldc, const double* A, int64_
         g_impl = (e && !strcmp(e, "cpasync")) ? 0 : 1;
     }
     if (g_impl == 1 && encode_init() == 1) {
-        if (bn == 128) return launch_tma_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
-        return launch_tma_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+        static int wm32 = -1;     // GP_GEMM_WM=32: 32 x 32 warp tiles, 8 consumer warps per CTA (4 warps per sub-partition)
+        if (wm32 < 0) { const char* e = getenv("GP_GEMM_WM"); wm32 = (e && atoi(e) == 32) ? 1 : 0; }
+        if (bn == 128) return launch_tma_bn<128, 64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+        if (wm32) return launch_tma_bn<64, 32>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
+        return launch_tma_bn<64, 64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     }
     if (bn == 128) return launch_bn<128>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
     return launch_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, krange, tmask, stream);
@@ -691,7 +695,7 @@ int launch_dgemm_ktab(int at, int bt, double* C, int64_t ldc, const double* A, i
     if (C == A || C == B) return -6;
     if (encode_init() != 1) return -7;
     if (K == 0) K = 32;   // a zero k extent still has to scale C by beta: the tables (or kend = 0) keep the loop empty
-    return launch_tma_bn<64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, KR_FULL, TM_ALL, stream, kbeg_tab, kend_tab);
+    return launch_tma_bn<64, 64>(at, bt, C, ldc, A, lda, B, ldb, M, N, K, alpha, beta, KR_FULL, TM_ALL, stream, kbeg_tab, kend_tab);
 }
 
 int set_gemm_impl(int impl) { g_impl = impl; return 0; }

@@ -58,7 +58,8 @@ def _worker(rank, world, port, n, nb, out):
 @pytest.mark.parametrize('world,n,nb', [(2, 700, 128), (3, 1000, 128), (4, 1100, 256)])
 def test_block_cyclic_matches_dense_oracle(world, n, nb):
     from oracle import likelihood as L, matern
-    out = mp.Manager().dict()
+    from conftest import RankResults
+    out = RankResults()          # no multiprocessing.Manager: it would fork() this process
     mp.spawn(_worker, args=(world, _free_port(), n, nb, out), nprocs=world, join=True)
     pts, z, X = _problem(n)
     Ko = L.MixedCorrelation(matern.generate_dense_correlation(pts, 0.1, 2.5), 'cholesky')

@@ -65,8 +65,8 @@ def _worker(rank, world, port, out):
 
 def test_two_rank_gloo_matches_single_process():
     world = 2
-    mgr = mp.Manager()
-    out = mgr.dict()
+    from conftest import RankResults
+    out = RankResults()          # no multiprocessing.Manager: it would fork() this process
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
