@@ -745,32 +745,57 @@ def run_ours(args):
                   'ProfileLikelihood.log_likelihood_and_gradient_async(z, X, K_mixed, eta)() ',
            'last_result': [float(v) for v in r]}
 
-    sharded = None
+    # ---- the headline line is complete here; everything below is reported alongside it -------------------------------------
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': bench_config(n, npad, C),
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
+    printed = threading.Lock()
+
+    def emit(extra):
+        """prints the ONE JSON line (rank 0), exactly once"""
+        if printed.acquire(blocking=False):
+            if rank == 0:
+                out = dict(line)
+                out.update(extra)
+                print(json.dumps(out), flush=True)
+
+    # Watchdog: the secondary legs contain collectives; if one rank fails inside them the others would wait forever and the
+    # headline would never be printed. After the deadline rank 0 prints the line without the unfinished legs and every
+    # rank leaves.
+    deadline = float(os.environ.get('GP_BENCH_SECONDARY_TIMEOUT', '600'))
+
+    def watchdog():
+        emit({'secondary': {'error': 'secondary measurements did not finish within %.0f s' % deadline}})
+        sys.stdout.flush()
+        os._exit(0)
+    timer = threading.Timer(deadline, watchdog)
+    timer.daemon = True
+    extra = {}
     if not args.no_secondary:
+        timer.start()
         del hp, hz, hX
         torch.cuda.empty_cache()
         try:
             sharded = sharded_measurements(world, rank)
         except Exception as e:  # noqa: BLE001 -- the headline must still print
             sharded = {'error': repr(e)[:300]}
-    if rank == 0:
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': bench_config(n, npad, C),
-                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e}
-        if not args.no_secondary:
-            line['secondary'] = {'sharded': sharded}
-            if world == 1:
-                try:
-                    line['secondary'].update(secondary_measurements())
-                except Exception as e:  # noqa: BLE001 -- the headline must still print
-                    line['secondary']['error'] = repr(e)[:300]
-        if world == 1 and not args.no_cpu:
-            # bounded (~30 s): n = 4000 and 8000 measured, n = 20 000 from the n^2 / n^3 fit (flagged); the measured
-            # n = 20 000 evaluation is the reference arm's (`bench.py --impl reference`)
-            line['cpu_baseline'] = cpu_sample(n, full=os.environ.get('GP_BENCH_CPU_FULL', '0') != '0')
-        print(json.dumps(line))
+        extra['secondary'] = {'sharded': sharded}
+        if world == 1 and rank == 0:
+            try:
+                extra['secondary'].update(secondary_measurements())
+            except Exception as e:  # noqa: BLE001 -- the headline must still print
+                extra['secondary']['error'] = repr(e)[:300]
+    if world == 1 and rank == 0 and not args.no_cpu:
+        # bounded (~30 s): n = 4000 and 8000 measured, n = 20 000 from the n^2 / n^3 fit (flagged); the measured
+        # n = 20 000 evaluation is the reference arm's (`bench.py --impl reference`)
+        try:
+            extra['cpu_baseline'] = cpu_sample(n, full=os.environ.get('GP_BENCH_CPU_FULL', '0') != '0')
+        except Exception as e:  # noqa: BLE001
+            extra['cpu_baseline'] = {'error': repr(e)[:300]}
+    timer.cancel()
+    emit(extra)
     if world > 1:
         dist.destroy_process_group()
 

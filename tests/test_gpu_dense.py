@@ -593,3 +593,30 @@ def test_anisotropic_gradient_matches_oracle(gp, problem, nu):
     Ka = MixedCorrelation(gp.generate_correlation(pts, numpy.array([0.1, 0.1 * (1 + 1e-15)]), nu, device=True))
     iso = ProfileLikelihood.log_likelihood_and_gradient(z, X, Ki, eta)[2]
     assert numpy.isscalar(iso) or numpy.ndim(iso) == 0
+
+
+def test_legacy_rho_nu_surface_and_restartable_sweeps(gp, golden_pickles, tmp_path):
+    """The reference's legacy workload as one call: profile_likelihood_surface over a corner of the (rho, nu) grid of
+    data/OptimalCovariance_WithoutPrior.pickle (examples/FindOptimalCovarianceParameters.py:632-702) equals the shipped
+    answer sheet (1e-9); a sweep restarted from its checkpoint directory recomputes only the missing rows; nu as a third
+    axis of likelihood_grid equals the per-nu grids."""
+    from oracle import data_utilities as du
+    from gaussian_proc.sweep import likelihood_grid, profile_likelihood_surface
+    pts = du.generate_points(30, 2, grid=True)
+    z = du.generate_data(pts, 0.2)
+    X = du.generate_basis_functions(pts, 2)
+    rhos, nus = golden_pickles['rho'][[0, 30, 60]], golden_pickles['nu'][[0, 20, 59]]
+    ck = str(tmp_path / 'surface')
+    Lp, eta_hat = profile_likelihood_surface(pts, z, X, rhos, nus, checkpoint=ck)
+    ref = golden_pickles['Lp_noprior'][numpy.ix_([0, 30, 60], [0, 20, 59])]
+    assert rel(Lp, ref) <= RTOL and (eta_hat > 1e-3).all() and (eta_hat < 1e3).all()
+    import os
+    os.remove(os.path.join(ck, 'row_1.npy'))
+    Lp2, _ = profile_likelihood_surface(pts, z, X, rhos, nus, checkpoint=ck)          # rows 0 and 2 come from the files
+    assert numpy.array_equal(Lp2, Lp)
+    etas = numpy.logspace(-1, 1, 3)
+    G3 = likelihood_grid(pts, z, X, [1.5, 2.5], [0.1, 0.2], etas, checkpoint=str(tmp_path / 'grid'))
+    assert G3.shape == (2, 2, 3, 3)
+    assert rel(G3[1], likelihood_grid(pts, z, X, 2.5, [0.1, 0.2], etas)) <= 1e-12
+    assert rel(G3[0], likelihood_grid(pts, z, X, 1.5, [0.1, 0.2], etas)) <= 1e-12
+    assert numpy.array_equal(likelihood_grid(pts, z, X, [1.5, 2.5], [0.1, 0.2], etas, checkpoint=str(tmp_path / 'grid')), G3)

@@ -273,12 +273,12 @@ def test_lanczos_block_quadrature_and_solution_coefficients():
 
 
 def test_recorded_bench_line_follows_the_contract():
-    """The committed bench record (profiles/r01_bench_1gpu_final.json, written by `python bench.py` on a B200) carries
+    """The committed bench record (profiles/r02_bench_1gpu_builder.json, written by `python bench.py --steps 20 --warmup 5` on a B200) carries
     every key of the driver's contract: headline metric, roofline, cpu_baseline, e2e, clocks, launch count."""
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    line = json.loads(open(os.path.join(root, 'profiles', 'r01_bench_1gpu_final.json')).read().strip().splitlines()[-1])
+    line = json.loads(open(os.path.join(root, 'profiles', 'r02_bench_1gpu_builder.json')).read().strip().splitlines()[-1])
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
               'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'cpu_baseline', 'e2e', 'gpu_launches', 'clocks'):
         assert k in line, k
@@ -292,6 +292,12 @@ def test_recorded_bench_line_follows_the_contract():
     assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
     assert line['gpu_launches'] > 0 and not line['clocks']['reasons']
     assert abs(line['value'] - line['steps'] * line['n_gpus'] / (line['ms_per_step'] * line['steps'] * 1e-3)) < 1e-9
+    sh = line['secondary']['sharded']                      # the workloads that shard, measured at every N
+    assert set(('C3_sweep_n8k', 'C4_sparse_n1M_probe_split', 'C4_sparse_sweep_n1M', 'C5_blockcyclic')) <= set(sh)
+    assert 'extrapolated' in line['cpu_baseline']
+    ref = json.loads(open(os.path.join(root, 'profiles', 'r02_bench_reference_builder.json')).read().strip().splitlines()[-1])
+    assert ref['impl'] == 'reference' and ref['config'] == line['config'] and ref['cpu_baseline']['extrapolated'] is False
+    assert ref['ms_per_step'] * ref['steps'] * 1e-3 < 300          # the bounded samples, not the n = 20 000 evaluation
 
 
 def test_sparse_engine_host_helpers():
