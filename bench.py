@@ -596,7 +596,7 @@ def run_ours(args):
     # `cells_in_flight` independent evaluations are kept in flight per GPU, each with its own K buffer / scratch and its
     # own CUDA stream (the latency-bound phases of one evaluation - diagonal blocks, small recursion levels, the
     # HBM-bound reductions - are filled by the GEMMs of another; the grid sweep does the same, gaussian_proc/sweep.py)
-    dpts = torch.from_numpy(pts).cuda()
+    dpts = torch.from_numpy(numpy.array(pts)).cuda()         # (pts is a read-only array: copy before wrapping)
     C = max(1, int(args.cells_in_flight))
     slots = []
     for c in range(C):

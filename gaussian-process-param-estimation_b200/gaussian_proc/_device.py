@@ -75,6 +75,12 @@ SIGNATURES = {
     'gp_rect_apply_t': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _f64, _f64, _vp, _vp]),
     'gp_pair_dot': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
     'gp_dk_apply': (_int, [_vp, _i64, _i64, _vp, _f64, _vp, _i64, _i64, _vp, _vp]),
+    'gp_points_bbox': (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    'gp_sort_workspace_bytes': (_i64, [_i64]),
+    'gp_sort_keys_u64': (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
+    'gp_inverse_permutation': (_int, [_vp, _i64, _vp, _vp]),
+    'gp_scan_counts': (_int, [_vp, _i64, _vp, _vp]),
+    'gp_gather_rows': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     'gp_sytrd_workspace_bytes': (_i64, [_i64]),
     'gp_sytrd_f64': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'gp_stebz_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -123,11 +123,17 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
                                     _p(indptr), ctypes.byref(nnz), s)
     check(rc, 'gp_matern_sparse_count')
     # deterministic, spatially local order of the points (stable sort of Hilbert / Z-order keys) for the row-blocked operator
-    lo, hi = dev.host_f64(dpts.amin(dim=0).cpu().numpy()), dev.host_f64(dpts.amax(dim=0).cpu().numpy())
+    # (bounding box, stable radix sort: the library's own kernels, csrc/gp_index.cu)
+    box = numpy.empty(2 * d)
+    box_ws = torch.empty(148 * 2 * d + 2 * d, dtype=torch.float64, device='cuda')   # (ws holds the count pass's cell lists)
+    check(lib.gp_points_bbox(_p(dpts), n, d, dev.host_ptr(box), _p(box_ws), s), 'gp_points_bbox')
+    lo, hi = dev.host_f64(box[:d]), dev.host_f64(box[d:])
     keys = torch.empty(n, dtype=torch.int64, device='cuda')
     check(lib.gp_spatial_keys(_p(dpts), n, d, dev.host_ptr(lo), dev.host_ptr(hi), _p(keys), s), 'gp_spatial_keys')
-    order = torch.sort(keys, stable=True)[1].to(torch.int32)
-    del keys
+    order = torch.empty(n, dtype=torch.int32, device='cuda')
+    sort_ws = torch.empty(lib.gp_sort_workspace_bytes(n) // 8 + 8, dtype=torch.float64, device='cuda')
+    check(lib.gp_sort_keys_u64(_p(keys), n, 64, _p(order), _p(sort_ws), s), 'gp_sort_keys_u64')
+    del keys, sort_ws
     indices = torch.empty(nnz.value, dtype=torch.int32, device='cuda')
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
@@ -237,12 +243,11 @@ class SparseEngine(object):
     def _build_blocked(self, K, R):
         torch = dev.torch
         n = self.n
-        order = K.order.to(torch.int64)
+        s = dev.stream_ptr()
         inv = torch.empty(n, dtype=torch.int32, device='cuda')
-        inv[order] = torch.arange(n, dtype=torch.int32, device='cuda')
+        check(lib.gp_inverse_permutation(_p(K.order), n, _p(inv), s), 'gp_inverse_permutation')
         nrb = (n + R - 1) // R
         nblk = torch.empty(nrb, dtype=torch.int32, device='cuda')
-        s = dev.stream_ptr()
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
         check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), _p(flag), s),
               'gp_bcsr_count')
@@ -251,8 +256,8 @@ class SparseEngine(object):
             K.canonicalize()
             check(lib.gp_bcsr_count(R, n, _p(K.order), _p(inv), _p(K.indptr), _p(K.indices), _p(nblk), _p(flag), s),
                   'gp_bcsr_count')
-        bptr = torch.zeros(nrb + 1, dtype=torch.int64, device='cuda')
-        bptr[1:] = torch.cumsum(nblk, 0, dtype=torch.int64)
+        bptr = torch.empty(nrb + 1, dtype=torch.int64, device='cuda')
+        check(lib.gp_scan_counts(_p(nblk), nrb, _p(bptr), s), 'gp_scan_counts')
         total = int(bptr[-1].item())
         bidx = torch.empty(total, dtype=torch.int32, device='cuda')
         bvals = torch.empty(total * R, dtype=torch.float64, device='cuda')
@@ -263,7 +268,7 @@ class SparseEngine(object):
         self.R = R
         self.blocked = (bptr, bidx, bvals, bdvals)
         self.fill_ratio = total * R / float(max(K.nnz, 1))     # stored values per original nonzero (>= 1)
-        self.order, self.inv_order = order, inv.to(torch.int64)
+        self.order, self.inv_order = K.order, inv            # device int32 row maps of to_op / from_op
 
     # ---- plumbing ----------------------------------------------------------------------------------------------
     def _workspace(self, B, side=False):
@@ -291,11 +296,19 @@ class SparseEngine(object):
                                   _p(X_dev), B, _p(Y), dev.stream_ptr()), 'gp_csr_spmm')
         return Y
 
+    def _gather(self, X_dev, rmap):
+        X_dev = X_dev.contiguous()
+        Y = dev.torch.empty_like(X_dev)
+        B = X_dev.numel() // self.n
+        check(lib.gp_gather_rows(_p(X_dev), _p(rmap), self.n, B, _p(Y), dev.stream_ptr()), 'gp_gather_rows')
+        return Y
+
     def to_op(self, X_dev):
-        return X_dev if self.order is None else X_dev[self.order].contiguous()
+        """rows of an (n x B) block from the caller's order into operator order"""
+        return X_dev if self.order is None else self._gather(X_dev, self.order)
 
     def from_op(self, X_dev):
-        return X_dev if self.order is None else X_dev[self.inv_order].contiguous()
+        return X_dev if self.order is None else self._gather(X_dev, self.inv_order)
 
     def probes(self, first, B, out=None):
         torch = dev.torch

@@ -229,6 +229,21 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
                      void* stream);
 
+/* ---- index plumbing of the sparse operator build (csrc/gp_index.cu): own kernels instead of library sort / scan ------ */
+/* out_host[0..d) = column minima, out_host[d..2d) = column maxima of the device points; ws >= (148 * d * 2 + 2 * d) doubles;
+ * synchronises the stream */
+int gp_points_bbox(const double* points, int64_t n, int64_t d, double* out_host, void* ws, void* stream);
+/* stable LSD radix sort: order_out[i] = index of the i-th smallest key; keys_dev (low key_bits bits significant) is used as
+ * scratch. ws: gp_sort_workspace_bytes(n). Replaces the stable sort of the spatial keys (a CSR from the reference's generator,
+ * _generate_sparse_correlation.pyx:472-594, has no spatial order; this is the operator-internal permutation). */
+int64_t gp_sort_workspace_bytes(int64_t n);
+int gp_sort_keys_u64(unsigned long long* keys_dev, int64_t n, int key_bits, int* order_out, void* ws, void* stream);
+int gp_inverse_permutation(const int* order, int64_t n, int* inv, void* stream);
+/* offsets[0] = 0, offsets[i + 1] = counts[0] + ... + counts[i] */
+int gp_scan_counts(const int* counts, int64_t n, int64_t* offsets, void* stream);
+/* out[i][:] = in[map[i]][:] for rows of B doubles (in != out) */
+int gp_gather_rows(const double* in, const int* map, int64_t n, int64_t B, double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Symmetric eigenvalue path (imate_method = 'eigenvalue', the reference's default: _likelihood/likelihood.py:41,
  * _mixed_correlation/mixed_correlation.py:76-79 -> scipy.linalg.eigh(K, eigvals_only=True); :127-136,172-181,239-248 reduce

@@ -533,3 +533,55 @@ def test_sparse_grid_sweep(sparse_problem):
     K = generate_sparse_correlation(pts, numpy.array([0.03, 0.03]), 0.5, 0.01, device=True, with_derivative=True)
     ref = ProfileLikelihood.log_likelihood_and_gradient(z, X, MixedCorrelation(K, imate_method='slq', imate_options=opts), 20.0)
     assert numpy.allclose(G[1, 1], ref, rtol=1e-7, atol=0)
+
+
+@pytest.mark.parametrize('n,bits', [(1, 64), (31, 8), (1024, 62), (1025, 63), (5000, 20), (300001, 64), (1 << 20, 62),
+                                    (70000, 5)])
+def test_index_kernels_match_numpy(n, bits):
+    """csrc/gp_index.cu against numpy: stable radix argsort of 64-bit keys (odd and even pass counts, heavy duplicates),
+    inverse permutation, count scan, row gather, bounding box - all bit-exact (integer / copy / min-max work)."""
+    import ctypes
+    from gaussian_proc import _device as dev
+    torch = dev.require_cuda()
+    lib = dev.lib
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rng = numpy.random.RandomState(n % 9973 + bits)
+    keys = rng.randint(0, 1 << 62, size=n, dtype=numpy.int64).astype(numpy.uint64)
+    if bits < 64:
+        keys &= numpy.uint64((1 << bits) - 1)
+    if n > 4096:
+        keys[rng.randint(0, n, n // 3)] = keys[rng.randint(0, n, n // 3)]          # duplicates: stability matters
+    dkeys = torch.from_numpy(keys.view(numpy.int64).copy()).cuda()
+    order = torch.empty(n, dtype=torch.int32, device='cuda')
+    ws = torch.empty(lib.gp_sort_workspace_bytes(n) // 8 + 8, dtype=torch.float64, device='cuda')
+    s = dev.stream_ptr()
+    assert lib.gp_sort_keys_u64(P(dkeys), n, bits, P(order), P(ws), s) == 0
+    want = numpy.argsort(keys, kind='stable').astype(numpy.int32)
+    got = order.cpu().numpy()
+    assert (got == want).all()
+
+    inv = torch.empty(n, dtype=torch.int32, device='cuda')
+    assert lib.gp_inverse_permutation(P(order), n, P(inv), s) == 0
+    inv_want = numpy.empty(n, dtype=numpy.int32)
+    inv_want[want] = numpy.arange(n, dtype=numpy.int32)
+    assert (inv.cpu().numpy() == inv_want).all()
+
+    counts = rng.randint(0, 4000, size=n).astype(numpy.int32)
+    offs = torch.empty(n + 1, dtype=torch.int64, device='cuda')
+    assert lib.gp_scan_counts(P(torch.from_numpy(counts).cuda()), n, P(offs), s) == 0
+    assert (offs.cpu().numpy() == numpy.concatenate([[0], numpy.cumsum(counts, dtype=numpy.int64)])).all()
+
+    for B in (1, 7, 16):
+        X = rng.randn(n, B)
+        dX = torch.from_numpy(X).cuda()
+        Y = torch.empty_like(dX)
+        assert lib.gp_gather_rows(P(dX), P(order), n, B, P(Y), s) == 0
+        assert (Y.cpu().numpy() == X[want]).all()
+    assert lib.gp_gather_rows(P(dX), P(order), n, B, P(dX), s) == -1               # in place is refused
+
+    for d in (1, 2, 3, 8):
+        pts = rng.randn(n, d)
+        box = numpy.empty(2 * d)
+        bws = torch.empty(148 * 2 * d + 2 * d, dtype=torch.float64, device='cuda')
+        assert lib.gp_points_bbox(P(torch.from_numpy(pts).cuda()), n, d, dev.host_ptr(box), P(bws), s) == 0
+        assert (box[:d] == pts.min(axis=0)).all() and (box[d:] == pts.max(axis=0)).all()
