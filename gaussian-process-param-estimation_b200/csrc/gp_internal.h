@@ -36,4 +36,26 @@ int set_gemm_impl(int impl);   // 1 = TMA + mbarrier kernel (default), 0 = cp.as
 int profile_enable(int on);
 int profile_read(double* ms_sum, double* ms_union, double* flops, long long* launches);
 
+// ---- row-slab (multi-GPU) sparse operator: every rank maps its peers' arenas through CUDA IPC (csrc/gp_peer.cu) ------------
+constexpr int PEER_MAX = 8;         // ranks of one NVSwitch domain
+constexpr int PEER_SLOTS = 8;       // mailbox ring (a peer is never more than one exchange ahead; see peer_block_sum)
+constexpr int PEER_PAYLOAD = 256;   // doubles per (slot, rank): up to a 16 x 16 Gram block
+constexpr int PEER_VECS = 3;        // exchange vectors per arena (the SpMM inputs peers gather from)
+
+struct PeerComm {                   // one exchange, passed to the kernel by value
+    int rank, world;                // world <= 1: no exchange
+    unsigned long long seq;         // sequence number of this exchange (1, 2, ...), the same on every rank
+    double* mail[PEER_MAX];         // mail[p]: rank p's mailbox: payload[SLOTS][MAX][PAYLOAD] doubles, then flags[SLOTS][MAX] u64
+    int* err;                       // local flag: a wait timed out
+};
+struct PeerVec {                    // one exchange vector as mapped on this rank: base[p] = rank p's copy (its own rows)
+    const double* base[PEER_MAX];
+};
+struct PeerCtx;                     // host side (gp_peer.cu)
+PeerComm peer_next(PeerCtx* ctx);                  // the next exchange (advances the sequence number); world 1 without ctx
+PeerVec peer_vec(PeerCtx* ctx, int k);             // exchange vector k on every rank
+double* peer_local_vec(PeerCtx* ctx, int k);       // this rank's copy of exchange vector k
+int peer_world(const PeerCtx* ctx);
+int peer_barrier_launch(PeerCtx* ctx, cudaStream_t s);
+
 }  // namespace gp

@@ -7,6 +7,7 @@
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_internal.h"
+#include "gp_peer.cuh"
 
 namespace gp {
 
@@ -42,7 +43,8 @@ csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 template <int MODE>
 __global__ void __launch_bounds__(256)
 col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const double* Y, double* W,
-                 double* Z, const double* __restrict__ a, const double* __restrict__ b, double* partial) {
+                 double* Z, const double* __restrict__ a, const double* __restrict__ b, double* partial,
+                 double* Z2 = nullptr) {
     __shared__ double red[256];
     const int64_t stride = (int64_t)gridDim.x * 256;  // multiple of 32 >= B: a thread stays in one column
     const int c = threadIdx.x % B;
@@ -54,6 +56,7 @@ col_fused_kernel(int64_t total, int B, const double* __restrict__ X, const doubl
         } else if (MODE == 1) {
             double w = W[idx] - ac * X[idx] - bc * Y[idx];   // X = u_j, Y = u_{j-1}, Z = u_{j+1} (may alias Y)
             Z[idx] = w;
+            if (Z2) Z2[idx] = w;                              // row-slab operator: the copy the peers' SpMM gathers from
             acc += w * w;
         } else {
             Z[idx] += ac * X[idx];                            // Z = solution, X = p
@@ -99,16 +102,18 @@ col_partial_reduce_kernel(const double* __restrict__ partial, int nparts, int B,
 // op 4 (cg rr_new):     beta[c] = active ? sum/rr : 0; rr = sum; active &= rr > tol2*bb
 __global__ void __launch_bounds__(256)
 col_final_kernel(const double* __restrict__ partial, int nparts, int B, int op, double* out, double* s1, double* s2,
-                 double* s3, double tol2) {
+                 double* s3, double tol2, const __grid_constant__ PeerComm pc) {
     __shared__ double red[256];
     const int c = threadIdx.x % B, sl = threadIdx.x / B, nsl = 256 / B;
     double s = 0.0;
     for (int i = sl; i < nparts; i += nsl) s += partial[(int64_t)i * B + c];
     red[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x >= B) return;
     s = 0.0;
-    for (int k = 0; k < nsl; ++k) s += red[k * B + c];
+    if (threadIdx.x < B)
+        for (int k = 0; k < nsl; ++k) s += red[k * B + c];
+    s = peer_block_sum(pc, s, B);      // row-slab operator: the sum over the ranks' slabs (no-op on one GPU)
+    if (threadIdx.x >= B) return;
     if (op == 0) {
         out[c] = s;
     } else if (op == 1) {
@@ -338,11 +343,15 @@ bcsr_build_kernel(int n, const int* __restrict__ order, const int* __restrict__ 
 // Epilogue: Y = scale[c] (A X + eta X) (scale optional) and, with DOT, partial[cta][c] = sum over the CTA's 64 rows
 // of X[i][c] Y[i][c] (fixed order) - the Lanczos alpha / CG p^T A p reduction without another pass over the vectors.
 // H = 1: 8 x 1 row blocks; H = 2: 16 x 1 row blocks (two A fragments and two MMAs per gathered B fragment).
-template <int B, bool DOT, int H>
+// PEER (row-slab operator on several GPUs): the rows of this rank's slab; a block-column index carries the owner rank in its
+// top 4 bits and the row within the owner's slab below (gp_slab_encode_columns), and the gather goes to the owner's copy of
+// the exchange vector - local HBM for the own slab, a load over NVLink from the mapped arena of a peer for the halo.
+constexpr int PEER_SHIFT = 28;
+template <int B, bool DOT, int H, bool PEER = false>
 __global__ void __launch_bounds__(256, GP_SPMM_MINB)
 bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__ bidx, const double* __restrict__ bvals, int n,
                        double eta, const double* __restrict__ X, const double* __restrict__ scale, double* __restrict__ Y,
-                       double* __restrict__ partial) {
+                       double* __restrict__ partial, const __grid_constant__ PeerVec pv) {
     constexpr int NT = (B >= 8) ? B / 8 : 1;   // 8-column MMA tiles per step
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;     // DMMA.8x8x4 fragments: A[g][t], B[t][g], D[g][2t .. 2t+1]
@@ -359,7 +368,8 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     const int coff = (B >= 8) ? g * NT : (colok ? g : 0);
     const double* aptr = bvals + lane;          // A fragment order: element (row g, block-column t) at 4 g + t = lane
     auto load_x = [&](int col, double* x) {
-        const double* xr = X + (int64_t)col * B + coff;
+        const double* xr = PEER ? pv.base[(unsigned)col >> PEER_SHIFT] + (int64_t)(col & ((1 << PEER_SHIFT) - 1)) * B + coff
+                                : X + (int64_t)col * B + coff;
         if (NT == 1) {
             x[0] = colok ? *xr : 0.0;
         } else {
@@ -461,25 +471,28 @@ static int bcsr8_parts(int n) { return bcsr_parts(n, 8); }
 
 template <int B>
 static void bcsr8_spmm_launch_b(const SparseOp& A, double eta, const double* X, const double* scale, double* Y,
-                                double* partial, cudaStream_t s) {
+                                double* partial, cudaStream_t s, const PeerVec* pvp) {
     const int blocks = bcsr_parts(A.n, A.R);
-    if (A.R == 16) {
-        if (partial)
-            bcsr8_spmm_dmma_kernel<B, true, 2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
-        else
-            bcsr8_spmm_dmma_kernel<B, false, 2><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
-        return;
+    PeerVec pv = {};
+    if (pvp) pv = *pvp;
+#define GP_SPMM_LAUNCH(DOT, H, PEER) \
+    bcsr8_spmm_dmma_kernel<B, DOT, H, PEER><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial, pv)
+    if (pvp) {       // row-slab operator (16-row blocks only)
+        if (partial) GP_SPMM_LAUNCH(true, 2, true); else GP_SPMM_LAUNCH(false, 2, true);
+    } else if (A.R == 16) {
+        if (partial) GP_SPMM_LAUNCH(true, 2, false); else GP_SPMM_LAUNCH(false, 2, false);
+    } else {
+        if (partial) GP_SPMM_LAUNCH(true, 1, false); else GP_SPMM_LAUNCH(false, 1, false);
     }
-    if (partial)
-        bcsr8_spmm_dmma_kernel<B, true, 1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, partial);
-    else
-        bcsr8_spmm_dmma_kernel<B, false, 1><<<blocks, 256, 0, s>>>(A.ptr64, A.idx, A.val, A.n, eta, X, scale, Y, nullptr);
+#undef GP_SPMM_LAUNCH
 }
 
 // Y = scale (.) ((A + eta I) X); with `partial` also the per-column partial sums of X (.) Y: *nparts rows of B doubles
+// `pv` (row-slab operator): X is this rank's copy of the exchange vector (epilogue rows), the gathers go through pv
 static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y, cudaStream_t s,
-                const double* scale = nullptr, double* partial = nullptr, int* nparts = nullptr) {
+                const double* scale = nullptr, double* partial = nullptr, int* nparts = nullptr, const PeerVec* pv = nullptr) {
     const int n = A.n;
+    if (pv && A.R != 16) return -3;
     if (A.R == 1) {
         int blocks = (int)(((int64_t)n * 32 + 255) / 256);
         switch (B) {
@@ -499,12 +512,12 @@ static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y
         }
     } else if (A.R == 8 || A.R == 16) {
         switch (B) {
-            case 1: bcsr8_spmm_launch_b<1>(A, eta, X, scale, Y, partial, s); break;
-            case 2: bcsr8_spmm_launch_b<2>(A, eta, X, scale, Y, partial, s); break;
-            case 4: bcsr8_spmm_launch_b<4>(A, eta, X, scale, Y, partial, s); break;
-            case 8: bcsr8_spmm_launch_b<8>(A, eta, X, scale, Y, partial, s); break;
-            case 16: bcsr8_spmm_launch_b<16>(A, eta, X, scale, Y, partial, s); break;
-            case 32: bcsr8_spmm_launch_b<32>(A, eta, X, scale, Y, partial, s); break;
+            case 1: bcsr8_spmm_launch_b<1>(A, eta, X, scale, Y, partial, s, pv); break;
+            case 2: bcsr8_spmm_launch_b<2>(A, eta, X, scale, Y, partial, s, pv); break;
+            case 4: bcsr8_spmm_launch_b<4>(A, eta, X, scale, Y, partial, s, pv); break;
+            case 8: bcsr8_spmm_launch_b<8>(A, eta, X, scale, Y, partial, s, pv); break;
+            case 16: bcsr8_spmm_launch_b<16>(A, eta, X, scale, Y, partial, s, pv); break;
+            case 32: bcsr8_spmm_launch_b<32>(A, eta, X, scale, Y, partial, s, pv); break;
             default: return -2;
         }
         if (partial) *nparts = bcsr_parts(n, A.R);
@@ -517,15 +530,16 @@ static int spmm(const SparseOp& A, double eta, const double* X, int B, double* Y
 }
 
 // partial (nparts x B) -> scalar recurrence `op`; long lists go through col_partial_reduce_kernel into `scratch`
+// `px` (row-slab operator): the sums are all-reduced over the ranks inside the final kernel (peer_block_sum)
 static void col_final(const double* partial, int nparts, int B, int op, double* out, double* s1, double* s2, double* s3,
-                      double tol2, double* scratch, cudaStream_t s) {
+                      double tol2, double* scratch, cudaStream_t s, PeerCtx* px = nullptr) {
     if (nparts > 1024) {
         const int nb = (nparts + 255) / 256;
         col_partial_reduce_kernel<<<nb, 256, 0, s>>>(partial, nparts, B, scratch);
-        col_final_kernel<<<1, 256, 0, s>>>(scratch, nb, B, op, out, s1, s2, s3, tol2);
+        col_final_kernel<<<1, 256, 0, s>>>(scratch, nb, B, op, out, s1, s2, s3, tol2, peer_next(px));
         GP_COUNT(2);
     } else {
-        col_final_kernel<<<1, 256, 0, s>>>(partial, nparts, B, op, out, s1, s2, s3, tol2);
+        col_final_kernel<<<1, 256, 0, s>>>(partial, nparts, B, op, out, s1, s2, s3, tol2, peer_next(px));
         GP_COUNT(1);
     }
 }
@@ -710,15 +724,27 @@ int64_t gp_krylov_workspace_bytes(int64_t n, int64_t B) {
 }
 
 // out[c] = sum_i X[i][c] * Y[i][c]
-int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream) {
+static int col_dot_run(PeerCtx* px, const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws,
+                       void* stream) {
     if (!X || !Y || !out_dev || !ws || B <= 0 || B > 32 || (32 % B)) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     double* partial = (double*)ws;
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(n * B, (int)B, X, Y, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, (int)B, 0, out_dev, nullptr, nullptr, nullptr, 0.0);
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, (int)B, 0, out_dev, nullptr, nullptr, nullptr, 0.0, peer_next(px));
     GP_COUNT(2);
     GP_LAUNCH_CHECK();
     return 0;
+}
+
+int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* out_dev, void* ws, void* stream) {
+    return col_dot_run(nullptr, X, Y, n, B, out_dev, ws, stream);
+}
+
+// row-slab operator: X, Y are this rank's rows; out = the dot products over ALL rows (identical on every rank)
+int gp_slab_col_dot(void* peer, const double* X, const double* Y, int64_t nloc, int64_t B, double* out_dev, void* ws,
+                    void* stream) {
+    if (!peer) return -1;
+    return col_dot_run((PeerCtx*)peer, X, Y, nloc, B, out_dev, ws, stream);
 }
 
 }  // extern "C"
@@ -731,8 +757,14 @@ int gp_col_dot(const double* X, const double* Y, int64_t n, int64_t B, double* o
 // so a step is two passes over the vectors (the SpMM and one fused update) and four launches.
 // With `basis` (m x n x B doubles) the vectors u_0 .. u_{m-1} are kept: q_j = u_j / beta_{j-1} (beta_{-1} = ||v||) is the
 // Krylov basis from which the caller forms (K + eta I)^-1 v = ||v|| Q T^-1 e_1 without a separate CG solve.
+// Row-slab operator (`px`): A holds this rank's rows, every vector is the rank's slab, the reductions are summed over the
+// ranks inside col_final_kernel, and u_j additionally lives in exchange vector (j mod 2) of the rank's arena - the copy the
+// other ranks' SpMM gathers its halo rows from. Hazards: u_{j+1} is written by the update kernel BEFORE this rank
+// contributes to the beta_j exchange, and a peer starts its SpMM j+1 only after that exchange (read after write); the
+// buffer it overwrites held u_{j-1}, which the peers finished reading before they contributed to alpha_{j-1} (write after
+// read). No barrier beyond the two reductions a Lanczos step has anyway.
 static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B, int64_t m, double* alpha_dev,
-                       double* beta_dev, double* basis, void* ws, void* stream) {
+                       double* beta_dev, double* basis, void* ws, void* stream, PeerCtx* px = nullptr) {
     const int64_t n = A.n;
     if (!A.idx || !A.val || !V || !alpha_dev || !beta_dev || !ws || n <= 0 || m <= 0) return -1;
     if (B <= 0 || B > 32 || (32 % B)) return -2;
@@ -747,6 +779,12 @@ static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B
     double* partial = (double*)(base + 4 * vb);
     double* scratch = partial + partial_rows(n) * 32;
     double* sc = (double*)(base + 4 * vb + partial_bytes(n));
+    double* E[2] = {nullptr, nullptr};      // row-slab operator: the exchange copies of u_j (j even / odd)
+    PeerVec pv[2];
+    if (px) {
+        for (int k = 0; k < 2; ++k) { E[k] = peer_local_vec(px, k); pv[k] = peer_vec(px, k); }
+        if (!basis) { U0 = E[0]; U1 = E[1]; }      // no kept vectors: the two-buffer rotation runs in the exchange vectors
+    }
     double* st = sc;           // s_cur, s_prev (+32), beta_prev (+64)
     double* a1 = sc + 96;      // alpha_j s_j
     double* b1 = sc + 128;     // beta_{j-1} s_{j-1}
@@ -757,20 +795,23 @@ static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B
         return (j & 1) ? U1 : U0;
     };
     GP_CUDA_CHECK(cudaMemcpyAsync(vec(0), V, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
+    if (px && basis) GP_CUDA_CHECK(cudaMemcpyAsync(E[0], V, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
     GP_CUDA_CHECK(cudaMemsetAsync(U1, 0, sizeof(double) * total, s));
     GP_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(double) * 96, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, V, V, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, tmp, st, nullptr, nullptr, 0.0);
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, tmp, st, nullptr, nullptr, 0.0, peer_next(px));
     GP_CUDA_CHECK(cudaMemsetAsync(st + 32, 0, sizeof(double) * 64, s));    // s_prev = beta_prev = 0 for the first step
     GP_COUNT(2);
     for (int64_t j = 0; j < m; ++j) {
         double* u = vec(j);
         int nparts = 0;
-        int rc = spmm(A, eta, u, Bc, W, s, st, partial, &nparts);
+        int rc = spmm(A, eta, px ? E[j & 1] : u, Bc, W, s, st, partial, &nparts, px ? &pv[j & 1] : nullptr);
         if (rc) return rc;
-        col_final(partial, nparts, Bc, 1, alpha_dev + j * B, st, a1, b1, 0.0, scratch, s);
-        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, u, vec(j - 1), W, vec(j + 1), a1, b1, partial);
-        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, beta_dev + j * B, st, nullptr, nullptr, 0.0);
+        col_final(partial, nparts, Bc, 1, alpha_dev + j * B, st, a1, b1, 0.0, scratch, s, px);
+        col_fused_kernel<1><<<RED_PARTS, 256, 0, s>>>(total, Bc, u, vec(j - 1), W, vec(j + 1), a1, b1, partial,
+                                                      (px && basis) ? E[(j + 1) & 1] : nullptr);
+        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 2, beta_dev + j * B, st, nullptr, nullptr, 0.0,
+                                           peer_next(px));
         GP_COUNT(2);
     }
     GP_LAUNCH_CHECK();
@@ -780,8 +821,10 @@ static int lanczos_run(const SparseOp& A, double eta, const double* V, int64_t B
 // Batched CG for (K + eta I) X = R0, all B columns at once, stop per column at ||r|| <= tol ||b|| (the reference's
 // scipy cg tol=1e-6, atol=0). X: in = initial guess is ignored (zero start), out = solution. R0 is overwritten.
 // iters_host receives the number of iterations performed. Returns 0, or 1 if maxiter was hit before convergence.
+// Row-slab operator (`px`): the direction p lives in exchange vector 2 of the rank's arena; it is rewritten AFTER the last
+// reduction of an iteration, so a cross-GPU barrier follows the direction kernel (the peers' next SpMM gathers from it).
 static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t B, double tol, int64_t maxiter,
-                  int64_t* iters_host, void* ws, void* stream) {
+                  int64_t* iters_host, void* ws, void* stream, PeerCtx* px = nullptr) {
     const int64_t n = A.n;
     if (!A.idx || !A.val || !R0 || !X || !ws || n <= 0) return -1;
     if (B <= 0 || B > 32 || (32 % B)) return -2;
@@ -790,7 +833,9 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     const int64_t total = n * B;
     char* base = (char*)ws;
     size_t vb = al256(sizeof(double) * total);
-    double* Pd = (double*)base;
+    double* Pd = px ? peer_local_vec(px, 2) : (double*)base;
+    PeerVec pv;
+    if (px) pv = peer_vec(px, 2);
     double* AP = (double*)(base + vb);
     double* partial = (double*)(base + 4 * vb);
     double* scratch = partial + partial_rows(n) * 32;
@@ -802,7 +847,8 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     GP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(double) * 32, s));
     GP_CUDA_CHECK(cudaMemcpyAsync(Pd, R0, sizeof(double) * total, cudaMemcpyDeviceToDevice, s));
     col_fused_kernel<0><<<RED_PARTS, 256, 0, s>>>(total, Bc, R0, R0, nullptr, nullptr, nullptr, nullptr, partial);
-    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 0, rr, nullptr, nullptr, nullptr, 0.0);
+    // (the exchange of ||r0||^2 also orders the copy of p_0 above before the peers' first SpMM)
+    col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 0, rr, nullptr, nullptr, nullptr, 0.0, peer_next(px));
     GP_CUDA_CHECK(cudaMemcpyAsync(bb, rr, sizeof(double) * 32, cudaMemcpyDeviceToDevice, s));
     double ones[32], act[32];
     GP_CUDA_CHECK(cudaMemcpyAsync(ones, rr, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
@@ -815,13 +861,14 @@ static int cg_run(const SparseOp& A, double eta, double* R0, double* X, int64_t 
     const int check_every = 8;
     while (it < maxiter) {
         int nparts = 0;
-        int rc = spmm(A, eta, Pd, Bc, AP, s, nullptr, partial, &nparts);
+        int rc = spmm(A, eta, Pd, Bc, AP, s, nullptr, partial, &nparts, px ? &pv : nullptr);
         if (rc) return rc;
-        col_final(partial, nparts, Bc, 3, alpha, rr, active, flag, 0.0, scratch, s);
+        col_final(partial, nparts, Bc, 3, alpha, rr, active, flag, 0.0, scratch, s, px);
         col_fused_kernel<2><<<RED_PARTS, 256, 0, s>>>(total, Bc, Pd, AP, R0, X, alpha, nullptr, partial);
-        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 4, beta, rr, active, bb, tol2);
+        col_final_kernel<<<1, 256, 0, s>>>(partial, RED_PARTS, Bc, 4, beta, rr, active, bb, tol2, peer_next(px));
         cg_direction_kernel<<<eb, 256, 0, s>>>(total, Bc, R0, beta, Pd);
         GP_COUNT(3);
+        if (px) { if (int rb = peer_barrier_launch(px, s)) return rb; }
         ++it;
         if (it % check_every == 0 || it == maxiter) {
             double brk = 0.0;
@@ -879,6 +926,78 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws, void* stream) {
     if (!bptr || n <= 0 || n > INT32_MAX || (R != 8 && R != 16)) return -1;
     return cg_run(bcsr_op(R, bptr, bidx, bvals, n), eta, R0, X, B, tol, maxiter, iters_host, ws, stream);
+}
+
+// ---- row-slab operator on several GPUs (one process per GPU, peers' arenas mapped: gp_peer_*) ---------------------------------
+// Every rank holds the 16-row blocks of ITS rows [rank * slab, ...) of the (spatially ordered) operator; bidx carries
+// (owner << 28 | row within the owner's slab). Vectors are the rank's rows; results of reductions are identical on all ranks.
+
+__global__ void encode_columns_kernel(int* __restrict__ bidx, int64_t total, int slab, int rank, unsigned long long* halo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < total;
+    int owner = rank;
+    if (ok) {
+        const int col = bidx[i];
+        owner = col / slab;
+        bidx[i] = (owner << PEER_SHIFT) | (col - owner * slab);
+    }
+    const unsigned remote = __ballot_sync(0xffffffffu, ok && owner != rank);
+    if (halo && (threadIdx.x & 31) == 0 && remote) atomicAdd(halo, (unsigned long long)__popc(remote));
+}
+
+// global operator-space column -> (owner, local row) for uniform slabs of `slab` rows (slab < 2^28, owner < 8);
+// halo_host (optional): the number of block-columns owned by another rank than `rank` (synchronises the stream)
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t* halo_host, void* stream) {
+    if (!bidx || total < 0 || slab <= 0 || slab >= (1 << PEER_SHIFT) || rank < 0 || rank >= PEER_MAX) return -1;
+    if (halo_host) *halo_host = 0;
+    if (total == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* cnt = nullptr;
+    if (halo_host) {
+        GP_CUDA_CHECK(cudaMallocAsync((void**)&cnt, sizeof(unsigned long long), s));
+        GP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+    }
+    encode_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bidx, total, (int)slab, (int)rank, cnt);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    if (halo_host) {
+        unsigned long long h = 0;
+        GP_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+        GP_CUDA_CHECK(cudaFreeAsync(cnt, s));
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+        *halo_host = (int64_t)h;
+    }
+    return 0;
+}
+
+// Y = (K + eta I) X restricted to this rank's rows. X (nloc x B, this rank's rows) is first copied into exchange vector 2;
+// a barrier before (every rank's copy is in place) and after (nobody overwrites it while a peer still gathers) the SpMM.
+int gp_slab_spmm(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                 const double* X, int64_t B, double* Y, void* stream) {
+    PeerCtx* px = (PeerCtx*)peer;
+    if (!px || !bptr || !bidx || !bvals || !X || !Y || nloc <= 0 || nloc > INT32_MAX) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* E = peer_local_vec(px, 2);
+    PeerVec pv = peer_vec(px, 2);
+    GP_CUDA_CHECK(cudaMemcpyAsync(E, X, sizeof(double) * nloc * B, cudaMemcpyDeviceToDevice, s));
+    if (int rc = peer_barrier_launch(px, s)) return rc;
+    if (int rc = spmm(bcsr_op(16, bptr, bidx, bvals, nloc), eta, E, (int)B, Y, s, nullptr, nullptr, nullptr, &pv)) return rc;
+    return peer_barrier_launch(px, s);
+}
+
+int gp_slab_lanczos(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws,
+                    void* stream) {
+    if (!peer || !bptr || nloc <= 0 || nloc > INT32_MAX) return -1;
+    return lanczos_run(bcsr_op(16, bptr, bidx, bvals, nloc), eta, V, B, m, alpha_dev, beta_dev, basis_dev, ws, stream,
+                       (PeerCtx*)peer);
+}
+
+int gp_slab_cg_solve(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                     double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
+                     void* stream) {
+    if (!peer || !bptr || nloc <= 0 || nloc > INT32_MAX) return -1;
+    return cg_run(bcsr_op(16, bptr, bidx, bvals, nloc), eta, R0, X, B, tol, maxiter, iters_host, ws, stream, (PeerCtx*)peer);
 }
 
 }  // extern "C"

@@ -81,6 +81,20 @@ SIGNATURES = {
     'gp_inverse_permutation': (_int, [_vp, _i64, _vp, _vp]),
     'gp_scan_counts': (_int, [_vp, _i64, _vp, _vp]),
     'gp_gather_rows': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    'gp_peer_handle_bytes': (_i64, []),
+    'gp_peer_create': (_vp, [_i64, _i64, _i64]),
+    'gp_peer_handle': (_int, [_vp, _vp]),
+    'gp_peer_connect': (_int, [_vp, _vp]),
+    'gp_peer_destroy': (_int, [_vp]),
+    'gp_peer_vec': (_vp, [_vp, _i64]),
+    'gp_peer_barrier': (_int, [_vp, _vp]),
+    'gp_peer_allreduce': (_int, [_vp, _vp, _i64, _vp]),
+    'gp_peer_error': (_int, [_vp, _vp]),
+    'gp_slab_encode_columns': (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    'gp_slab_spmm': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
+    'gp_slab_col_dot': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'gp_slab_lanczos': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'gp_slab_cg_solve': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _f64, _i64, _vp, _vp, _vp]),
     'gp_sytrd_workspace_bytes': (_i64, [_i64]),
     'gp_sytrd_f64': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'gp_stebz_f64': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -52,7 +52,13 @@ class MixedCorrelation(object):
             if self.imate_options.pop('probe_split', False):
                 from .._distributed import rank_world
                 probe_range = rank_world()
-            self.engine = SparseEngine(K, imate_method, self.imate_options, probe_range=probe_range)
+            if self.imate_options.pop('row_slabs', False):
+                # ONE evaluation on all GPUs of the group: this rank holds a slab of the operator's rows; halo rows and
+                # reductions cross NVLink inside the kernels (gaussian_proc/_slab.py)
+                from .._slab import SlabSparseEngine
+                self.engine = SlabSparseEngine(K, imate_method, self.imate_options)
+            else:
+                self.engine = SparseEngine(K, imate_method, self.imate_options, probe_range=probe_range)
             self.K = self.engine.K
         else:
             if imate_method not in _DENSE_METHODS:

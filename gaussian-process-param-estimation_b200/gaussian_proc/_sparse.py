@@ -216,6 +216,7 @@ class SparseEngine(object):
             K = DeviceCSR.from_scipy(K)
         self.K = K
         self.n = K.n
+        self.rows = K.n            # rows of the vectors this engine works on (a slab of n on the row-slab engine, _slab.py)
         self.method = imate_method
         self.opt = dict(DEFAULTS)
         self.opt.update(imate_options or {})
@@ -277,7 +278,7 @@ class SparseEngine(object):
         torch = dev.torch
         key = ('side', B) if side else B
         if key not in self._ws:
-            self._ws[key] = torch.empty(lib.gp_krylov_workspace_bytes(self.n, B) // 8 + 8, dtype=torch.float64, device='cuda')
+            self._ws[key] = torch.empty(lib.gp_krylov_workspace_bytes(self.rows, B) // 8 + 8, dtype=torch.float64, device='cuda')
         return self._ws[key]
 
     def spmm(self, eta, X_dev, derivative=False):
@@ -312,9 +313,9 @@ class SparseEngine(object):
 
     def probes(self, first, B, out=None):
         torch = dev.torch
-        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda') if out is None else out
+        V = torch.empty((self.rows, B), dtype=torch.float64, device='cuda') if out is None else out
         rmap = self.K.order if self.order is not None else None
-        check(lib.gp_rademacher(_p(V), self.n, B, int(self.opt['seed']), int(first), _p(rmap) if rmap is not None else None,
+        check(lib.gp_rademacher(_p(V), self.rows, B, int(self.opt['seed']), int(first), _p(rmap) if rmap is not None else None,
                                 dev.stream_ptr()), 'gp_rademacher')
         return V
 
@@ -369,7 +370,7 @@ class SparseEngine(object):
         if not hasattr(self, '_side_stream'):
             self._side_stream = torch.cuda.Stream()
         # every buffer is allocated on the main stream; the side stream only runs kernels on them
-        V = torch.empty((self.n, B), dtype=torch.float64, device='cuda')
+        V = torch.empty((self.rows, B), dtype=torch.float64, device='cuda')
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda')
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda')
         basis = self._new_basis(m, B) if with_dk else None
@@ -418,7 +419,7 @@ class SparseEngine(object):
         return ent, 0.0
 
     def _new_basis(self, m, B):
-        return dev.torch.empty((m, self.n, B), dtype=dev.torch.float64, device='cuda')
+        return dev.torch.empty((m, self.rows, B), dtype=dev.torch.float64, device='cuda')
 
     def _slq_samples(self, eta, first, B, with_dk=False):
         """Per-probe quadratures [log, 1/x, 1/x^2] * n for probes first .. first+B-1. With ``with_dk`` a fourth column:
@@ -445,7 +446,7 @@ class SparseEngine(object):
             if resid <= float(self.opt['cg_tol']):
                 U = torch.empty_like(V)
                 cd = torch.from_numpy(coef).cuda()
-                check(lib.gp_block_combine(_p(ent['basis']), self.n, B, m, _p(cd), _p(U), dev.stream_ptr()),
+                check(lib.gp_block_combine(_p(ent['basis']), self.rows, B, m, _p(cd), _p(U), dev.stream_ptr()),
                       'gp_block_combine')
                 self.last_dk_solver = 'lanczos'
             else:
@@ -490,7 +491,7 @@ class SparseEngine(object):
             return self.solve_dev(eta, Rop.clone())
         S = torch.empty_like(Rop)
         cd = torch.from_numpy(coef).cuda()
-        check(lib.gp_block_combine(_p(ent['basis']), self.n, B, m, _p(cd), _p(S), dev.stream_ptr()), 'gp_block_combine')
+        check(lib.gp_block_combine(_p(ent['basis']), self.rows, B, m, _p(cd), _p(S), dev.stream_ptr()), 'gp_block_combine')
         self.last_rhs_solver = 'lanczos'
         return S
 

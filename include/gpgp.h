@@ -229,6 +229,38 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
                      void* stream);
 
+/* ---- row-slab sparse operator on several GPUs (csrc/gp_peer.cu, gp_sparse_la.cu) ------------------------------------------
+ * One process per GPU. The reference evaluates one sparse likelihood on one host (imate SLQ + scipy CG over the whole matrix,
+ * gaussian_proc/_mixed_correlation/mixed_correlation.py:193-209, 263-299); here the rows of the (spatially ordered) operator
+ * are cut into contiguous slabs, one per GPU. Each rank allocates an ARENA (mailboxes + 3 exchange vectors), exports it as a
+ * CUDA IPC handle (gp_peer_handle), receives the handles of its peers through the caller's process group and maps them
+ * (gp_peer_connect). Kernels then gather halo rows of the Krylov vectors straight from the owner's arena over NVLink and sum
+ * the Lanczos / CG reductions by pushing partial sums into every rank's mailbox - no library collective on the path. */
+int64_t gp_peer_handle_bytes(void);
+void* gp_peer_create(int64_t rank, int64_t world, int64_t nloc_max);      /* world <= 8; NULL on failure */
+int gp_peer_handle(void* peer, unsigned char* handle_out);
+int gp_peer_connect(void* peer, const unsigned char* handles);            /* world x gp_peer_handle_bytes(), rank-major */
+int gp_peer_destroy(void* peer);
+double* gp_peer_vec(void* peer, int64_t k);                               /* this rank's exchange vector k (0..2) */
+int gp_peer_barrier(void* peer, void* stream);                            /* cross-GPU barrier in stream order */
+int gp_peer_allreduce(void* peer, double* values_dev, int64_t count, void* stream);   /* count <= 256, in place, rank order */
+int gp_peer_error(void* peer, void* stream);                              /* 1: a wait timed out (ranks diverged) */
+/* bidx: global operator-space column -> (owner << 28 | row within the owner's slab) for uniform slabs of `slab` rows;
+ * halo_host (optional) receives the number of block-columns owned by another rank (the rows gathered over NVLink) */
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t* halo_host, void* stream);
+/* The drivers below take the 16-row blocks of this rank's rows (gp_bcsr_count / gp_bcsr_fill on order + first row) with
+ * encoded columns; vectors are the rank's rows (nloc x B); alpha, beta, dots are identical on every rank. */
+int gp_slab_spmm(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                 const double* X, int64_t B, double* Y, void* stream);
+int gp_slab_col_dot(void* peer, const double* X, const double* Y, int64_t nloc, int64_t B, double* out_dev, void* ws,
+                    void* stream);
+int gp_slab_lanczos(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                    const double* V, int64_t B, int64_t m, double* alpha_dev, double* beta_dev, double* basis_dev, void* ws,
+                    void* stream);
+int gp_slab_cg_solve(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
+                     double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
+                     void* stream);
+
 /* ---- index plumbing of the sparse operator build (csrc/gp_index.cu): own kernels instead of library sort / scan ------ */
 /* out_host[0..d) = column minima, out_host[d..2d) = column maxima of the device points; ws >= (148 * d * 2 + 2 * d) doubles;
  * synchronises the stream */

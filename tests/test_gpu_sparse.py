@@ -585,3 +585,23 @@ def test_index_kernels_match_numpy(n, bits):
         bws = torch.empty(148 * 2 * d + 2 * d, dtype=torch.float64, device='cuda')
         assert lib.gp_points_bbox(P(torch.from_numpy(pts).cuda()), n, d, dev.host_ptr(box), P(bws), s) == 0
         assert (box[:d] == pts.min(axis=0)).all() and (box[d:] == pts.max(axis=0)).all()
+
+
+def test_row_slab_engine_on_one_rank_equals_sparse_engine(sparse_problem):
+    """gaussian_proc/_slab.py with a group of one: the peer-gather SpMM (owner-encoded block columns, exchange vectors in the
+    arena), the slab Lanczos / CG drivers and the Gram all-reduce entry run on this GPU and must reproduce SparseEngine
+    (same kernels apart from the gather address; the multi-rank check is tools/gpu_check_sparse_slab.py under torchrun)."""
+    from gaussian_proc._sparse import SparseEngine
+    from gaussian_proc._slab import SlabSparseEngine, slab_geometry
+    pts, z, X, K = sparse_problem
+    opts = {'seed': 3, 'lanczos_degree': 40, 'overlap': False}
+    one = SparseEngine(K, 'slq', dict(opts))
+    slab = SlabSparseEngine(K, 'slq', dict(opts), rank=0, world=1)
+    assert slab.rows == K.n and slab.halo_fraction == 0.0
+    assert slab_geometry(K.n, 1, 0)[1:] == (0, K.n)
+    f1 = one.fused(2.0, X, z, cubic=True)
+    f2 = slab.fused(2.0, X, z, cubic=True)
+    assert numpy.max(numpy.abs(f1 - f2) / numpy.maximum(numpy.abs(f1), 1e-300)) <= 1e-12
+    y = numpy.random.RandomState(0).randn(K.n, 3)
+    assert numpy.max(numpy.abs(one.solve(2.0, y) - slab.solve(2.0, y))) <= 1e-12 * numpy.abs(y).max()
+    assert numpy.max(numpy.abs(one.matmul(y) - slab.matmul(y))) <= 1e-12 * numpy.abs(y).max()

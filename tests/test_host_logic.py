@@ -326,3 +326,20 @@ def test_sparse_engine_host_helpers():
         assert dev.host_key(b) != k1
     assert dev.host_key(a.copy()) == k1            # same content, another object: same device copy can be reused
     assert dev.host_key(numpy.zeros((0, 3)))[0] == (0, 3)
+
+
+def test_row_slab_geometry_covers_every_row_once():
+    """gaussian_proc/_slab.py: uniform slabs of 16-row blocks; the ranks' row ranges tile [0, n) (last slab may be short)."""
+    from gaussian_proc._slab import slab_geometry
+    for n in (16, 17, 3000, 131072, 2 ** 20, 2 ** 20 + 5):
+        for world in (1, 2, 3, 4, 8):
+            geo = [slab_geometry(n, world, r) for r in range(world)]
+            slab = geo[0][0]
+            assert slab % 16 == 0 and slab < 2 ** 28 and all(g[0] == slab for g in geo)
+            assert geo[0][1] == 0 and geo[-1][2] == n
+            assert all(geo[r][2] == geo[r + 1][1] for r in range(world - 1))
+            assert all(g[2] - g[1] <= slab for g in geo)
+            # owner / local row of a global row, as gp_slab_encode_columns computes it
+            rows = numpy.array([0, n // 3, n - 1])
+            owner = rows // slab
+            assert all(geo[o][1] <= r < geo[o][2] for o, r in zip(owner, rows))
