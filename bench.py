@@ -522,6 +522,35 @@ def sharded_measurements(world, rank):
         'num_samples': ns_split, 'loglik_grad': r_split,
         'rel_diff_vs_unsplit': [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(r_split, r_single)],
         'collective': 'all_reduce of (count, failed, sum, sum of squares) per estimator round'}
+    # the same evaluation with the ROWS of the operator cut into one slab per GPU (gaussian_proc/_slab.py): generation, build
+    # and every Krylov vector are 1/N per rank; halo rows of the SpMM input are loaded from the owner's memory over NVLink and
+    # the Lanczos / CG reductions are summed inside the reduction kernels through peer mailboxes (no library collective)
+    def slab_eval():
+        Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True, row_slab=(rank, world))
+        o = dict(opts)
+        o['row_slabs'] = True
+        Km = MixedCorrelation(Kc, imate_method='slq', imate_options=o)
+        r = ProfileLikelihood.log_likelihood_and_gradient(zs, Xs, Km, 10.0)
+        e = Km.engine
+        return [float(v) for v in r], (e.halo_blocks, e.halo_rows, e.total_blocks, e.rows)
+
+    try:
+        slab_eval()
+        (r_slab, halo), ms_slab = _timed_max_ms(slab_eval, world)
+        out['C4_sparse_n1M_row_slabs'] = {
+            'workload': 'configs[3]: ONE loglik+grad at n=2^20 (nu=0.5, rho=0.005, density=1e-3, eta=10) with the operator '
+                        'rows in %d slabs, one per GPU: slab generation + slab build + CG for [X z] + SLQ / Hutchinson' % world,
+            'scaling': 'strong', 'seconds': ms_slab * 1e-3, 'evals_per_s': 1e3 / ms_slab,
+            'seconds_one_gpu_same_run': ms_single * 1e-3, 'speedup_vs_one_gpu': ms_single / ms_slab,
+            'loglik_grad': r_slab,
+            'rel_diff_vs_one_gpu': [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(r_slab, r_single)],
+            'rows_per_gpu': int(halo[3]), 'halo_fraction_of_block_columns': halo[0] / float(max(halo[2], 1)),
+            'nvlink_bytes_per_spmm_B16_rank0': int(halo[0]) * 16 * 8,
+            'halo_algorithmic_bytes_B16_rank0': int(halo[1]) * 16 * 8,
+            'exchange': 'halo rows: loads from the owner GPU inside the SpMM kernel (CUDA IPC mapping, NVLink); reductions: '
+                        'in-kernel sum through per-rank mailboxes, 2 per Lanczos step / 3 per CG iteration'}
+    except Exception as e:  # noqa: BLE001 -- the other legs must still print
+        out['C4_sparse_n1M_row_slabs'] = {'error': repr(e)[:300]}
     rh, et = numpy.linspace(0.004, 0.006, 8), numpy.logspace(1, 3, 16)
     Gs, ms = _timed_max_ms(lambda: likelihood_grid(sp, zs, Xs, 0.5, rh, et, sparse=True, density=1e-3, imate_options=opts), world)
     out['C4_sparse_sweep_n1M'] = {'workload': 'configs[3] sweep: n=2^20, 8 rho x 16 eta = 128 cells, one CSR + operator per rho',

@@ -203,6 +203,10 @@ struct SparseParams {
     double scale[8];
     MaternParams mp;
     int d, n;
+    // row filter of the row-slab engine (one slab of the ordered operator per GPU): only rows i with
+    // row_first <= row_pos[i] < row_last are generated, the others stay empty. row_pos == nullptr: every row.
+    const int* row_pos;
+    int row_first, row_last;
 };
 
 // reference arithmetic: divide-then-square, k-ordered sum, IEEE sqrt (_kernels.pyx:130-136)
@@ -233,6 +237,13 @@ sparse_rows_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_sta
     const int wpos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wpos >= sp.n) return;
     const int i = sorted_idx[wpos];
+    if (sp.row_pos) {
+        const int pos = sp.row_pos[i];
+        if (pos < sp.row_first || pos >= sp.row_last) {      // another rank's row
+            if (PASS == 0 && lane == 0) devcount[i] = 0;
+            return;
+        }
+    }
     double pi[8];
     for (int k = 0; k < sp.d; ++k) pi[k] = sorted_pts[(int64_t)wpos * sp.d + k];
     int cc[SMAXD] = {0, 0, 0};
@@ -481,6 +492,8 @@ static int make_params(int64_t n, int64_t d, const double* scale_host, double nu
     sp->band = 8.0 * 2.220446049250313e-16 * fabs(tau);
     sp->d = (int)d;
     sp->n = (int)n;
+    sp->row_pos = nullptr;
+    sp->row_first = sp->row_last = 0;
     for (int k = 0; k < d; ++k) sp->scale[k] = scale_host[k];
     sp->mp.nu = nu;
     sp->mp.coef = 0.0; sp->mp.sq2nu = 0.0;
@@ -615,8 +628,11 @@ int gp_kernel_threshold(int64_t n, int64_t d, double density, const double* scal
 
 int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d) { return (int64_t)carve_sparse(nullptr, n, d).total; }
 
-int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
-                           double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream) {
+}  // extern "C"
+
+static int sparse_count_impl(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                             double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream,
+                             const int* row_pos, int64_t row_first, int64_t row_last) {
     if (!points || !points_host || !scale_host || !ws || !indptr_dev || !nnz_host || n <= 0 || d <= 0 || d > 8 || n > INT32_MAX)
         return -1;
     cudaStream_t s = (cudaStream_t)stream;
@@ -642,6 +658,9 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     SparseParams sp;
     CellGrid g;
     make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
+    sp.row_pos = row_pos;
+    sp.row_first = (int)row_first;
+    sp.row_last = (int)row_last;
     GP_CUDA_CHECK(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * (g.ncells + 1), s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.border_cnt, 0, sizeof(int) * 4, s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int) * 4, s));
@@ -732,6 +751,13 @@ int gp_matern_sparse_count(const double* points, const double* points_host, int6
     return 0;
 }
 
+extern "C" {
+
+int gp_matern_sparse_count(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                           double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream) {
+    return sparse_count_impl(points, points_host, n, d, scale_host, nu, tau, ws, indptr_dev, nnz_host, stream, nullptr, 0, 0);
+}
+
 // Space-filling-curve keys of the points over their bounding box (2-D: Hilbert index, 31 bits per coordinate; otherwise
 // Z-order / Morton over the first min(d, 3) coordinates, 63 / min(d, 3) bits each): a stable sort by this key gives a deterministic, spatially local ordering of the points. The sparse operator
 // uses it internally (row-blocked form, gp_bcsr_*): consecutive rows then have nearly identical patterns.
@@ -783,9 +809,12 @@ int gp_csr_sort_rows(int64_t n, const int* indptr_dev, int* indices_dev, double*
     return sort_rows_run(n, indptr_dev, indices_dev, data_dev, ddata_dev, flags_dev, (cudaStream_t)stream);
 }
 
-int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
-                          double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
-                          double* ddata_dev, int sort_rows, void* stream) {
+}  // extern "C"
+
+static int sparse_fill_impl(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                            double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
+                            double* ddata_dev, int sort_rows, void* stream, const int* row_pos, int64_t row_first,
+                            int64_t row_last) {
     if (!points || !points_host || !scale_host || !ws || !indptr_dev || !indices_dev || !data_dev || n <= 0 || d <= 0 || d > 8)
         return -1;
     if (ddata_dev)
@@ -801,6 +830,9 @@ int gp_matern_sparse_fill(const double* points, const double* points_host, int64
     SparseParams sp;
     CellGrid g;
     make_params(n, d, scale_host, nu, tau, bb, bb + 8, &sp, &g);
+    sp.row_pos = row_pos;
+    sp.row_first = (int)row_first;
+    sp.row_last = (int)row_last;
     int ne = meta[0];
     launch_rows_mode(matern_mode_of(nu), 1, ddata_dev != nullptr, sp, g, w, indptr_dev, indices_dev, data_dev, ddata_dev, s);
     if (ne > 0) {
@@ -832,6 +864,35 @@ int gp_matern_sparse_fill(const double* points, const double* points_host, int64
     if (sort_rows) return sort_rows_run(n, indptr_dev, indices_dev, data_dev, ddata_dev, w.overflow, s);
     GP_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
+}
+
+extern "C" {
+
+int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                          double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
+                          double* ddata_dev, int sort_rows, void* stream) {
+    return sparse_fill_impl(points, points_host, n, d, scale_host, nu, tau, ws, indptr_dev, indices_dev, data_dev, ddata_dev,
+                            sort_rows, stream, nullptr, 0, 0);
+}
+
+// The same two passes restricted to the rows i with row_first <= row_pos_dev[i] < row_last (row_pos: position of row i in
+// the operator's spatial order): the slab of one GPU of the row-slab engine. The other rows stay empty (indptr is still
+// n + 1 long, column ids are global), so counts, memory and time are those of the slab.
+int gp_matern_sparse_count_rows(const double* points, const double* points_host, int64_t n, int64_t d,
+                                const double* scale_host, double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host,
+                                const int* row_pos_dev, int64_t row_first, int64_t row_last, void* stream) {
+    if (!row_pos_dev || row_first < 0 || row_last < row_first || row_last > n) return -1;
+    return sparse_count_impl(points, points_host, n, d, scale_host, nu, tau, ws, indptr_dev, nnz_host, stream, row_pos_dev,
+                             row_first, row_last);
+}
+
+int gp_matern_sparse_fill_rows(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                               double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
+                               double* ddata_dev, int sort_rows, const int* row_pos_dev, int64_t row_first, int64_t row_last,
+                               void* stream) {
+    if (!row_pos_dev || row_first < 0 || row_last < row_first || row_last > n) return -1;
+    return sparse_fill_impl(points, points_host, n, d, scale_host, nu, tau, ws, indptr_dev, indices_dev, data_dev, ddata_dev,
+                            sort_rows, stream, row_pos_dev, row_first, row_last);
 }
 
 }  // extern "C"

@@ -355,7 +355,10 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     constexpr int NT = (B >= 8) ? B / 8 : 1;   // 8-column MMA tiles per step
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;     // DMMA.8x8x4 fragments: A[g][t], B[t][g], D[g][2t .. 2t+1]
-    const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // PEER: the CTAs alternate between the two ends of the slab, where the halo rows (NVLink latency) are - the slow row
+    // blocks start first and the interior ones fill the tail
+    const int bx = PEER ? ((blockIdx.x & 1) ? (int)gridDim.x - 1 - (int)(blockIdx.x >> 1) : (int)(blockIdx.x >> 1)) : (int)blockIdx.x;
+    const int rb = (bx * blockDim.x + threadIdx.x) >> 5;
     const bool live = rb * (8 * H) < n;
     if (!DOT && !live) return;
     const int64_t p0 = live ? bptr[rb] : 0, p1 = live ? bptr[rb + 1] : 0;   // p1 - p0 is a multiple of 4
@@ -932,7 +935,8 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
 // Every rank holds the 16-row blocks of ITS rows [rank * slab, ...) of the (spatially ordered) operator; bidx carries
 // (owner << 28 | row within the owner's slab). Vectors are the rank's rows; results of reductions are identical on all ranks.
 
-__global__ void encode_columns_kernel(int* __restrict__ bidx, int64_t total, int slab, int rank, unsigned long long* halo) {
+__global__ void encode_columns_kernel(int* __restrict__ bidx, int64_t total, int slab, int rank, unsigned long long* halo,
+                                      unsigned* seen) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = i < total;
     int owner = rank;
@@ -940,32 +944,51 @@ __global__ void encode_columns_kernel(int* __restrict__ bidx, int64_t total, int
         const int col = bidx[i];
         owner = col / slab;
         bidx[i] = (owner << PEER_SHIFT) | (col - owner * slab);
+        if (seen && owner != rank) atomicOr(seen + (col >> 5), 1u << (col & 31));
     }
     const unsigned remote = __ballot_sync(0xffffffffu, ok && owner != rank);
     if (halo && (threadIdx.x & 31) == 0 && remote) atomicAdd(halo, (unsigned long long)__popc(remote));
 }
 
-// global operator-space column -> (owner, local row) for uniform slabs of `slab` rows (slab < 2^28, owner < 8);
-// halo_host (optional): the number of block-columns owned by another rank than `rank` (synchronises the stream)
-int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t* halo_host, void* stream) {
-    if (!bidx || total < 0 || slab <= 0 || slab >= (1 << PEER_SHIFT) || rank < 0 || rank >= PEER_MAX) return -1;
-    if (halo_host) *halo_host = 0;
+__global__ void popcount_kernel(const unsigned* __restrict__ words, int64_t nwords, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x)
+        c += __popc(words[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// global operator-space column (< n) -> (owner, local row) for uniform slabs of `slab` rows (slab < 2^28, owner < 8).
+// halo_host (optional, 2 entries; synchronises the stream): [0] block-columns owned by another rank than `rank` = rows of X
+// gathered over NVLink per SpMM; [1] DISTINCT remote rows among them = the halo a bulk exchange would move.
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* stream) {
+    if (!bidx || total < 0 || slab <= 0 || slab >= (1 << PEER_SHIFT) || rank < 0 || rank >= PEER_MAX || n <= 0) return -1;
+    if (halo_host) halo_host[0] = halo_host[1] = 0;
     if (total == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long* cnt = nullptr;
+    unsigned* seen = nullptr;
+    const int64_t nwords = (n + 31) / 32;
     if (halo_host) {
-        GP_CUDA_CHECK(cudaMallocAsync((void**)&cnt, sizeof(unsigned long long), s));
-        GP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+        GP_CUDA_CHECK(cudaMallocAsync((void**)&cnt, 2 * sizeof(unsigned long long), s));
+        GP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+        GP_CUDA_CHECK(cudaMallocAsync((void**)&seen, nwords * sizeof(unsigned), s));
+        GP_CUDA_CHECK(cudaMemsetAsync(seen, 0, nwords * sizeof(unsigned), s));
     }
-    encode_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bidx, total, (int)slab, (int)rank, cnt);
+    encode_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bidx, total, (int)slab, (int)rank, cnt, seen);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     if (halo_host) {
-        unsigned long long h = 0;
-        GP_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+        popcount_kernel<<<148, 256, 0, s>>>(seen, nwords, cnt + 1);
+        GP_COUNT(1);
+        unsigned long long h[2] = {0, 0};
+        GP_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
         GP_CUDA_CHECK(cudaFreeAsync(cnt, s));
+        GP_CUDA_CHECK(cudaFreeAsync(seen, s));
         GP_CUDA_CHECK(cudaStreamSynchronize(s));
-        *halo_host = (int64_t)h;
+        halo_host[0] = (int64_t)h[0];
+        halo_host[1] = (int64_t)h[1];
     }
     return 0;
 }

@@ -49,6 +49,9 @@ SIGNATURES = {
     'gp_sparse_workspace_bytes': (_i64, [_i64, _i64]),
     'gp_matern_sparse_count': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp]),
     'gp_matern_sparse_fill': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    'gp_matern_sparse_count_rows': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    'gp_matern_sparse_fill_rows': (_int, [_vp, _vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _i64,
+                                          _vp]),
     'gp_csr_sort_rows': (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gp_csr_spmm': (_int, [_vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_rademacher': (_int, [_vp, _i64, _i64, ctypes.c_uint64, _i64, _vp, _vp]),
@@ -90,7 +93,7 @@ SIGNATURES = {
     'gp_peer_barrier': (_int, [_vp, _vp]),
     'gp_peer_allreduce': (_int, [_vp, _vp, _i64, _vp]),
     'gp_peer_error': (_int, [_vp, _vp]),
-    'gp_slab_encode_columns': (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    'gp_slab_encode_columns': (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     'gp_slab_spmm': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_slab_col_dot': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'gp_slab_lanczos': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -123,6 +123,10 @@ class SlabSparseEngine(SparseEngine):
         self.slab, self.first_row, self.last_row = slab_geometry(K.n, self.world, self.rank)
         if self.last_row <= self.first_row:
             raise ValueError('n = %d is too small for %d slabs of 16-row blocks.' % (K.n, self.world))
+        part = getattr(K, 'row_slab', None)         # a handle generated with row_slab=(rank, world) holds only this slab
+        if part is not None and part != (self.rank, self.world, self.first_row, self.last_row):
+            raise ValueError('this DeviceCSR holds the rows of slab %r, not those of rank %d of %d.'
+                             % (part, self.rank, self.world))
         self.peer = PeerArena.get(self.rank, self.world, self.slab)
         SparseEngine.__init__(self, K, imate_method, opts, probe_range=None)
 
@@ -132,8 +136,10 @@ class SlabSparseEngine(SparseEngine):
         n, r0, r1 = self.n, self.first_row, self.last_row
         nloc = r1 - r0
         s = dev.stream_ptr()
-        inv = torch.empty(n, dtype=torch.int32, device='cuda')
-        check(lib.gp_inverse_permutation(_p(K.order), n, _p(inv), s), 'gp_inverse_permutation')
+        inv = getattr(K, 'inv_order', None)
+        if inv is None:
+            inv = torch.empty(n, dtype=torch.int32, device='cuda')
+            check(lib.gp_inverse_permutation(_p(K.order), n, _p(inv), s), 'gp_inverse_permutation')
         my_rows = K.order[r0:r1]                              # original ids of this rank's rows (contiguous int32 view)
         nrb = (nloc + R - 1) // R
         nblk = torch.empty(nrb, dtype=torch.int32, device='cuda')
@@ -153,15 +159,14 @@ class SlabSparseEngine(SparseEngine):
         check(lib.gp_bcsr_fill(R, nloc, _p(my_rows), _p(inv), _p(K.indptr), _p(K.indices), _p(K.data),
                                _p(K.ddata) if K.ddata is not None else None, _p(bptr), total, _p(bidx), _p(bvals),
                                _p(bdvals) if bdvals is not None else None, s), 'gp_bcsr_fill')
-        halo = ctypes.c_int64()       # block-columns whose row of X lives on another rank (gathered over NVLink)
-        check(lib.gp_slab_encode_columns(_p(bidx), total, self.slab, self.rank, ctypes.byref(halo), s),
-              'gp_slab_encode_columns')
-        self.halo_blocks, self.total_blocks = int(halo.value), total
-        self.halo_fraction = halo.value / float(max(total, 1))
+        halo = (ctypes.c_int64 * 2)()   # block-columns whose row of X lives on another rank, and the distinct rows among them
+        check(lib.gp_slab_encode_columns(_p(bidx), total, self.slab, self.rank, n, halo, s), 'gp_slab_encode_columns')
+        self.halo_blocks, self.halo_rows, self.total_blocks = int(halo[0]), int(halo[1]), total
+        self.halo_fraction = halo[0] / float(max(total, 1))
         self.R = R
         self.rows = nloc
         self.blocked = (bptr, bidx, bvals, bdvals)
-        self.fill_ratio = total * R / float(max(K.nnz, 1)) * self.world
+        self.fill_ratio = total * R / float(max(K.nnz, 1)) * (1 if getattr(K, 'row_slab', None) else self.world)
         self.order, self.inv_order = K.order, inv
         self._my_rows = my_rows
 

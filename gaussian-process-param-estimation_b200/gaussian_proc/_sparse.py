@@ -101,11 +101,46 @@ class DeviceCSR(object):
                                        shape=(self.n, self.n))
 
 
+_POINTS_DEVICE_CACHE = []      # [(key, points array, device points, order, position)]
+
+
+def _device_points(points):
+    """(device copy, spatial order, position in the order) of a host point set. None of the three depends on the
+    hyper-parameters, and an optimiser or a sweep generates K for the same points at every step: the last two point sets
+    are kept (keyed by content, _device.host_key; arrays that cannot be written to are recognised without a digest).
+    order = stable sort of the Hilbert / Z-order keys over the bounding box (own kernels, csrc/gp_index.cu): the
+    deterministic, spatially local row order of the row-blocked operator; position = its inverse permutation."""
+    torch = dev.torch
+    key = dev.host_key(points)
+    for ent in _POINTS_DEVICE_CACHE:
+        if ent[0] == key:
+            return ent[2], ent[3], ent[4]
+    n, d = points.shape
+    s = dev.stream_ptr()
+    dpts = torch.from_numpy(numpy.array(points)).cuda()
+    box = numpy.empty(2 * d)
+    box_ws = torch.empty(148 * 2 * d + 2 * d, dtype=torch.float64, device='cuda')
+    check(lib.gp_points_bbox(_p(dpts), n, d, dev.host_ptr(box), _p(box_ws), s), 'gp_points_bbox')
+    lo, hi = dev.host_f64(box[:d]), dev.host_f64(box[d:])
+    keys = torch.empty(n, dtype=torch.int64, device='cuda')
+    check(lib.gp_spatial_keys(_p(dpts), n, d, dev.host_ptr(lo), dev.host_ptr(hi), _p(keys), s), 'gp_spatial_keys')
+    order = torch.empty(n, dtype=torch.int32, device='cuda')
+    sort_ws = torch.empty(lib.gp_sort_workspace_bytes(n) // 8 + 8, dtype=torch.float64, device='cuda')
+    check(lib.gp_sort_keys_u64(_p(keys), n, 64, _p(order), _p(sort_ws), s), 'gp_sort_keys_u64')
+    pos = torch.empty(n, dtype=torch.int32, device='cuda')
+    check(lib.gp_inverse_permutation(_p(order), n, _p(pos), s), 'gp_inverse_permutation')
+    _POINTS_DEVICE_CACHE.append((key, points, dpts, order, pos))
+    del _POINTS_DEVICE_CACHE[:-2]
+    return dpts, order, pos
+
+
 def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=False, device=False,
-                                with_derivative=False, kernel_threshold=None, sort_rows=None):
+                                with_derivative=False, kernel_threshold=None, sort_rows=None, row_slab=None):
     """Device generator behind the reference's generate_sparse_correlation. Returns scipy.sparse.csr_matrix (or a
     DeviceCSR when ``device``). ``sort_rows``: canonical (column-sorted) rows right away; default: yes for the SciPy
-    result, deferred (DeviceCSR.canonicalize) for a device handle."""
+    result, deferred (DeviceCSR.canonicalize) for a device handle.
+    ``row_slab`` = (rank, world) (device handle only): generate only this rank's slab of rows of the spatially ordered
+    operator (gaussian_proc/_slab.py); the other rows of the handle stay empty."""
     sort_rows = (not device) if sort_rows is None else bool(sort_rows)
     torch = dev.require_cuda()
     points = numpy.ascontiguousarray(points, dtype=numpy.float64)
@@ -114,34 +149,42 @@ def generate_sparse_correlation(points, correlation_scale, nu, density, verbose=
     tau = estimate_kernel_threshold(n, d, density, scale, nu) if kernel_threshold is None else float(kernel_threshold)
     if with_derivative and not numpy.all(scale == scale[0]):
         raise ValueError('d/d(correlation_scale) is defined for an isotropic correlation_scale.')
-    dpts = torch.from_numpy(points).cuda()
+    if row_slab is not None and not device:
+        raise ValueError('row_slab needs device=True (a slab is not a complete matrix).')
+    s = dev.stream_ptr()
+    dpts, order, pos = _device_points(points)
+    rows = None
+    if row_slab is not None:
+        from ._slab import slab_geometry
+        rank, world = int(row_slab[0]), int(row_slab[1])
+        _, first, last = slab_geometry(n, world, rank)
+        rows = (pos, first, last)
     ws = torch.empty(lib.gp_sparse_workspace_bytes(n, d) // 8 + 8, dtype=torch.float64, device='cuda')
     indptr = torch.empty(n + 1, dtype=torch.int32, device='cuda')
     nnz = ctypes.c_int64()
-    s = dev.stream_ptr()
-    rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
-                                    _p(indptr), ctypes.byref(nnz), s)
+    if rows is None:
+        rc = lib.gp_matern_sparse_count(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                        _p(indptr), ctypes.byref(nnz), s)
+    else:
+        rc = lib.gp_matern_sparse_count_rows(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                             _p(indptr), ctypes.byref(nnz), _p(rows[0]), rows[1], rows[2], s)
     check(rc, 'gp_matern_sparse_count')
-    # deterministic, spatially local order of the points (stable sort of Hilbert / Z-order keys) for the row-blocked operator
-    # (bounding box, stable radix sort: the library's own kernels, csrc/gp_index.cu)
-    box = numpy.empty(2 * d)
-    box_ws = torch.empty(148 * 2 * d + 2 * d, dtype=torch.float64, device='cuda')   # (ws holds the count pass's cell lists)
-    check(lib.gp_points_bbox(_p(dpts), n, d, dev.host_ptr(box), _p(box_ws), s), 'gp_points_bbox')
-    lo, hi = dev.host_f64(box[:d]), dev.host_f64(box[d:])
-    keys = torch.empty(n, dtype=torch.int64, device='cuda')
-    check(lib.gp_spatial_keys(_p(dpts), n, d, dev.host_ptr(lo), dev.host_ptr(hi), _p(keys), s), 'gp_spatial_keys')
-    order = torch.empty(n, dtype=torch.int32, device='cuda')
-    sort_ws = torch.empty(lib.gp_sort_workspace_bytes(n) // 8 + 8, dtype=torch.float64, device='cuda')
-    check(lib.gp_sort_keys_u64(_p(keys), n, 64, _p(order), _p(sort_ws), s), 'gp_sort_keys_u64')
-    del keys, sort_ws
     indices = torch.empty(nnz.value, dtype=torch.int32, device='cuda')
     data = torch.empty(nnz.value, dtype=torch.float64, device='cuda')
     ddata = torch.empty(nnz.value, dtype=torch.float64, device='cuda') if with_derivative else None
-    rc = lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
-                                   _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None,
-                                   1 if sort_rows else 0, s)
+    if rows is None:
+        rc = lib.gp_matern_sparse_fill(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                       _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None,
+                                       1 if sort_rows else 0, s)
+    else:
+        rc = lib.gp_matern_sparse_fill_rows(_p(dpts), dev.host_ptr(points), n, d, dev.host_ptr(scale), float(nu), tau, _p(ws),
+                                            _p(indptr), _p(indices), _p(data), _p(ddata) if ddata is not None else None,
+                                            1 if sort_rows else 0, _p(rows[0]), rows[1], rows[2], s)
     check(rc, 'gp_matern_sparse_fill')
     K = DeviceCSR(n, indptr, indices, data, ddata, kernel_threshold=tau, order=order, sorted_rows=sort_rows)
+    K.inv_order = pos
+    if rows is not None:
+        K.row_slab = (rank, world, rows[1], rows[2])       # only these rows of the ordered operator are present
     if verbose:
         print('Generated sparse correlation matrix using kernel threshold: %0.4f and sparse density: %0.2e.'
               % (tau, K.nnz / float(n) ** 2))
@@ -245,8 +288,10 @@ class SparseEngine(object):
         torch = dev.torch
         n = self.n
         s = dev.stream_ptr()
-        inv = torch.empty(n, dtype=torch.int32, device='cuda')
-        check(lib.gp_inverse_permutation(_p(K.order), n, _p(inv), s), 'gp_inverse_permutation')
+        inv = getattr(K, 'inv_order', None)
+        if inv is None:
+            inv = torch.empty(n, dtype=torch.int32, device='cuda')
+            check(lib.gp_inverse_permutation(_p(K.order), n, _p(inv), s), 'gp_inverse_permutation')
         nrb = (n + R - 1) // R
         nblk = torch.empty(nrb, dtype=torch.int32, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')

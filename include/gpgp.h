@@ -106,6 +106,16 @@ int gp_spatial_keys(const double* points, int64_t n, int64_t d, const double* lo
 int gp_matern_sparse_fill(const double* points, const double* points_host, int64_t n, int64_t d,
                           const double* scale_host, double nu, double tau, void* ws, const int* indptr_dev,
                           int* indices_dev, double* data_dev, double* ddata_dev, int sort_rows, void* stream);
+/* The same two passes for ONE slab of rows (row-slab engine, one slab of the spatially ordered operator per GPU): only rows i
+ * with row_first <= row_pos_dev[i] < row_last are generated, the others stay empty; indptr keeps n + 1 entries and the
+ * column ids stay global. Work, memory and time are those of the slab. */
+int gp_matern_sparse_count_rows(const double* points, const double* points_host, int64_t n, int64_t d,
+                                const double* scale_host, double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host,
+                                const int* row_pos_dev, int64_t row_first, int64_t row_last, void* stream);
+int gp_matern_sparse_fill_rows(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                               double nu, double tau, void* ws, const int* indptr_dev, int* indices_dev, double* data_dev,
+                               double* ddata_dev, int sort_rows, const int* row_pos_dev, int64_t row_first, int64_t row_last,
+                               void* stream);
 /* Sorts every row of a CSR matrix by column (data / ddata follow); flags_dev: 2 device ints of scratch. */
 int gp_csr_sort_rows(int64_t n, const int* indptr_dev, int* indices_dev, double* data_dev, double* ddata_dev,
                      int* flags_dev, void* stream);
@@ -245,9 +255,10 @@ double* gp_peer_vec(void* peer, int64_t k);                               /* thi
 int gp_peer_barrier(void* peer, void* stream);                            /* cross-GPU barrier in stream order */
 int gp_peer_allreduce(void* peer, double* values_dev, int64_t count, void* stream);   /* count <= 256, in place, rank order */
 int gp_peer_error(void* peer, void* stream);                              /* 1: a wait timed out (ranks diverged) */
-/* bidx: global operator-space column -> (owner << 28 | row within the owner's slab) for uniform slabs of `slab` rows;
- * halo_host (optional) receives the number of block-columns owned by another rank (the rows gathered over NVLink) */
-int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t* halo_host, void* stream);
+/* bidx: global operator-space column (< n) -> (owner << 28 | row within the owner's slab) for uniform slabs of `slab` rows.
+ * halo_host (optional, 2 entries): [0] block-columns owned by another rank (rows gathered over NVLink per SpMM), [1] distinct
+ * remote rows among them (what a bulk halo exchange would move) */
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* stream);
 /* The drivers below take the 16-row blocks of this rank's rows (gp_bcsr_count / gp_bcsr_fill on order + first row) with
  * encoded columns; vectors are the rank's rows (nloc x B); alpha, beta, dots are identical on every rank. */
 int gp_slab_spmm(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,

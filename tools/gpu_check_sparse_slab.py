@@ -45,6 +45,8 @@ rho = 0.005 * numpy.sqrt(2 ** 20 / n)
 dens = min(0.05, 1e-3 * 2 ** 20 / n)
 z = numpy.sin(pts[:, 0] * 7) + numpy.cos(pts[:, 1] * 5) + 0.1 * numpy.random.randn(n)
 X = numpy.stack([numpy.ones(n), pts[:, 0], pts[:, 1], pts[:, 0] ** 2, pts[:, 0] * pts[:, 1], pts[:, 1] ** 2], axis=1)
+for arr in (pts, z, X):
+    arr.setflags(write=False)      # (content keys of read-only arrays are cached: no digest per evaluation)
 K = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True)
 opts = {'seed': 0, 'lanczos_degree': 30}
 one = SparseEngine(K, 'slq', dict(opts, overlap=False))
@@ -70,32 +72,78 @@ if rank == 0:
     print(json.dumps(out), flush=True)
 
 # ---- 3. timing: fresh operator + evaluation (a new-rho step of an optimiser), slabs against one GPU
-def evaluate(cls, **kw):
-    Kc = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True)
+def evaluate(cls, phases=None):
+    slabbed = cls is SlabSparseEngine
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    Kc = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True,
+                                     row_slab=(rank, world) if slabbed else None)
     torch.cuda.synchronize(); ta = time.perf_counter()
-    eng = cls(Kc, 'slq', dict(opts), **kw)
+    eng = cls(Kc, 'slq', dict(opts))
     torch.cuda.synchronize(); tb = time.perf_counter()
+    if phases is not None:
+        for name in ('_rhs_block', 'solve_rhs_block', 'gram', 'spmm', '_slq', 'traceinv_dK'):
+            def wrap(fn, name=name):
+                def timed(*a, **k):
+                    torch.cuda.synchronize(); t = time.perf_counter()
+                    r = fn(*a, **k)
+                    torch.cuda.synchronize(); phases[name] = phases.get(name, 0.0) + time.perf_counter() - t
+                    return r
+                return timed
+            setattr(eng, name, wrap(getattr(eng, name)))
     r = eng.fused(10.0, X, z)
     torch.cuda.synchronize(); tc = time.perf_counter()
-    return r, tb - ta, tc - tb
+    return r, ta - t0, tb - ta, tc - tb
 
 tm = {}
+res = {}
 for name, cls in (('one_gpu', SparseEngine), ('slabs', SlabSparseEngine)):
     evaluate(cls)
     best = None
     for rep in range(3):
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        r, tbuild, tfused = evaluate(cls)
-        t = time.perf_counter() - t0
+        r, tgen, tbuild, tfused = evaluate(cls)
+        t = tgen + tbuild + tfused
         if best is None or t < best[0]:
-            best = (t, tbuild, tfused)
-    tm[name] = {'total_s': best[0], 'build_s': best[1], 'fused_s': best[2], 'generate_s': best[0] - best[1] - best[2]}
+            best = (t, tgen, tbuild, tfused)
+    res[name] = r
+    ph = {}
+    evaluate(cls, ph)
+    tm[name] = {'total_s': best[0], 'generate_s': best[1], 'build_s': best[2], 'fused_s': best[3],
+                'phases_ms_with_syncs': {k: round(v * 1e3, 3) for k, v in ph.items()}}
 tm['speedup_total'] = tm['one_gpu']['total_s'] / tm['slabs']['total_s']
 tm['speedup_fused'] = tm['one_gpu']['fused_s'] / tm['slabs']['fused_s']
+tm['rel_diff'] = float(numpy.max(numpy.abs(res['one_gpu'] - res['slabs']) / numpy.maximum(numpy.abs(res['one_gpu']), 1e-300)))
 if rank == 0:
     print(json.dumps({'timing': tm}), flush=True)
+# ---- 4. the Krylov drivers alone (CUDA events): Lanczos m = 30 on 16 probes with / without kept vectors, CG on 8 columns
+def ev_ms(fn, reps=3):
+    best = 1e30
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+kr = {}
+Kfull = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True)
+for name, eng in (('one_gpu', SparseEngine(Kfull, 'slq', dict(opts, overlap=False))), ('slabs', SlabSparseEngine(Kfull, 'slq', dict(opts)))):
+    V16 = eng.probes(0, 16)
+    V8 = eng.probes(0, 8)
+    basis = eng._new_basis(30, 16)
+    kr[name] = {
+        'lanczos_m30_B16_ms': ev_ms(lambda: eng._lanczos_launch(10.0, V16, 30)),
+        'lanczos_m30_B16_kept_ms': ev_ms(lambda: eng._lanczos_launch(10.0, V16, 30, basis)),
+        'cg_B8_ms': ev_ms(lambda: eng.solve_dev(10.0, V8.clone())),
+        'spmm_B16_ms': ev_ms(lambda: eng.spmm(10.0, V16)),
+        'spmm_B8_ms': ev_ms(lambda: eng.spmm(10.0, V8)),
+    }
+    del basis
+if rank == 0:
+    print(json.dumps({'krylov': kr}), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
