@@ -67,8 +67,8 @@ class PeerArena(object):
             check(lib.gp_peer_connect(self.ctx, None), 'gp_peer_connect')
 
     @classmethod
-    def get(cls, rank, world, nloc_max):
-        key = (int(rank), int(world))
+    def get(cls, rank, world, nloc_max, tag='main'):
+        key = (int(rank), int(world), tag)
         cur = cls._cache.get(key)
         if cur is None or cur.nloc_max < nloc_max:
             # (a larger arena replaces the old one on every rank at the same call: nloc_max depends on n and world only)
@@ -119,7 +119,6 @@ class SlabSparseEngine(SparseEngine):
         if int(opts.get('block_rows', 16)) != 16:
             raise ValueError('the row-slab engine works on 16-row blocks.')
         opts['block_rows'] = 16
-        opts['overlap'] = False            # one Krylov run at a time: the exchange vectors / mailboxes are per engine
         self.slab, self.first_row, self.last_row = slab_geometry(K.n, self.world, self.rank)
         if self.last_row <= self.first_row:
             raise ValueError('n = %d is too small for %d slabs of 16-row blocks.' % (K.n, self.world))
@@ -128,6 +127,10 @@ class SlabSparseEngine(SparseEngine):
             raise ValueError('this DeviceCSR holds the rows of slab %r, not those of rank %d of %d.'
                              % (part, self.rank, self.world))
         self.peer = PeerArena.get(self.rank, self.world, self.slab)
+        # the first SLQ block runs on a side stream next to the CG for [X z] (SparseEngine.prefetch_slq): its exchanges go
+        # through a second arena - mailboxes and exchange vectors of two concurrent Krylov runs must not mix
+        self.peer_side = (PeerArena.get(self.rank, self.world, self.slab, tag='side')
+                          if bool(opts.get('overlap', True)) else None)
         SparseEngine.__init__(self, K, imate_method, opts, probe_range=None)
 
     # ---- operator -------------------------------------------------------------------------------------------------
@@ -211,9 +214,6 @@ class SlabSparseEngine(SparseEngine):
                                 dev.stream_ptr()), 'gp_rademacher')
         return V
 
-    def prefetch_slq(self, eta):
-        return None
-
     # ---- Krylov drivers ---------------------------------------------------------------------------------------------
     def _lanczos_launch(self, eta, V, m, basis=None, alpha=None, beta=None, side=False):
         torch = dev.torch
@@ -221,8 +221,9 @@ class SlabSparseEngine(SparseEngine):
         alpha = torch.empty((m, B), dtype=torch.float64, device='cuda') if alpha is None else alpha
         beta = torch.empty((m, B), dtype=torch.float64, device='cuda') if beta is None else beta
         bptr, bidx, bvals, _ = self.blocked
-        check(lib.gp_slab_lanczos(self.peer.ctx, _p(bptr), _p(bidx), _p(bvals), self.rows, float(eta), _p(V), B, m, _p(alpha),
-                                  _p(beta), _p(basis) if basis is not None else None, _p(self._workspace(B)),
+        peer = self.peer_side if side else self.peer
+        check(lib.gp_slab_lanczos(peer.ctx, _p(bptr), _p(bidx), _p(bvals), self.rows, float(eta), _p(V), B, m, _p(alpha),
+                                  _p(beta), _p(basis) if basis is not None else None, _p(self._workspace(B, side)),
                                   dev.stream_ptr()), 'gp_slab_lanczos')
         return alpha, beta
 
@@ -267,6 +268,8 @@ class SlabSparseEngine(SparseEngine):
     def fused(self, eta, X, z, traceinv=True, drho=True, cubic=False):
         out = SparseEngine.fused(self, eta, X, z, traceinv=traceinv, drho=drho, cubic=cubic)
         self.peer.check_error()
+        if self.peer_side is not None:
+            self.peer_side.check_error()
         return out
 
     def trace_K(self):

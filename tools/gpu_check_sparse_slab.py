@@ -73,7 +73,7 @@ if rank == 0:
 
 # ---- 3. timing: fresh operator + evaluation (a new-rho step of an optimiser), slabs against one GPU
 def evaluate(cls, phases=None):
-    slabbed = cls is SlabSparseEngine
+    slabbed = issubclass(cls, SlabSparseEngine)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     Kc = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True,
                                      row_slab=(rank, world) if slabbed else None)
@@ -96,7 +96,11 @@ def evaluate(cls, phases=None):
 
 tm = {}
 res = {}
-for name, cls in (('one_gpu', SparseEngine), ('slabs', SlabSparseEngine)):
+class SlabNoOverlap(SlabSparseEngine):
+    def __init__(self, K, method, o):
+        SlabSparseEngine.__init__(self, K, method, dict(o, overlap=False))
+
+for name, cls in (('one_gpu', SparseEngine), ('slabs', SlabSparseEngine), ('slabs_no_overlap', SlabNoOverlap)):
     evaluate(cls)
     best = None
     for rep in range(3):
