@@ -512,6 +512,7 @@ def sharded_measurements(world, rank):
         return [float(v) for v in r], int(Km.engine.last_info.get('num_samples', 0))
 
     sparse_eval(True)
+    sparse_eval(False)          # (warm both variants: the unsplit one keeps twice the Lanczos vectors - allocator growth)
     (r_split, ns_split), ms_split = _timed_max_ms(lambda: sparse_eval(True), world)
     (r_single, ns_single), ms_single = _timed_max_ms(lambda: sparse_eval(False), world)
     out['C4_sparse_n1M_probe_split'] = {
