@@ -15,8 +15,11 @@ constexpr int MAXD = 8;          // max spatial dimension staged in shared memor
 constexpr int CH = 32;           // rows per transpose chunk
 constexpr int PITCH = MT + 1;    // padded pitch of the transpose buffer (doubles)
 
+#ifndef GP_MATERN_MINB
+#define GP_MATERN_MINB 2
+#endif
 template <int MODE, bool WITH_DK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WITH_DK ? 2 : GP_MATERN_MINB)
 matern_dense_kernel(const double* __restrict__ pts, int n, int d, int npad, double* __restrict__ K,
                     double* __restrict__ dK, MaternParams mp) {
     extern __shared__ double dyn_smem[];
@@ -52,11 +55,15 @@ matern_dense_kernel(const double* __restrict__ pts, int n, int d, int npad, doub
             for (int e = 0; e < 4; ++e) cx[k][e] = pc[k][tx * 4 + e];
 
     for (int chunk = 0; chunk < MT / CH; ++chunk) {
-        double v[4][4], dv[4][4];
+        // (the values go straight to the global row and to the transpose buffer: only 4 of them are live per thread, which
+        // keeps the kernel at 3 CTAs per SM - it is bound by instruction issue of the FP64 sqrt / exp sequences, not by HBM)
+        if (tm != tn && chunk > 0) __syncthreads();          // the previous chunk's mirror reads are done
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            int r = chunk * CH + ty + 8 * rr;
-            int gi = m0 + r;
+            const int rl = ty + 8 * rr;
+            const int r = chunk * CH + rl;
+            const int gi = m0 + r;
+            double v[4], dv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int gj = n0 + tx * 4 + e;
@@ -77,33 +84,30 @@ matern_dense_kernel(const double* __restrict__ pts, int n, int d, int npad, doub
                     if (WITH_DK) matern_value_drho<MODE>(x, mp, &val, &dval);
                     else val = matern_value<MODE>(x, mp);
                 }
-                v[rr][e] = val;
-                dv[rr][e] = dval;
+                v[e] = val;
+                dv[e] = dval;
             }
             // direct store: 4 doubles = 32 bytes per thread, a warp covers one full 1 KB tile row
             double* dst = K + (int64_t)gi * npad + n0 + tx * 4;
-            reinterpret_cast<double2*>(dst)[0] = make_double2(v[rr][0], v[rr][1]);
-            reinterpret_cast<double2*>(dst)[1] = make_double2(v[rr][2], v[rr][3]);
+            reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
+            reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
             if (WITH_DK) {
                 double* dd = dK + (int64_t)gi * npad + n0 + tx * 4;
-                reinterpret_cast<double2*>(dd)[0] = make_double2(dv[rr][0], dv[rr][1]);
-                reinterpret_cast<double2*>(dd)[1] = make_double2(dv[rr][2], dv[rr][3]);
+                reinterpret_cast<double2*>(dd)[0] = make_double2(dv[0], dv[1]);
+                reinterpret_cast<double2*>(dd)[1] = make_double2(dv[2], dv[3]);
+            }
+            if (tm != tn) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tbuf[rl * PITCH + tx * 4 + e] = v[e];
+                    if (WITH_DK) tbuf[CH * PITCH + rl * PITCH + tx * 4 + e] = dv[e];
+                }
             }
         }
         if (tm != tn) {
-            // mirror store through shared memory: tbuf[r_local][c]
+            // mirror store through shared memory: lane -> local row (32 consecutive doubles = 256 B of the mirrored row),
+            // warp -> column
             __syncthreads();
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                int rl = ty + 8 * rr;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    tbuf[rl * PITCH + tx * 4 + e] = v[rr][e];
-                    if (WITH_DK) tbuf[CH * PITCH + rl * PITCH + tx * 4 + e] = dv[rr][e];
-                }
-            }
-            __syncthreads();
-            // lane -> local row (32 consecutive doubles = 256 B of the mirrored row), warp -> column
             for (int c = ty; c < MT; c += 8) {
                 int64_t o = (int64_t)(n0 + c) * npad + m0 + chunk * CH + tx;
                 K[o] = tbuf[tx * PITCH + c];
