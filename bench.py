@@ -295,6 +295,7 @@ def secondary_measurements():
     n = 2 ** 20
     numpy.random.seed(0)
     sp = numpy.random.rand(n, 2)
+    sp.setflags(write=False)       # (content keys of read-only arrays are cached: no digest per generation)
     scale = numpy.array([0.005, 0.005])
     opts = {'seed': 0, 'lanczos_degree': 30}
 
@@ -374,12 +375,34 @@ def secondary_measurements():
     lgr = loglik_grad()
     torch.cuda.synchronize()
     tl = time.perf_counter() - t0
+
+    # the same evaluation with the operator generated DIRECTLY as row blocks (generate_sparse_operator: no CSR, no block
+    # build) - what sweeps and optimisers over rho use
+    from gaussian_proc._sparse import generate_sparse_operator
+
+    def loglik_grad_direct():
+        Kb = generate_sparse_operator(sp, scale, 0.5, 1e-3, with_derivative=True)
+        Km = MixedCorrelation(Kb, imate_method='slq', imate_options=opts)
+        return ProfileLikelihood.log_likelihood_and_gradient(zs, Xs, Km, 10.0)
+
+    loglik_grad_direct()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Kb = generate_sparse_operator(sp, scale, 0.5, 1e-3, with_derivative=True)
+    torch.cuda.synchronize()
+    tgd = time.perf_counter() - t0
+    direct_kind = type(Kb).__name__
+    del Kb
+    t0 = time.perf_counter()
+    lgd = loglik_grad_direct()
+    torch.cuda.synchronize()
+    tld = time.perf_counter() - t0
     # the reference's headline driver on this matrix: maximum profile likelihood by the root of d l^/d eta
     # (_profile_likelihood.py:244-415); the kept Krylov runs of the operator serve every eta of the root find
     import contextlib
     import io
     t0 = time.perf_counter()
-    Kr = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True)
+    Kr = generate_sparse_operator(sp, scale, 0.5, 1e-3)
     Kmr = MixedCorrelation(Kr, imate_method='slq', imate_options=opts)
     with contextlib.redirect_stdout(io.StringIO()):
         root = ProfileLikelihood.find_log_likelihood_der1_zeros(zs, Xs, Kmr, [10.0, 1e3])
@@ -438,6 +461,11 @@ def secondary_measurements():
                                            'algorithmic_bytes': 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * 16},
                          'evals_per_s': 1.0 / te, 'evals_per_s_further_eta': 1.0 / te2, 'evals_per_s_new_rho': 1.0 / tn,
                          'loglik_grad_evals_per_s_new_rho': 1.0 / tl, 'loglik_grad': [float(v) for v in lgr],
+                         'direct_operator': {'what': 'generate_sparse_operator: the 16-row blocks straight from the cell lists '
+                                                     '(replaces CSR generation + row-blocked build)', 'handle': direct_kind,
+                                             'generate_s': tgd, 'loglik_grad_evals_per_s_new_rho': 1.0 / tld,
+                                             'loglik_grad': [float(v) for v in lgd],
+                                             'rel_diff_vs_csr_path': [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(lgd, lgr)]},
                          'mle_root_find_s': tr_, 'mle_root': {k: float(v) for k, v in root.items()},
                          'eval': 'SLQ logdet + traceinv (degree 30, <= 50 Rademacher probes, batch 16, rtol 1e-2 @ 95 %) + '
                                  'Hutchinson tr(Kn^-1 dK/drho) at the first eta of an operator; further_eta = another eta served from the kept '
@@ -478,7 +506,7 @@ def sharded_measurements(world, rank):
     Collective per workload (the limiting one is named in DESIGN.md section 6)."""
     import torch
     from gaussian_proc.sweep import likelihood_grid
-    from gaussian_proc._sparse import generate_sparse_correlation
+    from gaussian_proc._sparse import generate_sparse_operator
     from gaussian_proc._mixed_correlation import MixedCorrelation
     from gaussian_proc._likelihood import ProfileLikelihood
     out = {}
@@ -504,7 +532,7 @@ def sharded_measurements(world, rank):
     opts = {'seed': 0, 'lanczos_degree': 30}
 
     def sparse_eval(split):
-        Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True)
+        Kc = generate_sparse_operator(sp, scale, 0.5, 1e-3, with_derivative=True)
         o = dict(opts)
         o['probe_split'] = bool(split)
         Km = MixedCorrelation(Kc, imate_method='slq', imate_options=o)
@@ -527,7 +555,7 @@ def sharded_measurements(world, rank):
     # and every Krylov vector are 1/N per rank; halo rows of the SpMM input are loaded from the owner's memory over NVLink and
     # the Lanczos / CG reductions are summed inside the reduction kernels through peer mailboxes (no library collective)
     def slab_eval():
-        Kc = generate_sparse_correlation(sp, scale, 0.5, 1e-3, device=True, with_derivative=True, row_slab=(rank, world))
+        Kc = generate_sparse_operator(sp, scale, 0.5, 1e-3, with_derivative=True, row_slab=(rank, world))
         o = dict(opts)
         o['row_slabs'] = True
         Km = MixedCorrelation(Kc, imate_method='slq', imate_options=o)

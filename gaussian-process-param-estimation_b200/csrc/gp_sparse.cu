@@ -630,13 +630,10 @@ int64_t gp_sparse_workspace_bytes(int64_t n, int64_t d) { return (int64_t)carve_
 
 }  // extern "C"
 
-static int sparse_count_impl(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
-                             double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream,
-                             const int* row_pos, int64_t row_first, int64_t row_last) {
-    if (!points || !points_host || !scale_host || !ws || !indptr_dev || !nnz_host || n <= 0 || d <= 0 || d > 8 || n > INT32_MAX)
-        return -1;
-    cudaStream_t s = (cudaStream_t)stream;
-    SparseWs w = carve_sparse(ws, n, d);
+// Bounding box, cell grid (cell edge >= support radius), cell-sorted point list: everything the row / row-block kernels
+// enumerate candidates from. Leaves the bounding box in w.bbox for the fill call.
+static int sparse_prepare(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, double tau,
+                          const SparseWs& w, cudaStream_t s, SparseParams* sp_out, CellGrid* g_out) {
     const int N = (int)n, D = (int)d;
     double lo[8], hi[8], bb[16];
     {
@@ -655,12 +652,9 @@ static int sparse_count_impl(const double* points, const double* points_host, in
         }
         GP_CUDA_CHECK(cudaMemcpyAsync(w.bbox, bb, sizeof(bb), cudaMemcpyHostToDevice, s));
     }
-    SparseParams sp;
-    CellGrid g;
+    SparseParams& sp = *sp_out;
+    CellGrid& g = *g_out;
     make_params(n, d, scale_host, nu, tau, lo, hi, &sp, &g);
-    sp.row_pos = row_pos;
-    sp.row_first = (int)row_first;
-    sp.row_last = (int)row_last;
     GP_CUDA_CHECK(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * (g.ncells + 1), s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.border_cnt, 0, sizeof(int) * 4, s));
     GP_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int) * 4, s));
@@ -684,6 +678,23 @@ static int sparse_count_impl(const double* points, const double* points_host, in
         gather_points_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, w.sorted_idx, w.sorted_pts);
         GP_COUNT(3);
     }
+    return 0;
+}
+
+static int sparse_count_impl(const double* points, const double* points_host, int64_t n, int64_t d, const double* scale_host,
+                             double nu, double tau, void* ws, int* indptr_dev, int64_t* nnz_host, void* stream,
+                             const int* row_pos, int64_t row_first, int64_t row_last) {
+    if (!points || !points_host || !scale_host || !ws || !indptr_dev || !nnz_host || n <= 0 || d <= 0 || d > 8 || n > INT32_MAX)
+        return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    SparseWs w = carve_sparse(ws, n, d);
+    SparseParams sp;
+    CellGrid g;
+    if (int rc = sparse_prepare(points, n, d, scale_host, nu, tau, w, s, &sp, &g)) return rc;
+    sp.row_pos = row_pos;
+    sp.row_first = (int)row_first;
+    sp.row_last = (int)row_last;
+    const int N = (int)n;
     launch_rows_mode(matern_mode_of(nu), 0, false, sp, g, w, nullptr, nullptr, nullptr, nullptr, s);
     GP_LAUNCH_CHECK();
     int nb = 0;
@@ -893,6 +904,333 @@ int gp_matern_sparse_fill_rows(const double* points, const double* points_host, 
     if (!row_pos_dev || row_first < 0 || row_last < row_first || row_last > n) return -1;
     return sparse_fill_impl(points, points_host, n, d, scale_host, nu, tau, ws, indptr_dev, indices_dev, data_dev, ddata_dev,
                             sort_rows, stream, row_pos_dev, row_first, row_last);
+}
+
+}  // extern "C"
+
+
+// =====================================================================================================================
+// Direct generation of the ROW-BLOCKED operator (16-row blocks of the spatially ordered matrix, the SpMM's storage,
+// gp_sparse_la.cu) without the CSR round trip: one warp per row block enumerates the candidate points of the cells its 16
+// rows touch ONCE, classifies every (row, candidate) pair by the squared scaled distance, and keeps a candidate as a
+// block-column when any of the 16 entries is in the pattern. PASS 0 counts block-columns (and the entries, = nnz);
+// PASS 1 evaluates the kept entries in the reference's arithmetic (the same device functions as the CSR generator: same
+// values, same pattern rule K > tau) and writes index + 16 values (zeros where an entry is outside the pattern) in the
+// SpMM's fragment order - no memset, no hash build, no second read of a CSR.
+// A pair inside the borderline band (|K - tau| <= 8 ulp: the host decides those in the CSR path) makes PASS 0 report it; the
+// caller then takes the CSR path for this matrix.
+constexpr int BR = 16;
+
+// DIM > 0: the dimension is a compile-time constant (coordinates stay in registers, loops unrolled); DIM = 0: sp.d at run time
+template <int DIM>
+__device__ __forceinline__ double scaled_distance_dim(const double* a, const double* b, const SparseParams& sp) {
+    const int dd = DIM > 0 ? DIM : sp.d;
+    double s = 0.0;     // the reference's arithmetic: divide, square, sum in coordinate order, IEEE sqrt (_kernels.pyx:130-136)
+#pragma unroll
+    for (int k = 0; k < (DIM > 0 ? DIM : 8); ++k)
+        if (k < dd) {
+            const double t = (a[k] - b[k]) / sp.scale[k];
+            s += t * t;
+        }
+    return sqrt(s);
+}
+
+template <int MODE, bool WITH_DK, int DIM>
+__device__ __forceinline__ void block_entry(const SparseParams& sp, int i, const double* pi, int j, const double* pj, double* val,
+                                            double* dval) {
+    const double x = (i <= j) ? scaled_distance_dim<DIM>(pi, pj, sp) : scaled_distance_dim<DIM>(pj, pi, sp);
+    if (WITH_DK) matern_value_drho<MODE>(x, sp.mp, val, dval);
+    else { *val = matern_value<MODE>(x, sp.mp); *dval = 0.0; }
+}
+
+template <int MODE, int PASS, bool WITH_DK, int DIM>
+__global__ void __launch_bounds__(128)
+sparse_blocks_kernel(SparseParams sp, CellGrid g, const int* __restrict__ cell_start, const int* __restrict__ sorted_idx,
+                     const double* __restrict__ sorted_pts, const double* __restrict__ pts, const int* __restrict__ order,
+                     const int* __restrict__ inv_order, int row_first, int nrows, int* __restrict__ nblk,
+                     unsigned long long* stats, const int64_t* __restrict__ bptr, int* __restrict__ bidx,
+                     double* __restrict__ bvals, double* __restrict__ bdvals) {
+    __shared__ double rowp_s[4][BR][8];
+    __shared__ int rowid_s[4][BR];
+    __shared__ int queue_s[4][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rb * BR >= nrows) return;
+    double (*rowp)[8] = rowp_s[w];
+    int* rowid = rowid_s[w];
+    int* queue = queue_s[w];
+    // the block's rows: original point ids and coordinates
+    int cmin[SMAXD] = {1 << 30, 1 << 30, 1 << 30}, cmax[SMAXD] = {-1, -1, -1};
+    if (lane < BR) {
+        const int r = rb * BR + lane;
+        const int id = (r < nrows) ? order[row_first + r] : -1;
+        rowid[lane] = id;
+        double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (id >= 0)
+            for (int k = 0; k < sp.d; ++k) p[k] = pts[(int64_t)id * sp.d + k];
+        for (int k = 0; k < 8; ++k) rowp[lane][k] = p[k];
+        if (id >= 0 && g.ncells > 1) {
+            int c = cell_of_point(p, g);
+            for (int k = g.d - 1; k >= 0; --k) { cmin[k] = cmax[k] = c % g.nc[k]; c /= g.nc[k]; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SMAXD; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin[k] = min(cmin[k], __shfl_xor_sync(0xffffffffu, cmin[k], o));
+            cmax[k] = max(cmax[k], __shfl_xor_sync(0xffffffffu, cmax[k], o));
+        }
+    __syncwarp();
+    int nvalid = nrows - rb * BR;
+    if (nvalid > BR) nvalid = BR;
+    // cell box of the block: the cells of its rows, one cell of margin (cell edge >= support radius)
+    int blo[SMAXD] = {0, 0, 0}, bsz[SMAXD] = {1, 1, 1};
+    int ncell_box = 1;
+    if (g.ncells > 1) {
+        for (int k = 0; k < g.d; ++k) {
+            const int a = max(cmin[k] - 1, 0), b = min(cmax[k] + 1, g.nc[k] - 1);
+            blo[k] = a;
+            bsz[k] = b - a + 1;
+            ncell_box *= bsz[k];
+        }
+    }
+    const int64_t base = (PASS == 1) ? bptr[rb] : 0;
+    int ncols = 0;                 // block-columns so far (warp-uniform)
+    unsigned long long nent = 0;   // entries in the pattern (this lane)
+    unsigned border = 0;
+    int qn = 0;
+    const int dd = DIM > 0 ? DIM : sp.d;
+    constexpr int PD = DIM > 0 ? DIM : 8;
+    // squared scaled distance for the quick classification (multiply by the reciprocal scale, as the CSR generator does)
+    auto sq_dist = [&](const double* a, const double* b) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < PD; ++k)
+            if (k < dd) {
+                const double t = (a[k] - b[k]) * sp.mp.inv_scale[k];
+                s2 += t * t;
+            }
+        return s2;
+    };
+
+    // PASS 1: the lanes with act take one queued candidate each. First the keep decision (exactly PASS 0's: an entry is in
+    // the pattern when it is certainly inside the support radius, or inside the margin with K > tau), then - the slot being
+    // known - one loop over the 16 rows that evaluates the entries and stores them (zeros outside the pattern). The loop is
+    // NOT unrolled: 16 inlined copies of the FP64 sqrt / exp sequences do not fit the instruction cache (first version:
+    // 145 ms, issue slots 4 % busy, `no_instruction` stalls).
+    auto emit = [&](int q, bool act) {
+        bool kept = false;
+        int j = -1;
+        double pj[PD];
+        if (act) {
+            j = sorted_idx[q];
+#pragma unroll
+            for (int k = 0; k < PD; ++k)
+                if (k < dd) pj[k] = sorted_pts[(int64_t)q * dd + k];
+#pragma unroll 1
+            for (int r = 0; r < nvalid && !kept; ++r) {
+                const double s2 = sq_dist(rowp[r], pj);
+                if (s2 < sp.r2_lo) kept = true;
+                else if (!(s2 > sp.r2_hi)) {
+                    double val, dval;
+                    block_entry<MODE, false, DIM>(sp, rowid[r], rowp[r], j, pj, &val, &dval);
+                    if (val > sp.tau) kept = true;
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, kept);
+        if (kept) {
+            const int64_t slot = base + ncols + __popc(m & ((1u << lane) - 1u));
+            bidx[slot] = inv_order[j];
+            const int64_t o = (slot >> 2) * (4 * BR) + (slot & 3);
+#pragma unroll 1
+            for (int r = 0; r < BR; ++r) {
+                double val = 0.0, dval = 0.0;
+                if (r < nvalid) {
+                    const double s2 = sq_dist(rowp[r], pj);
+                    if (!(s2 > sp.r2_hi)) {
+                        block_entry<MODE, WITH_DK, DIM>(sp, rowid[r], rowp[r], j, pj, &val, &dval);
+                        if (!(val > sp.tau)) { val = 0.0; dval = 0.0; }
+                    }
+                }
+                bvals[o + (r >> 3) * 32 + (r & 7) * 4] = val;
+                if (WITH_DK) bdvals[o + (r >> 3) * 32 + (r & 7) * 4] = dval;
+            }
+        }
+        ncols += __popc(m);
+    };
+
+    for (int cb = 0; cb < ncell_box; ++cb) {
+        int id = 0;
+        if (g.ncells > 1) {
+            int r = cb;
+            int cc[SMAXD] = {0, 0, 0};
+            for (int k = g.d - 1; k >= 0; --k) { cc[k] = blo[k] + r % bsz[k]; r /= bsz[k]; }
+            for (int k = 0; k < g.d; ++k) id = id * g.nc[k] + cc[k];
+        }
+        const int s0 = cell_start[id], s1 = cell_start[id + 1];
+        for (int q0 = s0; q0 < s1; q0 += 32) {
+            const int q = q0 + lane;
+            bool cand = false;       // PASS 0: the column is kept; PASS 1: some entry may be in the pattern
+            if (q < s1) {
+                double pj[PD];
+#pragma unroll
+                for (int k = 0; k < PD; ++k)
+                    if (k < dd) pj[k] = sorted_pts[(int64_t)q * dd + k];
+                int j = -1;
+                for (int r = 0; r < nvalid; ++r) {
+                    const double s2 = sq_dist(rowp[r], pj);
+                    if (PASS == 1) {
+                        if (!(s2 > sp.r2_hi)) { cand = true; break; }
+                    } else {
+                        if (s2 < sp.r2_lo) { cand = true; ++nent; }
+                        else if (!(s2 > sp.r2_hi)) {      // inside the margin of the support radius: exact value decides
+                            if (j < 0) j = sorted_idx[q];
+                            double val, dval;
+                            block_entry<MODE, false, DIM>(sp, rowid[r], rowp[r], j, pj, &val, &dval);
+                            if (rowid[r] != j && fabs(val - sp.tau) <= sp.band) ++border;
+                            if (val > sp.tau) { cand = true; ++nent; }
+                        }
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (PASS == 0) {
+                ncols += __popc(m);
+            } else {
+                if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = q;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const int qq = queue[lane];
+                    const int rest = (lane < qn - 32) ? queue[32 + lane] : 0;
+                    __syncwarp();
+                    if (lane < qn - 32) queue[lane] = rest;
+                    qn -= 32;
+                    __syncwarp();
+                    emit(qq, true);
+                }
+            }
+        }
+    }
+    if (PASS == 1 && qn > 0) emit(lane < qn ? queue[lane] : 0, lane < qn);
+    const int padded = (ncols + 3) & ~3;
+    if (PASS == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nent += __shfl_xor_sync(0xffffffffu, nent, o);
+            border += __shfl_xor_sync(0xffffffffu, border, o);
+        }
+        if (lane == 0) {
+            nblk[rb] = padded;
+            if (nent) atomicAdd(stats, nent);
+            if (border) atomicAdd(stats + 1, (unsigned long long)border);
+        }
+    } else if (lane < padded - ncols) {          // pad the block to a multiple of 4 block-columns (zero values, a valid index)
+        const int64_t slot = base + ncols + lane;
+        bidx[slot] = inv_order[rowid[0]];
+        const int64_t o = (slot >> 2) * (4 * BR) + (slot & 3);
+#pragma unroll
+        for (int r = 0; r < BR; ++r) {
+            bvals[o + (r >> 3) * 32 + (r & 7) * 4] = 0.0;
+            if (WITH_DK) bdvals[o + (r >> 3) * 32 + (r & 7) * 4] = 0.0;
+        }
+    }
+}
+
+template <int MODE>
+static void launch_blocks(int pass, bool with_dk, const SparseParams& sp, const CellGrid& g, const SparseWs& w, const double* pts,
+                          const int* order, const int* inv_order, int row_first, int nrows, int* nblk, unsigned long long* stats,
+                          const int64_t* bptr, int* bidx, double* bvals, double* bdvals, cudaStream_t s) {
+    const int nrb = (nrows + BR - 1) / BR;
+    const unsigned blocks = (unsigned)((nrb + 3) / 4);
+#define GP_BLOCKS_LAUNCH(PASS, DK, DIM)                                                                                         \
+    sparse_blocks_kernel<MODE, PASS, DK, DIM><<<blocks, 128, 0, s>>>(sp, g, w.cell_start, w.sorted_idx, w.sorted_pts, pts, order, \
+                                                                       inv_order, row_first, nrows, nblk, stats, bptr, bidx, bvals, bdvals)
+    if (sp.d == 2) {      // the common case (spatial data in the plane) with the dimension compiled in
+        if (pass == 0) GP_BLOCKS_LAUNCH(0, false, 2);
+        else if (with_dk) GP_BLOCKS_LAUNCH(1, true, 2);
+        else GP_BLOCKS_LAUNCH(1, false, 2);
+    } else {
+        if (pass == 0) GP_BLOCKS_LAUNCH(0, false, 0);
+        else if (with_dk) GP_BLOCKS_LAUNCH(1, true, 0);
+        else GP_BLOCKS_LAUNCH(1, false, 0);
+    }
+#undef GP_BLOCKS_LAUNCH
+    GP_COUNT(1);
+}
+
+static void launch_blocks_mode(int mode, int pass, bool with_dk, const SparseParams& sp, const CellGrid& g, const SparseWs& w,
+                               const double* pts, const int* order, const int* inv_order, int row_first, int nrows, int* nblk,
+                               unsigned long long* stats, const int64_t* bptr, int* bidx, double* bvals, double* bdvals,
+                               cudaStream_t s) {
+#define GP_BM(M) launch_blocks<M>(pass, with_dk, sp, g, w, pts, order, inv_order, row_first, nrows, nblk, stats, bptr, bidx, bvals, bdvals, s)
+    switch (mode) {
+        case MAT_05: GP_BM(MAT_05); break;
+        case MAT_15: GP_BM(MAT_15); break;
+        case MAT_25: GP_BM(MAT_25); break;
+        case MAT_GAUSS: GP_BM(MAT_GAUSS); break;
+        default: GP_BM(MAT_GENERAL); break;
+    }
+#undef GP_BM
+}
+
+extern "C" {
+
+// Pass 0 of the direct row-blocked generation for the operator rows [row_first, row_last) (row_first a multiple of 16;
+// the whole matrix: 0, n). order / inv_order: the spatial order of the points and its inverse (device int32).
+// nblk_dev[rb] = block-columns of row block rb, padded to a multiple of 4. stats_host[0] = entries in the pattern (nnz of
+// these rows), stats_host[1] = pairs inside the borderline band. Returns 3 when the direct path does not apply (borderline
+// pairs present, or a threshold without a finite support radius): use gp_matern_sparse_count / fill + gp_bcsr_* then.
+int gp_matern_blocks_count(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, double tau, void* ws,
+                           const int* order_dev, const int* inv_order_dev, int64_t row_first, int64_t row_last, int* nblk_dev,
+                           int64_t* stats_host, void* stream) {
+    if (!points || !scale_host || !ws || !order_dev || !inv_order_dev || !nblk_dev || !stats_host || n <= 0 || d <= 0 || d > 8 ||
+        n > INT32_MAX || row_first < 0 || row_last <= row_first || row_last > n || (row_first % BR))
+        return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    SparseWs w = carve_sparse(ws, n, d);
+    SparseParams sp;
+    CellGrid g;
+    if (int rc = sparse_prepare(points, n, d, scale_host, nu, tau, w, s, &sp, &g)) return rc;
+    stats_host[0] = stats_host[1] = 0;
+    if (!sp.quick) return 3;
+    unsigned long long* stats = w.bbox_keys + 16;
+    GP_CUDA_CHECK(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), s));
+    launch_blocks_mode(matern_mode_of(nu), 0, false, sp, g, w, points, order_dev, inv_order_dev, (int)row_first,
+                       (int)(row_last - row_first), nblk_dev, stats, nullptr, nullptr, nullptr, nullptr, s);
+    GP_LAUNCH_CHECK();
+    unsigned long long h[2] = {0, 0};
+    GP_CUDA_CHECK(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    stats_host[0] = (int64_t)h[0];
+    stats_host[1] = (int64_t)h[1];
+    return h[1] ? 3 : 0;
+}
+
+// Pass 1: after the exclusive scan of nblk (gp_scan_counts) and the allocation of bidx (total), bvals [, bdvals] (16 total).
+int gp_matern_blocks_fill(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, double tau, void* ws,
+                          const int* order_dev, const int* inv_order_dev, int64_t row_first, int64_t row_last,
+                          const int64_t* bptr_dev, int* bidx_dev, double* bvals_dev, double* bdvals_dev, void* stream) {
+    if (!points || !scale_host || !ws || !order_dev || !inv_order_dev || !bptr_dev || !bidx_dev || !bvals_dev || n <= 0 ||
+        d <= 0 || d > 8 || row_first < 0 || row_last <= row_first || row_last > n || (row_first % BR))
+        return -1;
+    if (bdvals_dev)
+        for (int k = 0; k < d; ++k)
+            if (scale_host[k] != scale_host[0]) return -4;
+    cudaStream_t s = (cudaStream_t)stream;
+    SparseWs w = carve_sparse(ws, n, d);
+    double bb[16];
+    GP_CUDA_CHECK(cudaMemcpyAsync(bb, w.bbox, sizeof(bb), cudaMemcpyDeviceToHost, s));      // left by the count call
+    GP_CUDA_CHECK(cudaStreamSynchronize(s));
+    SparseParams sp;
+    CellGrid g;
+    make_params(n, d, scale_host, nu, tau, bb, bb + 8, &sp, &g);
+    launch_blocks_mode(matern_mode_of(nu), 1, bdvals_dev != nullptr, sp, g, w, points, order_dev, inv_order_dev, (int)row_first,
+                       (int)(row_last - row_first), nullptr, nullptr, bptr_dev, bidx_dev, bvals_dev, bdvals_dev, s);
+    GP_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

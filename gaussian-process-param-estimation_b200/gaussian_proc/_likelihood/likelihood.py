@@ -21,7 +21,7 @@ class Likelihood(object):
         self.K = K
         self.likelihood_method = likelihood_method
         if imate_method is None:
-            is_sparse = scipy.sparse.issparse(K) or type(K).__name__ == 'DeviceCSR'
+            is_sparse = scipy.sparse.issparse(K) or type(K).__name__ in ('DeviceCSR', 'DeviceRowBlocks')
             imate_method = 'slq' if is_sparse else 'cholesky'
         self.K_mixed = MixedCorrelation(self.K, interpolate=False, imate_method=imate_method,
                                         imate_options=imate_options)

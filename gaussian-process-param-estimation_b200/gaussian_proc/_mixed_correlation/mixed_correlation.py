@@ -41,7 +41,7 @@ class MixedCorrelation(object):
         self.interpolate_traceinv = None      # built on first use (evaluates traceinv at the interpolant points)
         self.sparse = False
 
-        if scipy.sparse.issparse(K) or type(K).__name__ == 'DeviceCSR':
+        if scipy.sparse.issparse(K) or type(K).__name__ in ('DeviceCSR', 'DeviceRowBlocks'):
             from .._sparse import SparseEngine
             if imate_method not in _SPARSE_METHODS:
                 raise ValueError('For a sparse K, existing methods are "slq" and "hutchinson".')

@@ -23,7 +23,7 @@ import ctypes
 import numpy
 
 from . import _device as dev
-from ._sparse import SparseEngine, DeviceCSR, check, _p
+from ._sparse import SparseEngine, DeviceCSR, DeviceRowBlocks, check, _p
 
 lib = dev.lib
 
@@ -113,8 +113,9 @@ class SlabSparseEngine(SparseEngine):
         r, w = rank_world()
         self.rank = int(r if rank is None else rank)
         self.world = int(w if world is None else world)
-        if not isinstance(K, DeviceCSR) or K.order is None:
-            raise ValueError('the row-slab engine needs a device CSR from generate_sparse_correlation(..., device=True).')
+        if not isinstance(K, (DeviceCSR, DeviceRowBlocks)) or K.order is None:
+            raise ValueError('the row-slab engine needs a device handle from generate_sparse_operator / '
+                             'generate_sparse_correlation(..., device=True).')
         opts = dict(imate_options or {})
         if int(opts.get('block_rows', 16)) != 16:
             raise ValueError('the row-slab engine works on 16-row blocks.')
@@ -124,8 +125,10 @@ class SlabSparseEngine(SparseEngine):
             raise ValueError('n = %d is too small for %d slabs of 16-row blocks.' % (K.n, self.world))
         part = getattr(K, 'row_slab', None)         # a handle generated with row_slab=(rank, world) holds only this slab
         if part is not None and part != (self.rank, self.world, self.first_row, self.last_row):
-            raise ValueError('this DeviceCSR holds the rows of slab %r, not those of rank %d of %d.'
+            raise ValueError('this handle holds the rows of slab %r, not those of rank %d of %d.'
                              % (part, self.rank, self.world))
+        if isinstance(K, DeviceRowBlocks) and (K.first_row, K.last_row) != (self.first_row, self.last_row):
+            raise ValueError('a directly generated operator must be generated for this slab (row_slab=(rank, world)).')
         self.peer = PeerArena.get(self.rank, self.world, self.slab)
         # the first SLQ block runs on a side stream next to the CG for [X z] (SparseEngine.prefetch_slq): its exchanges go
         # through a second arena - mailboxes and exchange vectors of two concurrent Krylov runs must not mix
@@ -139,6 +142,23 @@ class SlabSparseEngine(SparseEngine):
         n, r0, r1 = self.n, self.first_row, self.last_row
         nloc = r1 - r0
         s = dev.stream_ptr()
+        if isinstance(K, DeviceRowBlocks):         # generated as the row blocks of this slab: only the column encoding is left
+            total = K.bidx.numel()
+            if K.encoded is None:
+                halo = (ctypes.c_int64 * 2)()
+                check(lib.gp_slab_encode_columns(_p(K.bidx), total, self.slab, self.rank, n, halo, s),
+                      'gp_slab_encode_columns')
+                K.encoded = (self.slab, self.rank, int(halo[0]), int(halo[1]))
+            elif K.encoded[:2] != (self.slab, self.rank):
+                raise ValueError('this operator was encoded for another slab geometry')
+            self.halo_blocks, self.halo_rows, self.total_blocks = K.encoded[2], K.encoded[3], total
+            self.halo_fraction = self.halo_blocks / float(max(total, 1))
+            self.R, self.rows = R, nloc
+            self.blocked = (K.bptr, K.bidx, K.bvals, K.bdvals)
+            self.fill_ratio = total * R / float(max(K.nnz, 1))
+            self.order, self.inv_order = K.order, K.inv_order
+            self._my_rows = K.order[r0:r1]
+            return
         inv = getattr(K, 'inv_order', None)
         if inv is None:
             inv = torch.empty(n, dtype=torch.int32, device='cuda')

@@ -98,11 +98,11 @@ class _GpuSparseRowEvaluator(object):
         self.options.setdefault('eager_rhs_basis', True)      # every row asks several eta of one operator
 
     def row(self, rho, etas):
-        from ._sparse import generate_sparse_correlation
+        from ._sparse import generate_sparse_operator
         from ._mixed_correlation import MixedCorrelation
         from ._likelihood import ProfileLikelihood
-        K = generate_sparse_correlation(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu, self.density,
-                                        device=True, with_derivative=True)
+        K = generate_sparse_operator(self.points, numpy.repeat(float(rho), self.points.shape[1]), self.nu, self.density,
+                                     with_derivative=True)
         Km = MixedCorrelation(K, imate_method='slq', imate_options=self.options)
         return numpy.array([ProfileLikelihood.log_likelihood_and_gradient(self.z, self.X, Km, eta) for eta in etas])
 

@@ -239,6 +239,23 @@ int gp_bcsr_cg_solve(int64_t R, const int64_t* bptr, const int* bidx, const doub
                      double* R0, double* X, int64_t B, double tol, int64_t maxiter, int64_t* iters_host, void* ws,
                      void* stream);
 
+/* ---- direct generation of the row-blocked operator (csrc/gp_sparse.cu, sparse_blocks_kernel) -------------------------------
+ * The consumer of a sparse K in the likelihood is the operator, not the CSR (the reference hands scipy's CSR to imate / cg,
+ * _generate_sparse_correlation.pyx:472-594 -> mixed_correlation.py:193-209): these two passes emit the 16-row blocks of the
+ * spatially ordered matrix straight from the cell lists - same kernel arithmetic and pattern rule (K > tau) as
+ * gp_matern_sparse_count / fill, no CSR, no hash build. Rows [row_first, row_last) of the ordered operator (row_first a
+ * multiple of 16; one slab per GPU, or 0 .. n). ws: gp_sparse_workspace_bytes(n, d).
+ * count: nblk_dev[rb] = block-columns of row block rb (padded to a multiple of 4); stats_host[0] = entries in the pattern
+ * (nnz of these rows), stats_host[1] = pairs inside the 8-ulp borderline band. Returns 3 when the direct path does not
+ * apply (borderline pairs, or a threshold without finite support): use the CSR path + gp_bcsr_count / fill for this matrix.
+ * fill: after gp_scan_counts(nblk) -> bptr and allocation of bidx (total), bvals [, bdvals] (16 * total doubles). */
+int gp_matern_blocks_count(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, double tau, void* ws,
+                           const int* order_dev, const int* inv_order_dev, int64_t row_first, int64_t row_last, int* nblk_dev,
+                           int64_t* stats_host, void* stream);
+int gp_matern_blocks_fill(const double* points, int64_t n, int64_t d, const double* scale_host, double nu, double tau, void* ws,
+                          const int* order_dev, const int* inv_order_dev, int64_t row_first, int64_t row_last,
+                          const int64_t* bptr_dev, int* bidx_dev, double* bvals_dev, double* bdvals_dev, void* stream);
+
 /* ---- row-slab sparse operator on several GPUs (csrc/gp_peer.cu, gp_sparse_la.cu) ------------------------------------------
  * One process per GPU. The reference evaluates one sparse likelihood on one host (imate SLQ + scipy CG over the whole matrix,
  * gaussian_proc/_mixed_correlation/mixed_correlation.py:193-209, 263-299); here the rows of the (spatially ordered) operator

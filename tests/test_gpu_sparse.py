@@ -605,3 +605,66 @@ def test_row_slab_engine_on_one_rank_equals_sparse_engine(sparse_problem):
     y = numpy.random.RandomState(0).randn(K.n, 3)
     assert numpy.max(numpy.abs(one.solve(2.0, y) - slab.solve(2.0, y))) <= 1e-12 * numpy.abs(y).max()
     assert numpy.max(numpy.abs(one.matmul(y) - slab.matmul(y))) <= 1e-12 * numpy.abs(y).max()
+
+
+@pytest.mark.parametrize('n,d,scale,nu,dens', [(3000, 2, [0.03, 0.03], 0.5, 0.01), (3000, 2, [0.03, 0.03], 2.5, 0.01),
+                                               (1000, 3, [0.2, 0.3, 0.25], 1.5, 0.02), (700, 2, [0.02, 0.05], 1.5, 0.02),
+                                               (300, 1, [0.02], 0.5, 0.05), (13, 2, [0.5, 0.5], 2.5, 0.5),
+                                               (2400, 2, [0.3, 0.3], 0.5, 0.9), (20011, 2, [0.02, 0.02], 0.5, 0.003)])
+def test_direct_row_block_generation_equals_the_csr_generator(gp, n, d, scale, nu, dens):
+    """generate_sparse_operator (row blocks straight from the cell lists, csrc/gp_sparse.cu sparse_blocks_kernel) holds exactly
+    the matrix of the CSR generator - which the tests above pin bit-for-bit to the reference: same pattern, same values
+    (same device arithmetic per entry), same dK/drho values where the scale is isotropic; nnz is counted by the count pass."""
+    from gaussian_proc._sparse import generate_sparse_operator, generate_sparse_correlation, DeviceRowBlocks
+    numpy.random.seed(n + d)
+    pts = numpy.random.rand(n, d)
+    iso = len(set(scale)) == 1
+    Kd = generate_sparse_correlation(pts, numpy.array(scale), nu, dens, device=True, with_derivative=iso)
+    S = Kd.to_scipy()
+    Kb = generate_sparse_operator(pts, numpy.array(scale), nu, dens, with_derivative=iso)
+    assert isinstance(Kb, DeviceRowBlocks) and Kb.nnz == S.nnz
+    assert Kb.kernel_threshold == Kd.kernel_threshold
+    B = Kb.to_scipy()
+    assert (B.indptr == S.indptr).all() and (B.indices == S.indices).all()
+    assert (B.data == S.data).all()
+    assert (numpy.diff(Kb.bptr.cpu().numpy()) % 4 == 0).all()
+    if iso:
+        Kd.canonicalize()
+        vals, Kb.bvals = Kb.bvals, Kb.bdvals          # the same reconstruction on the derivative values
+        D = Kb.to_scipy()
+        Kb.bvals = vals
+        ref = scipy.sparse.csr_matrix((Kd.ddata.cpu().numpy(), Kd.indices.cpu().numpy(), Kd.indptr.cpu().numpy()), shape=S.shape)
+        ref.eliminate_zeros()                         # (the diagonal and duplicate points have derivative exactly 0)
+        assert (D.indptr == ref.indptr).all() and (D.indices == ref.indices).all() and (D.data == ref.data).all()
+
+
+def test_direct_row_block_generation_falls_back_on_exact_ties_and_feeds_the_engine(gp, sparse_problem):
+    from gaussian_proc._sparse import generate_sparse_operator, SparseEngine, DeviceCSR, DeviceRowBlocks
+    from gaussian_proc._mixed_correlation import MixedCorrelation
+    # a regular grid with the threshold placed exactly on a lattice distance: those pairs sit inside the 8-ulp band, which
+    # the reference's rule decides in host arithmetic -> the CSR path
+    from oracle import matern
+    pts = grid_points()
+    sc = numpy.array([0.03, 0.03])
+    x = matern.scaled_distance_matrix(pts[[0, 2]], sc)[0, 1]
+    tau = float(matern.matern_kernel(x, 0.5))                 # the kernel value of a lattice distance, to the last bit
+    K = generate_sparse_operator(pts, sc, 0.5, 0.01, kernel_threshold=tau)
+    assert isinstance(K, DeviceCSR)
+    R = matern.generate_sparse_correlation(pts, sc, 0.5, 0.01, kernel_threshold=tau)
+    S = K.to_scipy()
+    assert (S.indptr == R.indptr).all() and (S.indices == R.indices).all()
+    # the engine on the directly generated operator = the engine on the CSR-built one
+    p, z, X, Kd = sparse_problem
+    Kb = generate_sparse_operator(p, numpy.array([0.03, 0.03]), 0.5, 0.01, with_derivative=True)
+    assert isinstance(Kb, DeviceRowBlocks)
+    opts = {'seed': 3, 'lanczos_degree': 40}
+    f1 = SparseEngine(Kd, 'slq', dict(opts)).fused(2.0, X, z)
+    f2 = SparseEngine(Kb, 'slq', dict(opts)).fused(2.0, X, z)
+    assert numpy.max(numpy.abs(f1 - f2) / numpy.maximum(numpy.abs(f1), 1e-300)) <= 1e-11
+    Km = MixedCorrelation(Kb, imate_method='slq', imate_options=opts)
+    y = numpy.random.RandomState(1).randn(Kb.n)
+    assert numpy.max(numpy.abs(Km.dot(0.0, y) - Kd.to_scipy() @ y)) <= 1e-12 * numpy.abs(y).max() * 50
+    from gaussian_proc._slab import SlabSparseEngine
+    Ks = generate_sparse_operator(p, numpy.array([0.03, 0.03]), 0.5, 0.01, with_derivative=True, row_slab=(0, 1))
+    f3 = SlabSparseEngine(Ks, 'slq', dict(opts), rank=0, world=1).fused(2.0, X, z)
+    assert numpy.max(numpy.abs(f1 - f3) / numpy.maximum(numpy.abs(f1), 1e-300)) <= 1e-11

@@ -11,7 +11,8 @@ if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 from gaussian_proc import _device as dev
-from gaussian_proc._sparse import generate_sparse_correlation, SparseEngine
+from gaussian_proc._sparse import generate_sparse_correlation, generate_sparse_operator, SparseEngine
+DIRECT = os.environ.get('GP_SLAB_DIRECT', '1') != '0'     # operators generated directly as row blocks (default) or via CSR
 from gaussian_proc._slab import SlabSparseEngine, PeerArena
 lib = dev.lib
 P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
@@ -75,8 +76,8 @@ if rank == 0:
 def evaluate(cls, phases=None):
     slabbed = issubclass(cls, SlabSparseEngine)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    Kc = generate_sparse_correlation(pts, numpy.array([rho, rho]), 0.5, dens, device=True, with_derivative=True,
-                                     row_slab=(rank, world) if slabbed else None)
+    gen = generate_sparse_operator if DIRECT else (lambda *a, **k: generate_sparse_correlation(*a, device=True, **k))
+    Kc = gen(pts, numpy.array([rho, rho]), 0.5, dens, with_derivative=True, row_slab=(rank, world) if slabbed else None)
     torch.cuda.synchronize(); ta = time.perf_counter()
     eng = cls(Kc, 'slq', dict(opts))
     torch.cuda.synchronize(); tb = time.perf_counter()
