@@ -750,10 +750,10 @@ def run_ours(args):
     gemm_ms_per_step = gu.value / args.steps
     alg_flops = float(n) ** 3
     achieved = alg_flops / (gemm_ms_per_step * 1e-3) * 1e-12
-    roofline = {'bound': 'tensor', 'kernel': 'gp::dgemm_dmma_kernel (DMMA.8x8x4, FP64 tensor pipe)',
+    roofline = {'bound': 'tensor', 'kernel': 'gp::dgemm_tma_kernel (TMA + mbarrier ring, DMMA.8x8x4 on the FP64 tensor pipe)',
                 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (potrf trailing update, 19456^2 lower
-                # tiles, K = 512) from the ncu --set full capture summarised in profiles/r01_gemm_ncu_summary.md;
+                # tiles, K = 512) from the ncu --set full capture summarised in profiles/r02_gemm_tma_ncu_summary.md (2.21 GB read + 1.42 GB written);
                 # algorithmic bytes of that launch: 3.12e9 (lower triangle of C read + written, plus the panel)
                 'traffic': 3.63e9,
                 'peak_source': 'in-run cuBLAS DGEMM 8192^3 (torch.matmul f64, best of 3); MEASURED_PEAKS.json has no FP64 '
