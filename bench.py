@@ -563,9 +563,25 @@ def sharded_measurements(world, rank):
         e = Km.engine
         return [float(v) for v in r], (e.halo_blocks, e.halo_rows, e.total_blocks, e.rows)
 
+    def slab_root_find(slabs):
+        # the reference's MLE driver (root of d l^/d eta, _profile_likelihood.py:244-415) on the row-slab operator: every
+        # rank runs the same bracketing + Chandrupatla iterations on identical numbers
+        import contextlib
+        import io
+        Kc = generate_sparse_operator(sp, scale, 0.5, 1e-3, row_slab=(rank, world) if slabs else None)
+        o = dict(opts)
+        o['row_slabs'] = bool(slabs)
+        Km = MixedCorrelation(Kc, imate_method='slq', imate_options=o)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return ProfileLikelihood.find_log_likelihood_der1_zeros(zs, Xs, Km, [10.0, 1e3])
+
     try:
         slab_eval()
         (r_slab, halo), ms_slab = _timed_max_ms(slab_eval, world)
+        slab_root_find(True)
+        root_slab, ms_root_slab = _timed_max_ms(lambda: slab_root_find(True), world)
+        slab_root_find(False)
+        root_one, ms_root_one = _timed_max_ms(lambda: slab_root_find(False), world)
         out['C4_sparse_n1M_row_slabs'] = {
             'workload': 'configs[3]: ONE loglik+grad at n=2^20 (nu=0.5, rho=0.005, density=1e-3, eta=10) with the operator '
                         'rows in %d slabs, one per GPU: slab generation + slab build + CG for [X z] + SLQ / Hutchinson' % world,
@@ -574,6 +590,9 @@ def sharded_measurements(world, rank):
             'loglik_grad': r_slab,
             'rel_diff_vs_one_gpu': [abs(a - b) / max(abs(b), 1e-300) for a, b in zip(r_slab, r_single)],
             'rows_per_gpu': int(halo[3]), 'halo_fraction_of_block_columns': halo[0] / float(max(halo[2], 1)),
+            'mle_root_find_s': ms_root_slab * 1e-3, 'mle_root_find_s_one_gpu_same_run': ms_root_one * 1e-3,
+            'mle_root': {k: float(v) for k, v in root_slab.items()},
+            'mle_root_rel_diff_vs_one_gpu': abs(root_slab['eta'] - root_one['eta']) / abs(root_one['eta']),
             'nvlink_bytes_per_spmm_B16_rank0': int(halo[0]) * 16 * 8,
             'halo_algorithmic_bytes_B16_rank0': int(halo[1]) * 16 * 8,
             'exchange': 'halo rows: loads from the owner GPU inside the SpMM kernel (CUDA IPC mapping, NVLink); reductions: '

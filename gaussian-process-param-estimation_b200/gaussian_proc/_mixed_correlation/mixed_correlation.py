@@ -127,7 +127,8 @@ class MixedCorrelation(object):
         if not self.sparse and self.imate_method == 'eigenvalue':
             if exponent in (1, 2):
                 return self._eigen.reductions(eta)[exponent]                              # :172-181
-            return float(((self.K_eigenvalues + eta) ** (-exponent)).sum().item())
+            lam = self.K_eigenvalues.cpu().numpy()                  # (other exponents: a host sum over the n eigenvalues)
+            return float(numpy.sum((lam + eta) ** (-float(exponent))))
         return self.engine.traceinv(eta, exponent)
 
     def logdet(self, eta, exponent=1):
