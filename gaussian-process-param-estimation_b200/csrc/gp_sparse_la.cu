@@ -17,6 +17,9 @@ namespace gp {
 #ifndef GP_SPMM_U
 #define GP_SPMM_U 4
 #endif
+#ifndef GP_SPMM_ROWLOAD
+#define GP_SPMM_ROWLOAD 0
+#endif
 constexpr int RED_PARTS = 592;  // CTAs of the column reductions (4 per SM)
 
 // ---- Y = (K + eta I) X, one warp per row; lane = (q, c): q-th nonzero of the current group, column c ---------
@@ -370,10 +373,25 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     const bool colok = (B >= 8) || (g < B);
     const int coff = (B >= 8) ? g * NT : (colok ? g : 0);
     const double* aptr = bvals + lane;          // A fragment order: element (row g, block-column t) at 4 g + t = lane
+    // B = 16: a gathered X row is 128 bytes = one L1 line. In the fragment layout (lane 4 g + t holds row t, columns 2 g,
+    // 2 g + 1) a quarter-warp - the unit a 16-byte load is served in - touches FOUR rows: 16 line accesses (wavefronts) per
+    // load instruction, and the L1 data pipe, not HBM, bounds the kernel (ncu, profiles/r01_spmm_ncu_summary.md). ROWLOAD
+    // (compile-time experiment, OFF): lane 8 t' + g' loads chunk g' of row t' - every quarter-warp reads one whole line -
+    // and two 64-bit warp shuffles bring the chunk to the lane that owns it in the fragment layout. Measured at n = 2^20:
+    // 1.043 ms against 0.910 ms for the direct fragment gather - the shuffles go through the same LSU data path and cost
+    // more than the saved line accesses (like the shared-memory staging of round 1: the bytes pass the pipe twice).
+    constexpr bool ROWLOAD = (B == 16) && (GP_SPMM_ROWLOAD != 0);
+    const int tsel = ROWLOAD ? (lane >> 3) : t;                    // which of the step's 4 block-columns this lane loads
+    const int xoff = ROWLOAD ? 2 * (lane & 7) : coff;
+    const int xsrc = 8 * t + g;                                    // ROWLOAD: the lane that loaded this lane's fragment
     auto load_x = [&](int col, double* x) {
-        const double* xr = PEER ? pv.base[(unsigned)col >> PEER_SHIFT] + (int64_t)(col & ((1 << PEER_SHIFT) - 1)) * B + coff
-                                : X + (int64_t)col * B + coff;
-        if (NT == 1) {
+        const double* xr = PEER ? pv.base[(unsigned)col >> PEER_SHIFT] + (int64_t)(col & ((1 << PEER_SHIFT) - 1)) * B + xoff
+                                : X + (int64_t)col * B + xoff;
+        if (ROWLOAD) {
+            const double2 v = *reinterpret_cast<const double2*>(xr);
+            x[0] = __shfl_sync(0xffffffffu, v.x, xsrc);
+            x[NT > 1 ? 1 : 0] = __shfl_sync(0xffffffffu, v.y, xsrc);
+        } else if (NT == 1) {
             x[0] = colok ? *xr : 0.0;
         } else {
 #pragma unroll
@@ -390,7 +408,7 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
         int col[U];
         double a[U][H], x[U][NT];
 #pragma unroll
-        for (int u = 0; u < U; ++u) col[u] = __ldcs(bidx + p + 4 * u + t);
+        for (int u = 0; u < U; ++u) col[u] = __ldcs(bidx + p + 4 * u + tsel);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -405,7 +423,7 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
                 for (int j = 0; j < NT; ++j) dmma884(acc[h][j][0], acc[h][j][1], a[u][h], x[u][j]);
     }
     for (; p < p1; p += 4) {
-        const int col = __ldcs(bidx + p + t);
+        const int col = __ldcs(bidx + p + tsel);
         double a[H], x[NT];
 #pragma unroll
         for (int h = 0; h < H; ++h) a[h] = __ldcs(aptr + p * (8 * H) + 32 * h);
