@@ -384,8 +384,9 @@ class SparseEngine(object):
         torch = dev.torch
         n = self.n
         if isinstance(K, DeviceRowBlocks):         # generated as row blocks: nothing to build
-            if (K.first_row, K.last_row) != (0, n):
-                raise ValueError('this operator holds one slab of rows: use the row-slab engine (row_slabs=True).')
+            if (K.first_row, K.last_row) != (0, n) or K.encoded is not None:
+                raise ValueError('this operator holds one slab of rows (or its columns were encoded for the row-slab engine): '
+                                 'use the row-slab engine (row_slabs=True).')
             self.R = R
             self.blocked = (K.bptr, K.bidx, K.bvals, K.bdvals)
             self.fill_ratio = K.bidx.numel() * R / float(max(K.nnz, 1))
