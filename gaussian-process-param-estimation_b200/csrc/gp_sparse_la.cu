@@ -12,7 +12,7 @@
 namespace gp {
 
 #ifndef GP_SPMM_MINB
-#define GP_SPMM_MINB 1
+#define GP_SPMM_MINB 4
 #endif
 #ifndef GP_SPMM_U
 #define GP_SPMM_U 4
