@@ -136,24 +136,31 @@ frob_lower_kernel(const double* __restrict__ W, int n, int npad, double* partial
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 }
 
-// ---- V = dK * S for S (n x p): 64 rows per CTA, all column tiles streamed through shared memory ---------
-// 4 adjacent lanes share a row (interleaved columns) and combine with two shuffles.
-constexpr int SSP = MAXP + 1;  // padded row pitch of the staged S tile
-template <int MODE>
+// ---- V = dK * S for S (n x p): 16 rows per CTA (2 per warp), all column tiles streamed through shared memory ---------
+// A lane evaluates its 4 columns of the 128-column tile for both rows of its warp; 5 shuffles per accumulator at the end.
+// PP = p padded to 8 or 16 at compile time: the accumulators stay in registers. (Round 1 mapped 64 rows to a CTA: n / 64
+// CTAs - 125 at n = 8000, less than one per SM - with the accumulators on the stack; 1.57 ms at n = 8000, 5.0 ms at n = 20 000.)
+constexpr int SSP = MAXP + 1;  // padded row pitch of a staged skinny tile
+constexpr int DKR = 16;        // rows per CTA
+template <int MODE, int PP>
 __global__ void __launch_bounds__(256)
 dk_apply_kernel(const double* __restrict__ pts, int n, int d, MaternParams mp, const double* __restrict__ S, int p,
                 int64_t lds, double* __restrict__ V) {
+    constexpr int SP = PP + 1;
     __shared__ double pcs[LMAXD][128];
-    __shared__ double ss[128 * SSP];
-    const int tid = threadIdx.x;
-    const int rl = tid >> 2, part = tid & 3;
-    const int gi = blockIdx.x * 64 + rl;
-    double pi[LMAXD];
+    __shared__ double ss[128 * SP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g0 = blockIdx.x * DKR + warp * 2;
+    double pi[2][LMAXD];
 #pragma unroll
-    for (int k = 0; k < LMAXD; ++k) pi[k] = (k < d && gi < n) ? pts[(int64_t)gi * d + k] : 0.0;
-    double acc[MAXP];
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int c = 0; c < MAXP; ++c) acc[c] = 0.0;
+        for (int k = 0; k < LMAXD; ++k) pi[r][k] = (k < d && g0 + r < n) ? pts[(int64_t)(g0 + r) * d + k] : 0.0;
+    double acc[2][PP];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < PP; ++c) acc[r][c] = 0.0;
     for (int j0 = 0; j0 < n; j0 += 128) {
         __syncthreads();
         for (int idx = tid; idx < 128 * d; idx += 256) {
@@ -162,39 +169,51 @@ dk_apply_kernel(const double* __restrict__ pts, int n, int d, MaternParams mp, c
         }
         for (int idx = tid; idx < 128 * p; idx += 256) {
             int r = idx / p, c = idx - r * p;
-            ss[r * SSP + c] = (j0 + r < n) ? S[(int64_t)(j0 + r) * lds + c] : 0.0;
+            ss[r * SP + c] = (j0 + r < n) ? S[(int64_t)(j0 + r) * lds + c] : 0.0;
         }
         __syncthreads();
-        if (gi < n) {
-            for (int t = 0; t < 32; ++t) {
-                int jj = t * 4 + part;
-                int gj = j0 + jj;
-                if (gj >= n || gj == gi) continue;
-                double s = 0.0, ud = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int jj = t * 32 + lane;
+            const int gj = j0 + jj;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int gi = g0 + r;
+                if (gi >= n || gj >= n || gj == gi) continue;
+                double s2 = 0.0, ud = 0.0;
 #pragma unroll
                 for (int k = 0; k < LMAXD; ++k)
                     if (k < d) {
-                        double u = (pi[k] - pcs[k][jj]) * mp.inv_scale[k];
-                        s += u * u;
+                        double u = (pi[r][k] - pcs[k][jj]) * mp.inv_scale[k];
+                        s2 += u * u;
                         if (k == mp.ddim) ud = u * u;
                     }
                 double val, dval;
-                matern_value_drho<MODE>(sqrt(s), mp, &val, &dval);
-                if (mp.ddim >= 0) dval = (s > 0.0) ? dval * (ud / s) * mp.inv_scale[mp.ddim] : 0.0;
+                matern_value_drho<MODE>(sqrt(s2), mp, &val, &dval);
+                if (mp.ddim >= 0) dval = (s2 > 0.0) ? dval * (ud / s2) * mp.inv_scale[mp.ddim] : 0.0;
 #pragma unroll
-                for (int c = 0; c < MAXP; ++c)
-                    if (c < p) acc[c] += dval * ss[jj * SSP + c];
+                for (int c = 0; c < PP; ++c)
+                    if (c < p) acc[r][c] += dval * ss[jj * SP + c];
             }
         }
     }
+    const int rows128 = ((n + 127) / 128) * 128;
 #pragma unroll
-    for (int c = 0; c < MAXP; ++c) {
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-    }
-    if (part == 0 && blockIdx.x * 64 + rl < ((n + 127) / 128) * 128) {
-        for (int c = 0; c < p; ++c) V[(int64_t)gi * lds + c] = (gi < n) ? acc[c] : 0.0;
-    }
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < PP; ++c)
+            if (c < p) {
+                const double v = warp_sum(acc[r][c]);
+                if (lane == 0 && g0 + r < rows128) V[(int64_t)(g0 + r) * lds + c] = (g0 + r < n) ? v : 0.0;
+            }
+}
+
+template <int MODE>
+static void launch_dk_apply(const double* pts, int n, int d, const MaternParams& mp, const double* S, int p, int64_t lds,
+                            double* V, cudaStream_t s) {
+    const unsigned grid = (unsigned)((((n + 127) / 128) * 128) / DKR);
+    if (p <= 8) dk_apply_kernel<MODE, 8><<<grid, 256, 0, s>>>(pts, n, d, mp, S, p, lds, V);
+    else dk_apply_kernel<MODE, MAXP><<<grid, 256, 0, s>>>(pts, n, d, mp, S, p, lds, V);
 }
 
 // ---- Y = K X for a skinny X (n x p): 32 rows per CTA, 4 rows per warp, X tile staged in shared memory ----
@@ -242,21 +261,25 @@ symm_skinny_kernel(const double* __restrict__ K, int n, int npad, const double* 
 
 // ---- solves through the explicit triangular inverse: S = W^T (W R), W = inv(L) lower ----------------------------
 // Y = W X : like symm_skinny_kernel but only columns j <= i are read (32 rows per CTA, 4 rows per warp).
+// PP = p padded to 8 or 16 at compile time (4 x 16 accumulators were 170 registers: one CTA per SM); the CTAs take the row
+// blocks from the bottom up - the long rows first, the short ones fill the tail.
+template <int PP>
 __global__ void __launch_bounds__(256)
 tril_skinny_kernel(const double* __restrict__ W, int npad, const double* __restrict__ X, int p, double* __restrict__ Y) {
-    __shared__ double xs[128 * SSP];
+    constexpr int SP = PP + 1;
+    __shared__ double xs[128 * SP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rb = blockIdx.x * 32, r0 = rb + warp * 4;
-    double acc[4][MAXP];
+    const int rb = ((int)gridDim.x - 1 - (int)blockIdx.x) * 32, r0 = rb + warp * 4;
+    double acc[4][PP];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < MAXP; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < PP; ++c) acc[r][c] = 0.0;
     for (int j0 = 0; j0 < rb + 32; j0 += 128) {
         __syncthreads();
         for (int idx = tid; idx < 128 * p; idx += 256) {
             int r = idx / p, c = idx - r * p;
-            xs[r * SSP + c] = X[(int64_t)(j0 + r) * p + c];
+            xs[r * SP + c] = X[(int64_t)(j0 + r) * p + c];
         }
         __syncthreads();
 #pragma unroll
@@ -266,9 +289,9 @@ tril_skinny_kernel(const double* __restrict__ W, int npad, const double* __restr
 #pragma unroll
             for (int r = 0; r < 4; ++r) kv[r] = (j0 + j <= r0 + r) ? W[(int64_t)(r0 + r) * npad + j0 + j] : 0.0;
 #pragma unroll
-            for (int c = 0; c < MAXP; ++c)
+            for (int c = 0; c < PP; ++c)
                 if (c < p) {
-                    double x = xs[j * SSP + c];
+                    double x = xs[j * SP + c];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[r][c] += kv[r] * x;
                 }
@@ -277,7 +300,7 @@ tril_skinny_kernel(const double* __restrict__ W, int npad, const double* __restr
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < MAXP; ++c)
+        for (int c = 0; c < PP; ++c)
             if (c < p) {
                 double v = warp_sum(acc[r][c]);
                 if (lane == 0) Y[(int64_t)(r0 + r) * p + c] = v;
@@ -286,24 +309,26 @@ tril_skinny_kernel(const double* __restrict__ W, int npad, const double* __restr
 
 // partial[kc][i][c] = sum_{k in chunk kc, k >= i} W[k][i] X[k][c]; 128 columns i per CTA, 1024-row k chunks
 constexpr int TCH = 1024;
+template <int PP>
 __global__ void __launch_bounds__(256)
 trilT_skinny_partial_kernel(const double* __restrict__ W, int npad, const double* __restrict__ X, int p, double* __restrict__ partial) {
-    __shared__ double xs[128 * SSP];
-    __shared__ double comb[128 * SSP];
+    constexpr int SP = PP + 1;
+    __shared__ double xs[128 * SP];
+    __shared__ double comb[128 * SP];
     const int tid = threadIdx.x;
     const int i0 = blockIdx.x * 128, kc = blockIdx.y;
     const int il = tid & 127, half = tid >> 7, i = i0 + il;
     int kbeg = kc * TCH, kend = min(npad, kbeg + TCH);
-    double acc[MAXP];
+    double acc[PP];
 #pragma unroll
-    for (int c = 0; c < MAXP; ++c) acc[c] = 0.0;
+    for (int c = 0; c < PP; ++c) acc[c] = 0.0;
     if (kend > i0) {   // uniform per CTA
         if (kbeg < i0) kbeg = i0;
         for (int k0 = kbeg; k0 < kend; k0 += 128) {
             __syncthreads();
             for (int idx = tid; idx < 128 * p; idx += 256) {
                 int r = idx / p, c = idx - r * p;
-                xs[r * SSP + c] = X[(int64_t)(k0 + r) * p + c];
+                xs[r * SP + c] = X[(int64_t)(k0 + r) * p + c];
             }
             __syncthreads();
 #pragma unroll 4
@@ -311,18 +336,18 @@ trilT_skinny_partial_kernel(const double* __restrict__ W, int npad, const double
                 int k = k0 + kk;
                 double w = (k >= i) ? W[(int64_t)k * npad + i] : 0.0;
 #pragma unroll
-                for (int c = 0; c < MAXP; ++c)
-                    if (c < p) acc[c] += w * xs[kk * SSP + c];
+                for (int c = 0; c < PP; ++c)
+                    if (c < p) acc[c] += w * xs[kk * SP + c];
             }
         }
     }
     __syncthreads();
     if (half == 1)
 #pragma unroll
-        for (int c = 0; c < MAXP; ++c) comb[il * SSP + c] = acc[c];
+        for (int c = 0; c < PP; ++c) comb[il * SP + c] = acc[c];
     __syncthreads();
     if (half == 0)
-        for (int c = 0; c < p; ++c) partial[((int64_t)kc * npad + i) * p + c] = acc[c] + comb[il * SSP + c];
+        for (int c = 0; c < p; ++c) partial[((int64_t)kc * npad + i) * p + c] = acc[c] + comb[il * SP + c];
 }
 
 __global__ void trilT_reduce_kernel(const double* __restrict__ partial, int npad, int p, int nchunks, double* __restrict__ Y) {
@@ -411,8 +436,13 @@ static int gram(const double* A, const double* B, int nrows, int p, int64_t ld, 
 // S := W^T (W S) in place (S: npad x p), tmp: npad x p
 static int solve_with_inverse(const double* W, int npad, double* S, double* tmp, int p, double* tpart, cudaStream_t s) {
     int nchunks = (npad + TCH - 1) / TCH;
-    tril_skinny_kernel<<<npad / 32, 256, 0, s>>>(W, npad, S, p, tmp);
-    trilT_skinny_partial_kernel<<<dim3(npad / 128, nchunks), 256, 0, s>>>(W, npad, tmp, p, tpart);
+    if (p <= 8) {
+        tril_skinny_kernel<8><<<npad / 32, 256, 0, s>>>(W, npad, S, p, tmp);
+        trilT_skinny_partial_kernel<8><<<dim3(npad / 128, nchunks), 256, 0, s>>>(W, npad, tmp, p, tpart);
+    } else {
+        tril_skinny_kernel<MAXP><<<npad / 32, 256, 0, s>>>(W, npad, S, p, tmp);
+        trilT_skinny_partial_kernel<MAXP><<<dim3(npad / 128, nchunks), 256, 0, s>>>(W, npad, tmp, p, tpart);
+    }
     trilT_reduce_kernel<<<(unsigned)(((int64_t)npad * p + 255) / 256), 256, 0, s>>>(tpart, npad, p, nchunks, S);
     GP_COUNT(3);
     GP_LAUNCH_CHECK();
@@ -425,7 +455,7 @@ static int grad_reductions(const double* Ainv, int n, int npad, const double* pt
     int T = npad / 128, tiles = T * (T + 1) / 2;
     if (with_dk) {
         trace_tiles_kernel<MODE, true><<<tiles, 256, 0, s>>>(Ainv, n, npad, pts, d, mp, w.tr);
-        dk_apply_kernel<MODE><<<(n + 63) / 64, 256, 0, s>>>(pts, n, d, mp, w.S, p, p, w.V);
+        launch_dk_apply<MODE>(pts, n, d, mp, w.S, p, p, w.V, s);
         GP_COUNT(2);
         GP_LAUNCH_CHECK();
         return gram(w.S, w.V, n, p, p, w.gram, outQ, s);
@@ -468,13 +498,12 @@ int gp_dk_apply(const double* points, int64_t n, int64_t d, const double* scale_
         mp.sq2nu = sqrt(2.0 * nu);
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((n + 63) / 64);
     switch (mode) {
-        case MAT_05: dk_apply_kernel<MAT_05><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
-        case MAT_15: dk_apply_kernel<MAT_15><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
-        case MAT_25: dk_apply_kernel<MAT_25><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
-        case MAT_GAUSS: dk_apply_kernel<MAT_GAUSS><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
-        default: dk_apply_kernel<MAT_GENERAL><<<grid, 256, 0, s>>>(points, (int)n, (int)d, mp, S, (int)p, lds, V); break;
+        case MAT_05: launch_dk_apply<MAT_05>(points, (int)n, (int)d, mp, S, (int)p, lds, V, s); break;
+        case MAT_15: launch_dk_apply<MAT_15>(points, (int)n, (int)d, mp, S, (int)p, lds, V, s); break;
+        case MAT_25: launch_dk_apply<MAT_25>(points, (int)n, (int)d, mp, S, (int)p, lds, V, s); break;
+        case MAT_GAUSS: launch_dk_apply<MAT_GAUSS>(points, (int)n, (int)d, mp, S, (int)p, lds, V, s); break;
+        default: launch_dk_apply<MAT_GENERAL>(points, (int)n, (int)d, mp, S, (int)p, lds, V, s); break;
     }
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
