@@ -576,6 +576,8 @@ def sharded_measurements(world, rank):
             return ProfileLikelihood.find_log_likelihood_der1_zeros(zs, Xs, Km, [10.0, 1e3])
 
     try:
+        if world < 2:
+            raise RuntimeError('one slab = the single-GPU evaluation above; measured for --gpus >= 2')
         slab_eval()
         (r_slab, halo), ms_slab = _timed_max_ms(slab_eval, world)
         slab_root_find(True)
@@ -598,7 +600,7 @@ def sharded_measurements(world, rank):
             'exchange': 'halo rows: loads from the owner GPU inside the SpMM kernel (CUDA IPC mapping, NVLink); reductions: '
                         'in-kernel sum through per-rank mailboxes, 2 per Lanczos step / 3 per CG iteration'}
     except Exception as e:  # noqa: BLE001 -- the other legs must still print
-        out['C4_sparse_n1M_row_slabs'] = {'error': repr(e)[:300]}
+        out['C4_sparse_n1M_row_slabs'] = {'skipped' if world < 2 else 'error': repr(e)[:300]}
     rh, et = numpy.linspace(0.004, 0.006, 8), numpy.logspace(1, 3, 16)
     Gs, ms = _timed_max_ms(lambda: likelihood_grid(sp, zs, Xs, 0.5, rh, et, sparse=True, density=1e-3, imate_options=opts), world)
     out['C4_sparse_sweep_n1M'] = {'workload': 'configs[3] sweep: n=2^20, 8 rho x 16 eta = 128 cells, one CSR + operator per rho',
