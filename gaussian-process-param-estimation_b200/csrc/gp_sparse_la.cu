@@ -978,10 +978,13 @@ __global__ void popcount_kernel(const unsigned* __restrict__ words, int64_t nwor
 }
 
 // global operator-space column (< n) -> (owner, local row) for uniform slabs of `slab` rows (slab < 2^28, owner < 8).
-// halo_host (optional, 2 entries; synchronises the stream): [0] block-columns owned by another rank than `rank` = rows of X
-// gathered over NVLink per SpMM; [1] DISTINCT remote rows among them = the halo a bulk exchange would move.
-int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* stream) {
+// halo_host (optional, 2 entries; needs ws >= 16 + 4 * ceil(n / 32) bytes; synchronises the stream): [0] block-columns owned
+// by another rank than `rank` = rows of X gathered over NVLink per SpMM; [1] DISTINCT remote rows among them = the halo a
+// bulk exchange would move.
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* ws,
+                           void* stream) {
     if (!bidx || total < 0 || slab <= 0 || slab >= (1 << PEER_SHIFT) || rank < 0 || rank >= PEER_MAX || n <= 0) return -1;
+    if (halo_host && !ws) return -1;
     if (halo_host) halo_host[0] = halo_host[1] = 0;
     if (total == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -989,10 +992,9 @@ int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank,
     unsigned* seen = nullptr;
     const int64_t nwords = (n + 31) / 32;
     if (halo_host) {
-        GP_CUDA_CHECK(cudaMallocAsync((void**)&cnt, 2 * sizeof(unsigned long long), s));
-        GP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
-        GP_CUDA_CHECK(cudaMallocAsync((void**)&seen, nwords * sizeof(unsigned), s));
-        GP_CUDA_CHECK(cudaMemsetAsync(seen, 0, nwords * sizeof(unsigned), s));
+        cnt = (unsigned long long*)ws;
+        seen = (unsigned*)(cnt + 2);
+        GP_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16 + nwords * sizeof(unsigned), s));
     }
     encode_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bidx, total, (int)slab, (int)rank, cnt, seen);
     GP_COUNT(1);
@@ -1002,8 +1004,6 @@ int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank,
         GP_COUNT(1);
         unsigned long long h[2] = {0, 0};
         GP_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
-        GP_CUDA_CHECK(cudaFreeAsync(cnt, s));
-        GP_CUDA_CHECK(cudaFreeAsync(seen, s));
         GP_CUDA_CHECK(cudaStreamSynchronize(s));
         halo_host[0] = (int64_t)h[0];
         halo_host[1] = (int64_t)h[1];

@@ -95,7 +95,7 @@ SIGNATURES = {
     'gp_peer_barrier': (_int, [_vp, _vp]),
     'gp_peer_allreduce': (_int, [_vp, _vp, _i64, _vp]),
     'gp_peer_error': (_int, [_vp, _vp]),
-    'gp_slab_encode_columns': (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    'gp_slab_encode_columns': (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     'gp_slab_spmm': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _vp, _vp]),
     'gp_slab_col_dot': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'gp_slab_lanczos': (_int, [_vp, _vp, _vp, _vp, _i64, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

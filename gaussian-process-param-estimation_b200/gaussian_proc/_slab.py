@@ -137,6 +137,10 @@ class SlabSparseEngine(SparseEngine):
         SparseEngine.__init__(self, K, imate_method, opts, probe_range=None)
 
     # ---- operator -------------------------------------------------------------------------------------------------
+    def _halo_ws(self):
+        """scratch of the halo statistics: two counters + one bit per row of the operator"""
+        return dev.torch.empty(2 + (self.n + 63) // 64 + 1, dtype=dev.torch.int64, device='cuda')
+
     def _build_blocked(self, K, R):
         torch = dev.torch
         n, r0, r1 = self.n, self.first_row, self.last_row
@@ -146,7 +150,7 @@ class SlabSparseEngine(SparseEngine):
             total = K.bidx.numel()
             if K.encoded is None:
                 halo = (ctypes.c_int64 * 2)()
-                check(lib.gp_slab_encode_columns(_p(K.bidx), total, self.slab, self.rank, n, halo, s),
+                check(lib.gp_slab_encode_columns(_p(K.bidx), total, self.slab, self.rank, n, halo, _p(self._halo_ws()), s),
                       'gp_slab_encode_columns')
                 K.encoded = (self.slab, self.rank, int(halo[0]), int(halo[1]))
             elif K.encoded[:2] != (self.slab, self.rank):
@@ -183,7 +187,8 @@ class SlabSparseEngine(SparseEngine):
                                _p(K.ddata) if K.ddata is not None else None, _p(bptr), total, _p(bidx), _p(bvals),
                                _p(bdvals) if bdvals is not None else None, s), 'gp_bcsr_fill')
         halo = (ctypes.c_int64 * 2)()   # block-columns whose row of X lives on another rank, and the distinct rows among them
-        check(lib.gp_slab_encode_columns(_p(bidx), total, self.slab, self.rank, n, halo, s), 'gp_slab_encode_columns')
+        check(lib.gp_slab_encode_columns(_p(bidx), total, self.slab, self.rank, n, halo, _p(self._halo_ws()), s),
+              'gp_slab_encode_columns')
         self.halo_blocks, self.halo_rows, self.total_blocks = int(halo[0]), int(halo[1]), total
         self.halo_fraction = halo[0] / float(max(total, 1))
         self.R = R

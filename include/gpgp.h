@@ -273,9 +273,10 @@ int gp_peer_barrier(void* peer, void* stream);                            /* cro
 int gp_peer_allreduce(void* peer, double* values_dev, int64_t count, void* stream);   /* count <= 256, in place, rank order */
 int gp_peer_error(void* peer, void* stream);                              /* 1: a wait timed out (ranks diverged) */
 /* bidx: global operator-space column (< n) -> (owner << 28 | row within the owner's slab) for uniform slabs of `slab` rows.
- * halo_host (optional, 2 entries): [0] block-columns owned by another rank (rows gathered over NVLink per SpMM), [1] distinct
- * remote rows among them (what a bulk halo exchange would move) */
-int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* stream);
+ * halo_host (optional, 2 entries, needs ws >= 16 + 4 * ceil(n / 32) bytes): [0] block-columns owned by another rank (rows
+ * gathered over NVLink per SpMM), [1] distinct remote rows among them (what a bulk halo exchange would move) */
+int gp_slab_encode_columns(int* bidx, int64_t total, int64_t slab, int64_t rank, int64_t n, int64_t* halo_host, void* ws,
+                           void* stream);
 /* The drivers below take the 16-row blocks of this rank's rows (gp_bcsr_count / gp_bcsr_fill on order + first row) with
  * encoded columns; vectors are the rank's rows (nloc x B); alpha, beta, dots are identical on every rank. */
 int gp_slab_spmm(void* peer, const int64_t* bptr, const int* bidx, const double* bvals, int64_t nloc, double eta,
