@@ -343,3 +343,40 @@ def test_row_slab_geometry_covers_every_row_once():
             rows = numpy.array([0, n // 3, n - 1])
             owner = rows // slab
             assert all(geo[o][1] <= r < geo[o][2] for o, r in zip(owner, rows))
+
+
+def test_row_block_layout_round_trip_on_the_host():
+    """The storage of the row-blocked operator as documented (csrc/gp_sparse_la.cu bval_pos): block rb holds
+    operator rows 16 rb .. 16 rb + 15, its block-columns are padded to a multiple of 4, and value (slot, row k) sits at
+    (slot >> 2) * 64 + (k >> 3) * 32 + (k & 7) * 4 + (slot & 3). Built here by hand from a small symmetric matrix and read back
+    by DeviceRowBlocks.to_scipy (host code; CPU tensors stand in for the device arrays)."""
+    import torch
+    from gaussian_proc._sparse import DeviceRowBlocks
+    rng = numpy.random.RandomState(4)
+    n, R = 41, 16
+    A = rng.rand(n, n)
+    A = numpy.where(A + A.T > 1.5, A + A.T, 0.0)
+    A[numpy.arange(n), numpy.arange(n)] = 1.0
+    order = rng.permutation(n).astype(numpy.int32)              # operator row r is original row order[r]
+    inv = numpy.empty(n, dtype=numpy.int32)
+    inv[order] = numpy.arange(n, dtype=numpy.int32)
+    P = A[numpy.ix_(order, order)]                               # the spatially ordered matrix
+    nrb = (n + R - 1) // R
+    bptr, bidx, vals = [0], [], []
+    for rb in range(nrb):
+        rows = numpy.arange(rb * R, min(n, rb * R + R))
+        cols = numpy.nonzero(numpy.any(P[rows] != 0.0, axis=0))[0]
+        cols = rng.permutation(cols)                             # any order of the block-columns is valid
+        padded = (len(cols) + 3) // 4 * 4
+        blockvals = numpy.zeros(padded * R)
+        for slot, c in enumerate(cols):
+            for k, r in enumerate(rows):
+                blockvals[(slot >> 2) * 64 + (k >> 3) * 32 + (k & 7) * 4 + (slot & 3)] = P[r, c]
+        bidx += list(cols) + [int(cols[0])] * (padded - len(cols))
+        vals.append(blockvals)
+        bptr.append(bptr[-1] + padded)
+    K = DeviceRowBlocks(n, torch.tensor(bptr, dtype=torch.int64), torch.tensor(bidx, dtype=torch.int32),
+                        torch.from_numpy(numpy.concatenate(vals)), None, torch.from_numpy(order), torch.from_numpy(inv),
+                        int((A != 0).sum()), 0.0, 0, n)
+    S = K.to_scipy()
+    assert S.nnz == K.nnz and (S.toarray() == A).all()
