@@ -50,6 +50,7 @@ struct PeerComm {                   // one exchange, passed to the kernel by val
 };
 struct PeerVec {                    // one exchange vector as mapped on this rank: base[p] = rank p's copy (its own rows)
     const double* base[PEER_MAX];
+    int rank;                       // this rank (base[rank] is local memory)
 };
 struct PeerCtx;                     // host side (gp_peer.cu)
 PeerComm peer_next(PeerCtx* ctx);                  // the next exchange (advances the sequence number); world 1 without ctx

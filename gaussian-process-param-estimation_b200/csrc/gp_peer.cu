@@ -43,6 +43,7 @@ PeerVec peer_vec(PeerCtx* ctx, int k) {
     PeerVec pv;
     memset(&pv, 0, sizeof(pv));
     for (int p = 0; p < ctx->world; ++p) pv.base[p] = (const double*)(ctx->arena[p] + ctx->mail_bytes + (size_t)k * ctx->vec_bytes);
+    pv.rank = ctx->rank;
     return pv;
 }
 

@@ -385,8 +385,18 @@ bcsr8_spmm_dmma_kernel(const int64_t* __restrict__ bptr, const int* __restrict__
     const int xoff = ROWLOAD ? 2 * (lane & 7) : coff;
     const int xsrc = 8 * t + g;                                    // ROWLOAD: the lane that loaded this lane's fragment
     auto load_x = [&](int col, double* x) {
-        const double* xr = PEER ? pv.base[(unsigned)col >> PEER_SHIFT] + (int64_t)(col & ((1 << PEER_SHIFT) - 1)) * B + xoff
-                                : X + (int64_t)col * B + xoff;
+        const double* xr;
+        if (PEER) {
+            // Interior row blocks (almost all of them: the halo is ~1 % of the block-columns) only reference this rank's
+            // rows: one warp vote keeps them on the single-GPU addressing (X = this rank's copy); the pointer-table lookup -
+            // a dependent constant-bank load in front of every gather - is taken only by steps that touch a peer.
+            const unsigned owner = (unsigned)col >> PEER_SHIFT;
+            const int64_t local = (int64_t)(col & ((1 << PEER_SHIFT) - 1));
+            if (__any_sync(0xffffffffu, owner != (unsigned)pv.rank)) xr = pv.base[owner] + local * B + xoff;
+            else xr = X + local * B + xoff;
+        } else {
+            xr = X + (int64_t)col * B + xoff;
+        }
         if (ROWLOAD) {
             const double2 v = *reinterpret_cast<const double2*>(xr);
             x[0] = __shfl_sync(0xffffffffu, v.x, xsrc);
