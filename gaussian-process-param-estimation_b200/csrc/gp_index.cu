@@ -157,6 +157,11 @@ scan_i32_to_i64_kernel(const int* __restrict__ a, int64_t n, long long* __restri
     cta_exclusive_scan<int, long long, true>(a, n, out);
 }
 
+__global__ void __launch_bounds__(1024)
+scan_i32_to_i32_kernel(const int* __restrict__ a, int64_t n, int* __restrict__ out) {
+    cta_exclusive_scan<int, int, true>(a, n, out);
+}
+
 // out[i][:] = in[map[i]][:] (rows of B doubles)
 __global__ void gather_rows_kernel(const double* __restrict__ in, const int* __restrict__ map, int64_t n, int B, double* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,6 +240,15 @@ int gp_inverse_permutation(const int* order, int64_t n, int* inv, void* stream) 
 int gp_scan_counts(const int* counts, int64_t n, int64_t* offsets, void* stream) {
     if (!counts || !offsets || n <= 0) return -1;
     scan_i32_to_i64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, (long long*)offsets);
+    GP_COUNT(1);
+    GP_LAUNCH_CHECK();
+    return 0;
+}
+
+// the same with 32-bit offsets (CSR row pointers); the caller guarantees that the total fits
+int gp_scan_counts_i32(const int* counts, int64_t n, int* offsets, void* stream) {
+    if (!counts || !offsets || n <= 0) return -1;
+    scan_i32_to_i32_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, offsets);
     GP_COUNT(1);
     GP_LAUNCH_CHECK();
     return 0;

@@ -11,8 +11,6 @@
 #include "../../include/gpgp.h"
 #include "gp_common.cuh"
 #include "gp_matern.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <math.h>
 #include <vector>
 
@@ -183,9 +181,10 @@ __global__ void sum64_kernel(const int* __restrict__ v, int n, unsigned long lon
 
 // The points of a cell are kept in ORIGINAL index order (stable radix sort of the cell ids): the generation order of
 // every row - and with it the row-blocked operator and every estimate - is the same in every run.
-__global__ void iota_kernel(int n, int* out) {
+// cell ids as 64-bit sort keys (gp_sort_keys_u64 works on 64-bit keys)
+__global__ void widen_keys_kernel(const int* __restrict__ in, int n, unsigned long long* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = i;
+    if (i < n) out[i] = (unsigned long long)(unsigned)in[i];
 }
 
 __global__ void gather_points_kernel(const double* __restrict__ pts, int n, int d, const int* __restrict__ sorted_idx,
@@ -445,7 +444,8 @@ sort_rows_kernel(int n, const int* __restrict__ indptr, int* indices, double* da
 
 // workspace carving (all int32 / f64 device arrays)
 struct SparseWs {
-    int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow, *cell_sorted, *iota;
+    int *cell_of, *cell_start, *cell_fill, *sorted_idx, *devcount, *border_cnt, *overflow;
+    unsigned long long* keys64;
     void* sort_temp;
     size_t sort_temp_bytes;
     unsigned long long* bbox_keys;   // [8] min keys, [8] max keys, [16] total nnz
@@ -476,8 +476,7 @@ static SparseWs carve_sparse(void* ws, int64_t n, int64_t d) {
     w.ev = (double*)take(sizeof(double) * BORDER_CAP);
     w.edv = (double*)take(sizeof(double) * BORDER_CAP);
     w.sorted_pts = (double*)take(sizeof(double) * n * d);
-    w.cell_sorted = (int*)take(sizeof(int) * n);
-    w.iota = (int*)take(sizeof(int) * n);
+    w.keys64 = (unsigned long long*)take(sizeof(unsigned long long) * n);
     w.sort_temp_bytes = (size_t)n * 16 + (8u << 20);      // radix sort scratch (alternate key/value buffers + histograms)
     w.sort_temp = (void*)take(w.sort_temp_bytes);
     w.bbox_keys = (unsigned long long*)take(sizeof(unsigned long long) * 24);
@@ -669,14 +668,12 @@ static int sparse_prepare(const double* points, int64_t n, int64_t d, const doub
     {
         int bits = 1;
         while ((1 << bits) < g.ncells && bits < 31) ++bits;
-        size_t need = 0;
-        GP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, w.cell_of, w.cell_sorted, w.iota, w.sorted_idx, N, 0, bits, s));
-        if (need > w.sort_temp_bytes) return -24;
-        iota_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, w.iota);
-        GP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.sort_temp, need, w.cell_of, w.cell_sorted, w.iota, w.sorted_idx, N, 0, bits,
-                                                      s));
+        // stable radix sort of the cell ids (own kernels, csrc/gp_index.cu): the points of a cell stay in index order
+        if ((size_t)gp_sort_workspace_bytes(N) > w.sort_temp_bytes) return -24;
+        widen_keys_kernel<<<(N + 255) / 256, 256, 0, s>>>(w.cell_of, N, w.keys64);
+        if (int rc = gp_sort_keys_u64(w.keys64, N, bits, w.sorted_idx, w.sort_temp, s)) return rc;
         gather_points_kernel<<<(N + 255) / 256, 256, 0, s>>>(points, N, D, w.sorted_idx, w.sorted_pts);
-        GP_COUNT(3);
+        GP_COUNT(2);
     }
     return 0;
 }
@@ -708,11 +705,7 @@ static int sparse_count_impl(const double* points, const double* points_host, in
     if (nb == 0) {
         // the common case: no borderline pair -> the row pointer is an exclusive scan on the device
         if (total > (unsigned long long)INT32_MAX) return -22;
-        size_t need = 0;
-        GP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, w.devcount, indptr_dev, N + 1, s));
-        if (need > w.sort_temp_bytes) return -24;
-        GP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.sort_temp, need, w.devcount, indptr_dev, N + 1, s));
-        GP_COUNT(1);
+        if (int rc = gp_scan_counts_i32(w.devcount, N, indptr_dev, s)) return rc;
         int meta0[4] = {0, 0, 0, 0};
         GP_CUDA_CHECK(cudaMemcpyAsync(w.border_cnt, meta0, sizeof(int) * 4, cudaMemcpyHostToDevice, s));
         GP_CUDA_CHECK(cudaStreamSynchronize(s));

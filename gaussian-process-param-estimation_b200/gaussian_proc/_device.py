@@ -83,6 +83,7 @@ SIGNATURES = {
     'gp_sort_keys_u64': (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     'gp_inverse_permutation': (_int, [_vp, _i64, _vp, _vp]),
     'gp_scan_counts': (_int, [_vp, _i64, _vp, _vp]),
+    'gp_scan_counts_i32': (_int, [_vp, _i64, _vp, _vp]),
     'gp_gather_rows': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     'gp_matern_blocks_count': (_int, [_vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'gp_matern_blocks_fill': (_int, [_vp, _i64, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -302,6 +302,7 @@ int gp_sort_keys_u64(unsigned long long* keys_dev, int64_t n, int key_bits, int*
 int gp_inverse_permutation(const int* order, int64_t n, int* inv, void* stream);
 /* offsets[0] = 0, offsets[i + 1] = counts[0] + ... + counts[i] */
 int gp_scan_counts(const int* counts, int64_t n, int64_t* offsets, void* stream);
+int gp_scan_counts_i32(const int* counts, int64_t n, int* offsets, void* stream);     /* 32-bit offsets (CSR row pointers) */
 /* out[i][:] = in[map[i]][:] for rows of B doubles (in != out) */
 int gp_gather_rows(const double* in, const int* map, int64_t n, int64_t B, double* out, void* stream);
 
